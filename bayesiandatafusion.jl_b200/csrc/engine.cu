@@ -1,0 +1,708 @@
+// libbdf_b200.so — C ABI (include/bdf_b200.h) over the sm_100a kernels. No CPU fallback: every numeric entry
+// launches device kernels; host code only validates arguments, moves buffers and builds launch metadata.
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <numeric>
+
+#include "../../include/bdf_b200.h"
+#include "nw_kernels.cuh"
+
+using namespace bdf;
+
+static thread_local std::string g_create_err;
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+      return BDF_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+#define FAIL(code, msg)  \
+  do {                   \
+    h->err = (msg);      \
+    return (code);       \
+  } while (0)
+#define CHECK_H()  \
+  if (!h) return BDF_ERR_INVALID
+#define CHECK_ENT(e) \
+  if ((e) < 0 || (e) >= (int)h->ents.size()) FAIL(BDF_ERR_INVALID, "entity id out of range")
+
+// ---- kernel dispatch over the padded latent dimension (instances live in row_inst.cu, one object per DP) ----------
+#define DP_CASES(X) X(8) X(16) X(24) X(32) X(40) X(48) X(56) X(64) X(72) X(80) X(88) X(96) X(104) X(112) X(120) X(128)
+#define X(dp)                                                                                           \
+  int bdf_launch_rows_##dp(bdf_t* h, const RowParams& p, int n_items, bool tensor);                     \
+  int bdf_launch_stats_##dp(bdf_t* h, const double* U, const double* uhat, int64_t slot0, int64_t nrows);     \
+  int64_t bdf_pst_##dp();
+DP_CASES(X)
+#undef X
+
+
+namespace {
+
+template <class T>
+int dev_alloc(bdf_t* h, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CU(cudaMalloc((void**)p, n * sizeof(T)));
+  return BDF_OK;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int launch_rows(bdf_t* h, const RowParams& p, int n_items, bool tensor) {
+  switch (h->DP) {
+#define X(dp) \
+  case dp:    \
+    return bdf_launch_rows_##dp(h, p, n_items, tensor);
+    DP_CASES(X)
+#undef X
+  }
+  FAIL(BDF_ERR_INVALID, "unsupported num_latent");
+}
+
+int launch_stats_partials(bdf_t* h, const double* U, const double* uhat, int64_t slot0, int64_t nrows) {
+  switch (h->DP) {
+#define X(dp) \
+  case dp:    \
+    return bdf_launch_stats_##dp(h, U, uhat, slot0, nrows);
+    DP_CASES(X)
+#undef X
+  }
+  FAIL(BDF_ERR_INVALID, "unsupported num_latent");
+}
+
+int64_t pst_of(int DP) {
+  switch (DP) {
+#define X(dp) \
+  case dp:    \
+    return bdf_pst_##dp();
+    DP_CASES(X)
+#undef X
+  }
+  return 0;
+}
+
+// ---- ingestion kernels ---------------------------------------------------------------------------------------
+// slot of 0-based global row i: rows are dealt cyclically to ranks (src/sampling.jl:154), each rank's rows contiguous
+__host__ __device__ inline int64_t slot_of(int64_t i, int world, int64_t nper) { return (i % world) * nper + i / world; }
+
+__global__ void make_keys_kernel(const int64_t* ids, int64_t nnz, int64_t N, int world, int64_t nper, uint32_t* keys, uint32_t* idx,
+                                 int* bad) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nnz; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = ids[o];
+    if (id < 1 || id > N) {
+      *bad = 1;
+      keys[o] = 0;
+    } else {
+      keys[o] = (uint32_t)slot_of(id - 1, world, nper);
+    }
+    idx[o] = (uint32_t)o;
+  }
+}
+
+__global__ void count_rows_kernel(const uint32_t* keys, int64_t nnz, int64_t slot0, int64_t nrows, unsigned long long* counts) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nnz; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = (int64_t)keys[o] - slot0;
+    if (r >= 0 && r < nrows) atomicAdd(counts + r, 1ULL);
+  }
+}
+
+__global__ void lower_bound_kernel(const uint32_t* keys, int64_t nnz, uint32_t target, int64_t* out) {
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  *out = lo;
+}
+
+__global__ void gather_obs_kernel(const uint32_t* perm, int64_t base, int64_t n, const int64_t* ids_other, int world, int64_t nper_other,
+                                  int32_t* col) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
+    col[o] = (int32_t)slot_of(ids_other[perm[base + o]] - 1, world, nper_other);
+}
+
+__global__ void gather_val_kernel(const uint32_t* perm, int64_t base, int64_t n, const double* vals, double* out) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) out[o] = vals[perm[base + o]];
+}
+
+__global__ void ids_to_slots_kernel(const int64_t* ids, int64_t n, int64_t N, int world, int64_t nper, int32_t* out, int* bad) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = ids[o];
+    if (id < 1 || id > N) { *bad = 1; out[o] = 0; } else out[o] = (int32_t)slot_of(id - 1, world, nper);
+  }
+}
+
+__global__ void set_identity_kernel(double* A, int D, double v) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D * D; e += gridDim.x * blockDim.x) A[e] = (e % D == e / D) ? v : 0.0;
+}
+
+inline int grid_for(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// host↔device copies between Julia's D×N column-major matrix and the slot-major, ld-pitched device buffer
+int copy_rows_h2d(bdf_t* h, const EntityS& e, const double* host, double* dev) {
+  const int D = h->D, W = h->world;
+  for (int r = 0; r < W; r++) {
+    const int64_t cnt = (e.N - r + W - 1) / W;  // rows r, r+W, ...
+    if (cnt <= 0) continue;
+    CU(cudaMemcpy2DAsync(dev + (size_t)r * e.Nper * h->ld, sizeof(double) * h->ld, host + (size_t)r * D, sizeof(double) * D * W,
+                         sizeof(double) * D, (size_t)cnt, cudaMemcpyHostToDevice, h->stream));
+  }
+  return BDF_OK;
+}
+int copy_rows_d2h(bdf_t* h, const EntityS& e, const double* dev, double* host) {
+  const int D = h->D, W = h->world;
+  for (int r = 0; r < W; r++) {
+    const int64_t cnt = (e.N - r + W - 1) / W;
+    if (cnt <= 0) continue;
+    CU(cudaMemcpy2DAsync(host + (size_t)r * D, sizeof(double) * D * W, dev + (size_t)r * e.Nper * h->ld, sizeof(double) * h->ld,
+                         sizeof(double) * D, (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+  }
+  return BDF_OK;
+}
+
+int check_err_flag(bdf_t* h) {
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (flag) {
+    CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+    FAIL(BDF_ERR_NUMERIC, flag & 1 ? "row draw: precision matrix not positive definite" : "Normal-Wishart draw: matrix not positive definite");
+  }
+  return BDF_OK;
+}
+
+int ensure_ws(bdf_t* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return BDF_OK;
+  if (h->ws) {
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(h->ws));
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+  }
+  CU(cudaMalloc((void**)&h->ws, bytes));
+  h->ws_bytes = bytes;
+  return BDF_OK;
+}
+
+// Split heavy rows into chunks, order work items by cost (heaviest first) and upload the list.
+int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr, int64_t real_rows) {
+  const int64_t CH = 8192;  // observations per chunk of a split row (multiple of every KS)
+  std::vector<int32_t> irow, ilen, isplit, ichunk, snch;
+  std::vector<int64_t> ibeg, swoff;
+  int64_t slots = 0;
+  for (int64_t r = 0; r < real_rows; r++) {
+    const int64_t b = row_ptr[r], n = row_ptr[r + 1] - b;
+    if (n <= CH + CH / 2) {
+      irow.push_back((int32_t)r); ibeg.push_back(b); ilen.push_back((int32_t)n); isplit.push_back(-1); ichunk.push_back(0);
+    } else {
+      const int64_t nch = (n + CH - 1) / CH;
+      const int sid = (int)snch.size();
+      snch.push_back((int32_t)nch);
+      swoff.push_back(slots);
+      slots += nch;
+      for (int64_t c = 0; c < nch; c++) {
+        const int64_t cb = b + c * CH, ce = std::min(b + n, cb + CH);
+        irow.push_back((int32_t)r); ibeg.push_back(cb); ilen.push_back((int32_t)(ce - cb)); isplit.push_back(sid); ichunk.push_back((int32_t)c);
+      }
+    }
+  }
+  const size_t ni = irow.size();
+  std::vector<int32_t> order(ni);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ilen[a] > ilen[b]; });
+  auto permute32 = [&](std::vector<int32_t>& v) { std::vector<int32_t> t(ni); for (size_t i = 0; i < ni; i++) t[i] = v[order[i]]; v.swap(t); };
+  auto permute64 = [&](std::vector<int64_t>& v) { std::vector<int64_t> t(ni); for (size_t i = 0; i < ni; i++) t[i] = v[order[i]]; v.swap(t); };
+  permute32(irow); permute32(ilen); permute32(isplit); permute32(ichunk); permute64(ibeg);
+  mi.n_items = (int)ni;
+  mi.n_split = (int)snch.size();
+  mi.ws_slots = slots;
+  int rc;
+  if ((rc = dev_alloc(h, &mi.item_row, ni))) return rc;
+  if ((rc = dev_alloc(h, &mi.item_beg, ni))) return rc;
+  if ((rc = dev_alloc(h, &mi.item_len, ni))) return rc;
+  if ((rc = dev_alloc(h, &mi.item_split, ni))) return rc;
+  if ((rc = dev_alloc(h, &mi.item_chunk, ni))) return rc;
+  if ((rc = dev_alloc(h, &mi.split_nchunks, snch.size()))) return rc;
+  if ((rc = dev_alloc(h, &mi.split_wsoff, snch.size()))) return rc;
+  if ((rc = dev_alloc(h, &mi.split_counter, snch.size()))) return rc;
+  if (ni) {
+    CU(cudaMemcpyAsync(mi.item_row, irow.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.item_beg, ibeg.data(), ni * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.item_len, ilen.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.item_split, isplit.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.item_chunk, ichunk.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!snch.empty()) {
+    CU(cudaMemcpyAsync(mi.split_nchunks, snch.data(), snch.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.split_wsoff, swoff.data(), swoff.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(cudaMemsetAsync(mi.split_counter, 0, std::max<size_t>(1, snch.size()) * sizeof(int), h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // host vectors die here
+  return ensure_ws(h, std::max<size_t>(sizeof(double) * (size_t)slots * h->pst, sizeof(double) * 296 * (size_t)tri(h->D + 1)));
+}
+
+int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev) {
+  EntityS& e = h->ents[entity];
+  if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
+  if (e.uses.size() > 1) FAIL(BDF_ERR_INVALID, "entities in several relations are not supported yet (SURVEY §8f N4)");
+  RelationS& rel = h->rels[e.uses[0].first];
+  const int mode = e.uses[0].second;
+  ModeIndex& mi = rel.modes[mode];
+  RowParams p{};
+  p.item_row = mi.item_row; p.item_beg = mi.item_beg; p.item_len = mi.item_len; p.item_split = mi.item_split; p.item_chunk = mi.item_chunk;
+  p.split_nchunks = mi.split_nchunks; p.split_wsoff = mi.split_wsoff; p.split_counter = mi.split_counter; p.ws = h->ws;
+  p.col0 = mi.col[0]; p.col1 = mi.col[1]; p.val = mi.val;
+  p.P0 = h->ents[mi.other_entity[0]].U;
+  p.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr;
+  p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper;
+  p.Lambda = Lambda_dev; p.mu = mu_dev; p.mu_ld = mu_ld; p.Z = Z_dev;
+  p.alpha = rel.alpha; p.mean = rel.mean; p.D = h->D; p.rank = h->rank; p.world = h->world;
+  p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag;
+  return launch_rows(h, p, mi.n_items, rel.K > 2);
+}
+
+int stats_entity(bdf_t* h, int entity) {
+  EntityS& e = h->ents[entity];
+  const int nblk = launch_stats_partials(h, e.U, nullptr, (int64_t)h->rank * e.Nper, e.nlocal);
+  if (nblk < 0) return nblk;
+  stats_reduce_kernel<<<8, 256, 0, h->stream>>>(h->ws, nblk, h->D, (double)e.nlocal, e.stats);
+  h->launches++;
+  CU(cudaGetLastError());
+  return BDF_OK;
+}
+
+int draw_entity(bdf_t* h, int entity, const double* mu0_dev, double b0, const double* Tinv_dev, double nu, const double* A_dev,
+                const double* z_dev) {
+  EntityS& e = h->ents[entity];
+  NWDrawParams p{};
+  p.D = h->D; p.stats = e.stats; p.mu0 = mu0_dev; p.Tinv = Tinv_dev; p.b0 = b0; p.nu = nu; p.A_inj = A_dev; p.z_inj = z_dev;
+  p.seed = h->seed; p.sweep = h->sweep; p.stream = 0x100u + 8u * (uint32_t)entity; p.scratch = h->scratch;
+  p.mu_out = e.mu; p.Lam_out = e.Lambda; p.err_flag = h->err_flag;
+  nw_draw_kernel<<<1, 256, 0, h->stream>>>(p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return BDF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+int bdf_version(void) { return 100; }
+
+const char* bdf_last_error(const bdf_t* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
+  if (!out) return BDF_ERR_INVALID;
+  *out = nullptr;
+  if (num_latent < 1 || num_latent > 128) { g_create_err = "num_latent must be in 1..128"; return BDF_ERR_INVALID; }
+  if (world < 1 || rank < 0 || rank >= world) { g_create_err = "need 0 <= rank < world"; return BDF_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) { g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(ce); return BDF_ERR_CUDA; }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return BDF_ERR_INVALID; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { g_create_err = "libbdf_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor); return BDF_ERR_CUDA; }
+  bdf_t* h = new bdf_t();
+  h->device = device; h->D = num_latent; h->rank = rank; h->world = world;
+  h->ld = round_up(num_latent, 4);
+  h->DP = (num_latent % 8 == 0) ? num_latent : round_up(num_latent, 8);
+  h->NW = h->DP <= 32 ? 1 : (h->DP <= 64 ? 4 : 8);
+  h->pst = pst_of(h->DP);
+  auto bail = [&](cudaError_t e, const char* what) { g_create_err = std::string(what) + ": " + cudaGetErrorString(e); delete h; return BDF_ERR_CUDA; };
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce, "cudaSetDevice");
+  if ((ce = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
+  h->stream = h->own_stream;
+  if ((ce = cudaMalloc((void**)&h->err_flag, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  cudaMemset(h->err_flag, 0, sizeof(int));
+  if ((ce = cudaMalloc((void**)&h->scratch, sizeof(double) * ((size_t)4 * num_latent * num_latent + 4 * num_latent))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  h->ws_bytes = sizeof(double) * 296 * (size_t)tri(num_latent + 1);
+  if ((ce = cudaMalloc((void**)&h->ws, h->ws_bytes)) != cudaSuccess) return bail(ce, "cudaMalloc");
+  *out = h;
+  return BDF_OK;
+}
+
+int bdf_destroy(bdf_t* h) {
+  if (!h) return BDF_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& e : h->ents) {
+    cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
+  }
+  for (auto& r : h->rels)
+    for (int m = 0; m < r.K; m++) {
+      ModeIndex& mi = r.modes[m];
+      cudaFree(mi.row_ptr); cudaFree(mi.col[0]); cudaFree(mi.col[1]); cudaFree(mi.val);
+      cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk);
+      cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
+    }
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return BDF_OK;
+}
+
+int bdf_set_stream(bdf_t* h, void* s) {
+  CHECK_H();
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return BDF_OK;
+}
+
+int bdf_set_seed(bdf_t* h, uint64_t seed) { CHECK_H(); h->seed = seed; return BDF_OK; }
+int64_t bdf_sweep_counter(const bdf_t* h) { return h ? (int64_t)h->sweep : -1; }
+int64_t bdf_launch_count(const bdf_t* h) { return h ? h->launches : -1; }
+int bdf_synchronize(bdf_t* h) { CHECK_H(); CU(cudaSetDevice(h->device)); CU(cudaStreamSynchronize(h->stream)); return BDF_OK; }
+
+int bdf_add_entity(bdf_t* h, int64_t count) {
+  CHECK_H();
+  if (count < 1 || count > 2000000000LL) FAIL(BDF_ERR_INVALID, "entity count must be in 1..2e9");
+  CU(cudaSetDevice(h->device));
+  EntityS e;
+  e.N = count;
+  e.Nper = (count + h->world - 1) / h->world;
+  e.nlocal = (count - h->rank + h->world - 1) / h->world;
+  if (e.nlocal < 0) e.nlocal = 0;
+  const int D = h->D;
+  const size_t un = (size_t)e.Nper * h->world * h->ld;
+  int rc;
+  if ((rc = dev_alloc(h, &e.U, un))) return rc;
+  if ((rc = dev_alloc(h, &e.mu, (size_t)D))) return rc;
+  if ((rc = dev_alloc(h, &e.Lambda, (size_t)D * D))) return rc;
+  if ((rc = dev_alloc(h, &e.stats, (size_t)1 + D + (size_t)D * D))) return rc;
+  if ((rc = dev_alloc(h, &e.hyper, (size_t)D + (size_t)D * D))) return rc;
+  // initModel! — src/RelationData.jl:66-90
+  CU(cudaMemsetAsync(e.U, 0, un * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(e.mu, 0, D * sizeof(double), h->stream));
+  set_identity_kernel<<<grid_for(D * D), 256, 0, h->stream>>>(e.Lambda, D, 5.0);
+  CU(cudaMemsetAsync(e.hyper, 0, D * sizeof(double), h->stream));
+  set_identity_kernel<<<grid_for(D * D), 256, 0, h->stream>>>(e.hyper + D, D, 1.0);
+  CU(cudaGetLastError());
+  e.mu0.assign(D, 0.0);
+  e.WI.assign((size_t)D * D, 0.0);
+  for (int i = 0; i < D; i++) e.WI[i + (size_t)i * D] = 1.0;
+  e.b0 = 2.0;
+  e.nu0 = D;
+  h->ents.push_back(e);
+  return (int)h->ents.size() - 1;
+}
+
+int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, const int64_t* ids, const double* vals) {
+  CHECK_H();
+  if (K < 2 || K > 3) FAIL(BDF_ERR_INVALID, "relations with 2 or 3 modes are supported");
+  if (nnz < 0 || nnz >= 2147483647LL) FAIL(BDF_ERR_INVALID, "nnz must be < 2^31");
+  if (!entity_of_mode || (nnz > 0 && (!ids || !vals))) FAIL(BDF_ERR_INVALID, "null argument");
+  for (int m = 0; m < K; m++) {
+    CHECK_ENT(entity_of_mode[m]);
+    for (int m2 = 0; m2 < m; m2++)
+      if (entity_of_mode[m] == entity_of_mode[m2]) FAIL(BDF_ERR_INVALID, "an entity may appear once per relation");
+  }
+  CU(cudaSetDevice(h->device));
+  RelationS rel;
+  rel.K = K; rel.nnz = nnz;
+  for (int m = 0; m < K; m++) rel.entity_of_mode[m] = entity_of_mode[m];
+  // staging copies of the table
+  int64_t* d_ids = nullptr; double* d_vals = nullptr; uint32_t *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *idx2 = nullptr;
+  int* d_bad = nullptr; int64_t* d_lb = nullptr; unsigned long long* d_cnt = nullptr; void* d_tmp = nullptr;
+  int rc = BDF_OK;
+  auto cleanup = [&]() { cudaFree(d_ids); cudaFree(d_vals); cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(idx2); cudaFree(d_bad); cudaFree(d_lb); cudaFree(d_cnt); cudaFree(d_tmp); };
+#define TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return BDF_ERR_CUDA; } } while (0)
+  const size_t n1 = std::max<int64_t>(nnz, 1);
+  TRY(dev_alloc(h, &d_ids, n1 * K)); TRY(dev_alloc(h, &d_vals, n1));
+  TRY(dev_alloc(h, &keys, n1)); TRY(dev_alloc(h, &keys2, n1)); TRY(dev_alloc(h, &idx, n1)); TRY(dev_alloc(h, &idx2, n1));
+  TRY(dev_alloc(h, &d_bad, 1)); TRY(dev_alloc(h, &d_lb, 2));
+  CUT(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+  if (nnz) {
+    CUT(cudaMemcpyAsync(d_ids, ids, sizeof(int64_t) * nnz * K, cudaMemcpyHostToDevice, h->stream));
+    CUT(cudaMemcpyAsync(d_vals, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->stream));
+  }
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, (int)n1, 0, 32, h->stream);
+  size_t scan_bytes = 0;
+  int64_t max_rows = 0;
+  for (int m = 0; m < K; m++) max_rows = std::max(max_rows, h->ents[entity_of_mode[m]].Nper);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned long long*)nullptr, (int64_t*)nullptr, (int)(max_rows + 1), h->stream);
+  tmp_bytes = std::max(tmp_bytes, scan_bytes);
+  CUT(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+  TRY(dev_alloc(h, &d_cnt, (size_t)max_rows + 1));
+
+  for (int m = 0; m < K; m++) {
+    EntityS& e = h->ents[entity_of_mode[m]];
+    ModeIndex& mi = rel.modes[m];
+    mi.nrows = e.Nper;
+    const int64_t slot0 = (int64_t)h->rank * e.Nper;
+    int bits = 1;
+    while ((1LL << bits) < e.Nper * h->world) bits++;
+    make_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(d_ids + (size_t)m * nnz, nnz, e.N, h->world, e.Nper, keys, idx, d_bad);
+    CUT(cudaGetLastError());
+    if (nnz) CUT(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys, keys2, idx, idx2, (int)nnz, 0, bits, h->stream));  // stable: table order kept
+    // local segment of the sorted table
+    lower_bound_kernel<<<1, 1, 0, h->stream>>>(keys2, nnz, (uint32_t)slot0, d_lb);
+    lower_bound_kernel<<<1, 1, 0, h->stream>>>(keys2, nnz, (uint32_t)(slot0 + e.Nper), d_lb + 1);
+    CUT(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (e.Nper + 1), h->stream));
+    count_rows_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(keys2, nnz, slot0, e.Nper, d_cnt);
+    CUT(cudaGetLastError());
+    TRY(dev_alloc(h, &mi.row_ptr, (size_t)e.Nper + 1));
+    CUT(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, mi.row_ptr, (int)(e.Nper + 1), h->stream));
+    int64_t lb[2] = {0, 0};
+    int bad = 0;
+    CUT(cudaMemcpyAsync(lb, d_lb, sizeof(lb), cudaMemcpyDeviceToHost, h->stream));
+    CUT(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUT(cudaStreamSynchronize(h->stream));
+    if (bad) { h->err = "relation id outside 1..count of its entity"; cleanup(); return BDF_ERR_INVALID; }
+    mi.nnz = lb[1] - lb[0];
+    int no = 0;
+    for (int m2 = 0; m2 < K; m2++) {
+      if (m2 == m) continue;
+      EntityS& eo = h->ents[entity_of_mode[m2]];
+      mi.other_entity[no] = entity_of_mode[m2];
+      TRY(dev_alloc(h, &mi.col[no], (size_t)std::max<int64_t>(mi.nnz, 1)));
+      gather_obs_kernel<<<grid_for(mi.nnz), 256, 0, h->stream>>>(idx2, lb[0], mi.nnz, d_ids + (size_t)m2 * nnz, h->world, eo.Nper, mi.col[no]);
+      CUT(cudaGetLastError());
+      no++;
+    }
+    TRY(dev_alloc(h, &mi.val, (size_t)std::max<int64_t>(mi.nnz, 1)));
+    gather_val_kernel<<<grid_for(mi.nnz), 256, 0, h->stream>>>(idx2, lb[0], mi.nnz, d_vals, mi.val);
+    CUT(cudaGetLastError());
+    std::vector<int64_t> rp((size_t)e.Nper + 1);
+    CUT(cudaMemcpyAsync(rp.data(), mi.row_ptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUT(cudaStreamSynchronize(h->stream));
+    TRY(build_work_list(h, mi, rp, e.nlocal));
+  }
+  CUT(cudaStreamSynchronize(h->stream));
+  cleanup();
+#undef TRY
+#undef CUT
+  h->rels.push_back(rel);
+  const int rid = (int)h->rels.size() - 1;
+  for (int m = 0; m < K; m++) h->ents[entity_of_mode[m]].uses.push_back({rid, m});
+  return rid;
+}
+
+int bdf_set_relation_params(bdf_t* h, int rel, double alpha, double mean_value) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  if (!(alpha > 0.0)) FAIL(BDF_ERR_INVALID, "alpha must be positive");
+  h->rels[rel].alpha = alpha;
+  h->rels[rel].mean = mean_value;
+  return BDF_OK;
+}
+
+int bdf_set_factors(bdf_t* h, int entity, const double* U) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!U) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  CU(cudaMemsetAsync(e.U, 0, sizeof(double) * (size_t)e.Nper * h->world * h->ld, h->stream));
+  int rc = copy_rows_h2d(h, e, U, e.U);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+int bdf_get_factors(bdf_t* h, int entity, double* U) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!U) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = copy_rows_d2h(h, h->ents[entity], h->ents[entity].U, U);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+int bdf_factors_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* nper, int64_t* ld) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (dev_ptr) *dev_ptr = h->ents[entity].U;
+  if (nper) *nper = h->ents[entity].Nper;
+  if (ld) *ld = h->ld;
+  return BDF_OK;
+}
+
+int bdf_stats_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* count) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (dev_ptr) *dev_ptr = h->ents[entity].stats;
+  if (count) *count = 1 + h->D + (int64_t)h->D * h->D;
+  return BDF_OK;
+}
+
+int bdf_sample_mode(bdf_t* h, int entity, const double* mu, int64_t mu_ld, const double* Lambda, const double* z) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!mu || !Lambda) FAIL(BDF_ERR_INVALID, "null argument");
+  if (mu_ld != 0 && mu_ld != h->D) FAIL(BDF_ERR_INVALID, "mu_ld must be 0 (vector) or num_latent (D×N matrix)");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const int D = h->D;
+  const size_t un = (size_t)e.Nper * h->world * h->ld;
+  int rc;
+  CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * D * D, cudaMemcpyHostToDevice, h->stream));
+  const double* mu_dev = e.mu;
+  int64_t mu_pitch = 0;
+  if (mu_ld == 0) {
+    CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    if (!e.mu_rows) { if ((rc = dev_alloc(h, &e.mu_rows, un))) return rc; CU(cudaMemsetAsync(e.mu_rows, 0, un * sizeof(double), h->stream)); }
+    if ((rc = copy_rows_h2d(h, e, mu, e.mu_rows))) return rc;
+    mu_dev = e.mu_rows;
+    mu_pitch = h->ld;
+  }
+  const double* z_dev = nullptr;
+  if (z) {
+    if (!e.Z) { if ((rc = dev_alloc(h, &e.Z, un))) return rc; CU(cudaMemsetAsync(e.Z, 0, un * sizeof(double), h->stream)); }
+    if ((rc = copy_rows_h2d(h, e, z, e.Z))) return rc;
+    z_dev = e.Z;
+  }
+  if ((rc = sample_entity(h, entity, mu_dev, mu_pitch, e.Lambda, z_dev))) return rc;
+  return check_err_flag(h);
+}
+
+int bdf_nw_stats(bdf_t* h, int entity, double* N, double* NU, double* NS) {
+  CHECK_H(); CHECK_ENT(entity);
+  CU(cudaSetDevice(h->device));
+  int rc = stats_entity(h, entity);
+  if (rc) return rc;
+  const int D = h->D;
+  std::vector<double> buf((size_t)1 + D + (size_t)D * D);
+  CU(cudaMemcpyAsync(buf.data(), h->ents[entity].stats, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (N) *N = buf[0];
+  if (NU) memcpy(NU, buf.data() + 1, sizeof(double) * D);
+  if (NS) memcpy(NS, buf.data() + 1 + D, sizeof(double) * D * D);
+  return BDF_OK;
+}
+
+int bdf_nw_sample(bdf_t* h, int entity, const double* mu0, double b0, const double* Tinv, double nu, const double* bartlettA,
+                  const double* z, double* mu_out, double* Lambda_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!mu0 || !Tinv) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const int D = h->D;
+  const size_t dd = (size_t)D * D;
+  CU(cudaMemcpyAsync(e.hyper, mu0, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(e.hyper + D, Tinv, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
+  double* A_dev = nullptr; double* z_dev = nullptr; double* stage = nullptr;
+  if (bartlettA || z) {
+    CU(cudaMalloc((void**)&stage, sizeof(double) * (dd + D)));
+    if (bartlettA) { A_dev = stage; CU(cudaMemcpyAsync(A_dev, bartlettA, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream)); }
+    if (z) { z_dev = stage + dd; CU(cudaMemcpyAsync(z_dev, z, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream)); }
+  }
+  int rc = draw_entity(h, entity, e.hyper, b0, e.hyper + D, nu, A_dev, z_dev);
+  if (!rc && mu_out) { cudaError_t ce = cudaMemcpyAsync(mu_out, e.mu, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream); if (ce != cudaSuccess) rc = BDF_ERR_CUDA; }
+  if (!rc && Lambda_out) { cudaError_t ce = cudaMemcpyAsync(Lambda_out, e.Lambda, sizeof(double) * dd, cudaMemcpyDeviceToHost, h->stream); if (ce != cudaSuccess) rc = BDF_ERR_CUDA; }
+  if (!rc) rc = check_err_flag(h); else cudaStreamSynchronize(h->stream);
+  if (stage) cudaFree(stage);
+  return rc;
+}
+
+int bdf_step_sample(bdf_t* h, int entity) {
+  CHECK_H(); CHECK_ENT(entity);
+  EntityS& e = h->ents[entity];
+  return sample_entity(h, entity, e.mu, 0, e.Lambda, nullptr);
+}
+int bdf_step_nw_stats(bdf_t* h, int entity) { CHECK_H(); CHECK_ENT(entity); return stats_entity(h, entity); }
+int bdf_step_nw_draw(bdf_t* h, int entity) {
+  CHECK_H(); CHECK_ENT(entity);
+  EntityS& e = h->ents[entity];
+  return draw_entity(h, entity, e.hyper, e.b0, e.hyper + h->D, e.nu0, nullptr, nullptr);
+}
+
+int bdf_sweep(bdf_t* h, int nsweeps) {
+  CHECK_H();
+  if (h->world != 1) FAIL(BDF_ERR_STATE, "bdf_sweep drives one GPU; with world > 1 use the bdf_step_* entries around the collectives");
+  CU(cudaSetDevice(h->device));
+  for (int s = 0; s < nsweeps; s++) {
+    for (int e = 0; e < (int)h->ents.size(); e++) {  // Gauss-Seidel order of src/macau.jl:96-134
+      int rc;
+      if ((rc = bdf_step_sample(h, e))) return rc;
+      if ((rc = bdf_step_nw_stats(h, e))) return rc;
+      if ((rc = bdf_step_nw_draw(h, e))) return rc;
+    }
+    h->sweep++;
+  }
+  return BDF_OK;
+}
+
+int bdf_get_hyper(bdf_t* h, int entity, double* mu, double* Lambda) {
+  CHECK_H(); CHECK_ENT(entity);
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if (mu) CU(cudaMemcpyAsync(mu, e.mu, sizeof(double) * h->D, cudaMemcpyDeviceToHost, h->stream));
+  if (Lambda) CU(cudaMemcpyAsync(Lambda, e.Lambda, sizeof(double) * h->D * h->D, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_err_flag(h);
+}
+
+int bdf_set_hyper(bdf_t* h, int entity, const double* mu, const double* Lambda) {
+  CHECK_H(); CHECK_ENT(entity);
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if (mu) CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+  if (Lambda) CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * h->D * h->D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+int bdf_debug_row_noise(bdf_t* h, int entity, uint64_t sweep, double* z) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!z) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  double* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(double) * (size_t)e.N * h->D));
+  row_noise_kernel<<<grid_for(e.N * h->D), 256, 0, h->stream>>>(d, h->D, e.N, h->seed, sweep, (uint32_t)entity);
+  cudaError_t ce = cudaMemcpyAsync(z, d, sizeof(double) * (size_t)e.N * h->D, cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  return BDF_OK;
+}
+
+int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yhat) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  if (ntest < 0 || (ntest > 0 && (!ids || !yhat))) FAIL(BDF_ERR_INVALID, "null argument");
+  if (ntest == 0) return BDF_OK;
+  CU(cudaSetDevice(h->device));
+  RelationS& r = h->rels[rel];
+  int64_t* d_ids = nullptr; int32_t* d_s = nullptr; double* d_out = nullptr; int* d_bad = nullptr;
+  CU(cudaMalloc((void**)&d_ids, sizeof(int64_t) * ntest * r.K));
+  CU(cudaMalloc((void**)&d_s, sizeof(int32_t) * ntest * r.K));
+  CU(cudaMalloc((void**)&d_out, sizeof(double) * ntest));
+  CU(cudaMalloc((void**)&d_bad, sizeof(int)));
+  CU(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+  CU(cudaMemcpyAsync(d_ids, ids, sizeof(int64_t) * ntest * r.K, cudaMemcpyHostToDevice, h->stream));
+  const double* Us[3] = {nullptr, nullptr, nullptr};
+  for (int m = 0; m < r.K; m++) {
+    EntityS& e = h->ents[r.entity_of_mode[m]];
+    Us[m] = e.U;
+    ids_to_slots_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(d_ids + (size_t)m * ntest, ntest, e.N, h->world, e.Nper, d_s + (size_t)m * ntest, d_bad);
+  }
+  predict_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(r.K, Us[0], Us[1], Us[2], d_s, d_s + ntest, d_s + 2 * ntest, h->ld, h->D, ntest, r.mean, d_out);
+  h->launches += 1 + r.K;
+  int bad = 0;
+  cudaError_t ce = cudaMemcpyAsync(yhat, d_out, sizeof(double) * ntest, cudaMemcpyDeviceToHost, h->stream);
+  cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t ce2 = cudaStreamSynchronize(h->stream);
+  cudaFree(d_ids); cudaFree(d_s); cudaFree(d_out); cudaFree(d_bad);
+  if (ce != cudaSuccess || ce2 != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+  if (bad) FAIL(BDF_ERR_INVALID, "test id outside 1..count of its entity");
+  return BDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Internal state of a bdf_t handle (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "row_kernel.cuh"
+
+namespace bdf {
+
+struct ModeIndex {            // one mode of one relation, restricted to the rows this rank owns
+  int64_t nrows = 0;          // local rows (= Nper of the entity)
+  int64_t nnz = 0;            // local observations
+  int64_t* row_ptr = nullptr; // [nrows+1] device
+  int32_t* col[2] = {nullptr, nullptr};  // partner slot indices per other mode (device)
+  double* val = nullptr;
+  int other_entity[2] = {-1, -1};
+  // work list
+  int n_items = 0, n_split = 0;
+  int32_t* item_row = nullptr;
+  int64_t* item_beg = nullptr;
+  int32_t* item_len = nullptr;
+  int32_t* item_split = nullptr;
+  int32_t* item_chunk = nullptr;
+  int32_t* split_nchunks = nullptr;
+  int64_t* split_wsoff = nullptr;
+  int* split_counter = nullptr;
+  int64_t ws_slots = 0;
+};
+
+struct RelationS {
+  int K = 0;
+  int entity_of_mode[3] = {-1, -1, -1};
+  int64_t nnz = 0;
+  double alpha = 1.0, mean = 0.0;
+  ModeIndex modes[3];
+};
+
+struct EntityS {
+  int64_t N = 0, Nper = 0;  // real rows; rows per rank (slots = world*Nper)
+  int64_t nlocal = 0;       // real rows owned by this rank
+  double* U = nullptr;      // world*Nper × ld, slot-major
+  double* mu = nullptr;     // D
+  double* Lambda = nullptr; // D×D col-major
+  double* mu_rows = nullptr;  // optional per-row mean, slot-major (ld pitch)
+  double* Z = nullptr;        // injected noise staging, slot-major
+  double* stats = nullptr;    // [N, NU(D), NS(D*D)]
+  double* hyper = nullptr;    // [mu0(D), WI(D*D), b0, nu0] device copy for the draw kernel
+  std::vector<double> mu0, WI;
+  double b0 = 2.0, nu0 = 0.0;
+  std::vector<std::pair<int, int>> uses;  // (relation, mode) pairs this entity takes part in
+};
+
+}  // namespace bdf
+
+struct bdf_handle {
+  int device = 0, D = 0, ld = 0, DP = 0, NW = 1, rank = 0, world = 1;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  uint64_t seed = 0x5eedULL;
+  uint64_t sweep = 0;
+  int64_t launches = 0;
+  std::vector<bdf::EntityS> ents;
+  std::vector<bdf::RelationS> rels;
+  double* ws = nullptr;  // partial workspace (split rows / stats partials)
+  size_t ws_bytes = 0;
+  double* scratch = nullptr;  // 4 D×D matrices for the Normal-Wishart draw
+  int* err_flag = nullptr;
+  int64_t pst = 0;  // doubles per parked partial for this D
+  std::string err;
+};

@@ -1,0 +1,73 @@
+// One padded latent dimension (-DBDF_DP=...) of the row-draw and statistics kernels; build.py compiles this file
+// once per DP so the 16 instances build in parallel.
+#include <string>
+
+#include "../../include/bdf_b200.h"
+#include "engine.cuh"
+#include "stats_kernel.cuh"
+
+#ifndef BDF_DP
+#error "compile with -DBDF_DP=<padded latent dimension>"
+#endif
+
+using namespace bdf;
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+      return BDF_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+static constexpr int kDP = BDF_DP;
+static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : 8);
+
+template <bool TENSOR>
+static int launch_rows_t(bdf_t* h, const RowParams& p, int n_items) {
+  using K = RowKernel<kDP, kNW, TENSOR>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(row_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
+    attr_done = true;
+  }
+  if (n_items > 0) {
+    row_kernel<K><<<n_items, K::NTHR, K::SMEM_BYTES, h->stream>>>(p);
+    h->launches++;
+    CU(cudaGetLastError());
+  }
+  return BDF_OK;
+}
+
+int CAT(bdf_launch_rows_, BDF_DP)(bdf_t* h, const RowParams& p, int n_items, bool tensor) {
+  return tensor ? launch_rows_t<true>(h, p, n_items) : launch_rows_t<false>(h, p, n_items);
+}
+
+// returns the number of partials written to h->ws (each tri(D+1) doubles), or a negative error
+int CAT(bdf_launch_stats_, BDF_DP)(bdf_t* h, const double* U, const double* uhat, int64_t slot0, int64_t nrows) {
+  using K = RowKernel<kDP, kNW, false>;
+  static bool attr_done = false;
+  const size_t smem = sizeof(double) * K::BUFSZ;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(stats_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  int64_t nblk = (nrows + 4 * K::KS - 1) / (4 * K::KS);
+  if (nblk > 296) nblk = 296;
+  if (nblk < 1) nblk = 1;
+  const int64_t rpb = (nrows + nblk - 1) / nblk;
+  const size_t need = sizeof(double) * (size_t)nblk * tri(h->D + 1);
+  if (need > h->ws_bytes) {
+    h->err = "workspace too small for statistics";
+    return BDF_ERR_STATE;
+  }
+  stats_kernel<K><<<(int)nblk, K::NTHR, smem, h->stream>>>(U, uhat, h->ld, h->D, slot0, nrows, rpb, h->ws);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return (int)nblk;
+}
+
+int64_t CAT(bdf_pst_, BDF_DP)() { return RowKernel<kDP, kNW, false>::PST; }

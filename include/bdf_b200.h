@@ -1,0 +1,112 @@
+/*
+ * bdf_b200.h — C ABI of libbdf_b200.so, the B200 (sm_100a) Gibbs-sampling engine that replaces the
+ * latent-factor hot path of BayesianDataFusion.jl. Plain pointers and sizes only; every entry returns
+ * an int status (0 = ok, negative = error; bdf_last_error() gives the message). No C++ exceptions
+ * cross this boundary and the library never calls exit().
+ *
+ * Conventions (they are the reference's own, so a Julia `ccall` needs no conversion):
+ *   - all matrices are column-major Float64 with explicit dimensions (pointer(A) of a Julia Matrix);
+ *     a factor matrix is D×N ("sample", src/RelationData.jl:15) — one latent vector per column;
+ *   - indices are 1-based: Int64 for relation ids (FastIDF.ids, src/IndexedDF.jl:46-50),
+ *     Int32 for sparse-binary rows/cols (src/parallel_matrix.jl:9-17);
+ *   - host arrays are copied during the call and never retained; device memory belongs to the handle;
+ *   - entry points taking host pointers are synchronous (they return after the stream is drained);
+ *     the *_dev / step entries only enqueue work on the handle's stream.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference checkout).
+ */
+#ifndef BDF_B200_H
+#define BDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bdf_handle bdf_t;
+
+#define BDF_OK 0
+#define BDF_ERR_INVALID (-1)  /* bad argument / DimensionMismatch / ArgumentError */
+#define BDF_ERR_CUDA (-2)     /* CUDA runtime failure (message in bdf_last_error) */
+#define BDF_ERR_NUMERIC (-3)  /* matrix not positive definite etc. */
+#define BDF_ERR_STATE (-4)    /* call order violated (e.g. sampling before data registration) */
+
+int bdf_version(void);
+/* Message of the last failure on `h` (or of the last failed bdf_create when h == NULL). */
+const char* bdf_last_error(const bdf_t* h);
+
+/* Handle lifecycle. One handle drives ONE device; multi-GPU = one process (one handle) per GPU with
+ * rank/world set here; rows of every entity are dealt out cyclically, row i (0-based) → rank i % world,
+ * exactly like the reference's worker shards `i:Nprocs:N` (src/sampling.jl:154). */
+int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world);
+int bdf_destroy(bdf_t* h);
+/* Run all work of this handle on the given cudaStream_t (NULL = the handle's own stream). */
+int bdf_set_stream(bdf_t* h, void* cuda_stream);
+/* Philox key for the device-side noise (used whenever an injected-noise pointer is NULL). */
+int bdf_set_seed(bdf_t* h, uint64_t seed);
+
+/* Entity(name) + initModel! — src/RelationData.jl:42-90: sample=0, mu=0, Lambda=5I, mu0=0, b0=2, WI=I, nu0=D.
+ * Returns the entity id (>= 0) or a negative error. */
+int bdf_add_entity(bdf_t* h, int64_t count);
+
+/* FastIDF(rel.data) + @spawnat (src/macau.jl:51-52, src/IndexedDF.jl:46-70): registers the observation table
+ * of a K-mode relation and builds one device CSR per mode (stable in table order, duplicates kept).
+ * ids: nnz×K column-major, 1-based; entity_of_mode[m] = entity id of mode m. Returns the relation id. */
+int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, const int64_t* ids, const double* vals);
+/* rel.model.alpha, rel.model.mean_value (src/RelationData.jl:107-118, :348). */
+int bdf_set_relation_params(bdf_t* h, int rel, double alpha, double mean_value);
+
+/* model.sample in / out: U is D×N column-major on the host. */
+int bdf_set_factors(bdf_t* h, int entity, const double* U);
+int bdf_get_factors(bdf_t* h, int entity, double* U);
+/* Device view for the torch.distributed plumbing: base pointer of the slot-ordered factor buffer
+ * (world*Nper rows × ld doubles, row-major; rank r owns rows [r*Nper, (r+1)*Nper)). */
+int bdf_factors_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* nper, int64_t* ld);
+
+/* sample_latent_all2!(rel, dataRefs, procs, mode, mu_u, Lambda_u) — src/sampling.jl:149-172 (and the general
+ * sample_user2_all! path, :251-289, when the entity sits in several relations): one half-sweep over `entity`,
+ * overwriting its factors on the device. mu: D vector (mu_ld == 0) or D×N matrix (mu_ld == D) as in
+ * src/macau.jl:102-107; Lambda: D×D; z: D×N injected standard normals in place of randn(D) per row, or NULL for
+ * device Philox noise. Only rows owned by this rank are sampled. */
+int bdf_sample_mode(bdf_t* h, int entity, const double* mu, int64_t mu_ld, const double* Lambda, const double* z);
+
+/* ConditionalNormalWishart's reductions — src/sampling.jl:117-119: N = size(U,2), NU = sum(U,2), NS = U*U'
+ * over the rows owned by this rank (all-reduce across ranks is the caller's, see bdf_stats_dev). */
+int bdf_nw_stats(bdf_t* h, int entity, double* N, double* NU, double* NS);
+/* Device buffer holding [N, NU(D), NS(D×D col-major)] of the last bdf_nw_stats / bdf_step_nw_stats. */
+int bdf_stats_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* count);
+
+/* rand(ConditionalNormalWishart(U, mu0, b0, Tinv, nu)) — src/sampling.jl:116-127 + src/normal_wishart.jl:38-42,
+ * from the statistics currently in the entity's stats buffer. bartlettA (D×D lower: A[i,i]=sqrt(chi2(nu_N-i+1)),
+ * A[i>j]~N(0,1)) and z (D) are the injected variates of Distributions' Wishart / MvNormal samplers; NULL = Philox.
+ * Stores (mu, Lambda) as the entity's current hyper-parameters and returns them when the pointers are non-NULL. */
+int bdf_nw_sample(bdf_t* h, int entity, const double* mu0, double b0, const double* Tinv, double nu,
+                  const double* bartlettA, const double* z, double* mu_out, double* Lambda_out);
+
+/* Device-resident sweep pieces (no host buffers): the loop body of src/macau.jl:96-134 for one entity, using the
+ * entity's current (mu, Lambda) and Philox noise. With world > 1 the caller all-gathers bdf_factors_dev after
+ * bdf_step_sample and all-reduces bdf_stats_dev after bdf_step_nw_stats. */
+int bdf_step_sample(bdf_t* h, int entity);
+int bdf_step_nw_stats(bdf_t* h, int entity);
+int bdf_step_nw_draw(bdf_t* h, int entity);
+/* Whole sweeps on one GPU (world == 1): for each entity {sample, stats, draw}. */
+int bdf_sweep(bdf_t* h, int nsweeps);
+int bdf_get_hyper(bdf_t* h, int entity, double* mu, double* Lambda);
+int bdf_set_hyper(bdf_t* h, int entity, const double* mu, const double* Lambda);
+/* The standard normals the device Philox stream yields for (entity, sweep): D×N column-major. Lets a test feed
+ * the oracle the very noise a Philox-mode half-sweep used. */
+int bdf_debug_row_noise(bdf_t* h, int entity, uint64_t sweep, double* z);
+int64_t bdf_sweep_counter(const bdf_t* h);
+int bdf_synchronize(bdf_t* h);
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int64_t bdf_launch_count(const bdf_t* h);
+
+/* pred(rel, test_vec, test_F) without relation features — src/sampling.jl:9-51: yhat[t] = sum_k prod_m U_m[k, ids[t,m]]
+ * + mean_value. ids: ntest×K column-major, 1-based. */
+int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yhat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDF_B200_H */

@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/bdf_b200.h
+declares; the ctypes table covers the same set; without a GPU the engine fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "bdf_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bdf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import bdf_b200
+    from bdf_b200 import _lib
+
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    if not os.path.exists(_lib.LIB_PATH):
+        from bdf_b200 import build  # noqa: F401
+
+        build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in bdf_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.bdf_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import bdf_b200
+
+    with pytest.raises(bdf_b200.BDFError) as ei:
+        bdf_b200.Engine(10)
+    assert "CUDA" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "bayesiandatafusion.jl_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), f"{f} mentions the oracle"
