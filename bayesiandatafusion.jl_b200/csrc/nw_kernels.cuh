@@ -16,6 +16,7 @@ __global__ void stats_reduce_kernel(const double* __restrict__ ws, int nblk, int
     while (tri(i + 1) <= e) i++;
     while (tri(i) > e) i--;
     const int j = e - tri(i);
+    if (j >= D) continue;  // (D, D) = Σ1·1 is not part of the statistics
     double s = 0.0;
     for (int b = 0; b < nblk; b++) s += ws[(size_t)b * ne + e];
     if (i < D) {

@@ -9,10 +9,12 @@
 //      of the tile when D is not a multiple of 8, else it is a DFMA side-sum;
 //   3. rows split over several CTAs park their partial in a workspace; the last CTA to arrive adds the partials
 //      in chunk order (deterministic);
-//   4. Λ* = Λ + αG is written index-REVERSED into shared memory, factored in place (LDLᵀ-style Cholesky with the
-//      rhs as an extra row = forward substitution for free), back-substituted by one warp, and the draw
-//      x = W⁻ᵀ(z + W⁻¹·rhs), Λ* = W·Wᵀ (W upper) is stored — algebraically identical, for the same z, to the
-//      reference's chol(inv(Λ*))ᵀ·z + inv(Λ*)·rhs (DESIGN.md §"draw formula").
+//   4. Λ* = Λ + αG stays in the accumulator registers and is factored there as Λ* = W·Wᵀ with W UPPER triangular
+//      ("UL" Cholesky, block rows eliminated from the last to the first): per 8-row panel every warp factors the
+//      8×8 diagonal block (shuffle-based, with its inverse), the panel tiles are scaled by one DMMA pair each and
+//      parked in shared memory, and the trailing update is again a DMMA syrk with the sign flipped;
+//   5. warp 0 runs the two blocked substitutions and stores the draw x = W⁻ᵀ(z + W⁻¹·rhs) — algebraically
+//      identical, for the same z, to the reference's chol(inv(Λ*))ᵀ·z + inv(Λ*)·rhs (DESIGN.md §"draw formula").
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -87,9 +89,11 @@ struct RowKernel {
   static constexpr int JP = (DP / 2 + 15) / 16;          // 16-byte pieces per thread per observation
   static constexpr int TPW = C::TPW;
   static constexpr int PST = NW * TPW * 64 + DP;         // doubles per parked partial
-  static constexpr int MSZ = tri(DP + 1) + DP + 1;       // packed lower triangle incl. rhs row
+  static constexpr int NB = C::NB;
+  static constexpr int PSZ = 32 * NB * NB;               // scaled panels: block row p = 8 × 8p doubles at pitch 8p+4, offset 32p²
   static constexpr int BUFSZ = 2 * KS * S + 2 * KS;
-  static constexpr int SMEM_DOUBLES = (MSZ > BUFSZ ? MSZ : BUFSZ) + 2 * DP;
+  static constexpr int REGSZ = PSZ > BUFSZ ? PSZ : BUFSZ;  // panels alias the (dead) stage buffers
+  static constexpr int SMEM_DOUBLES = REGSZ + 64 + NB * 64 + 4 * DP + 8;
   static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
 
   struct Pre {
@@ -211,9 +215,14 @@ struct RowKernel {
 
     double* bufs = smem;                    // [2][KS*S]
     double* rss = smem + 2 * KS * S;        // [2][KS]
-    double* M = smem;                       // packed lower triangle, aliases the stage buffers after the main loop
-    double* lmu = smem + (MSZ > BUFSZ ? MSZ : BUFSZ);  // Λ·μ  [DP]
-    double* xs = lmu + DP;                                // solution scratch [DP]
+    double* Pn = smem;                      // scaled panels, alias the stage buffers after the main loop
+    double* Dg = smem + REGSZ;              // current 8×8 diagonal block
+    double* Wv = Dg + 64;                   // inverse diagonal blocks W_pp⁻¹ [NB][8][8]
+    double* rhs = Wv + NB * 64;             // [DP]
+    double* lmu = rhs + DP;                 // Λ·μ [DP]
+    double* ys = lmu + DP;                  // W⁻¹·rhs (+ z) [DP]
+    double* xs = ys + DP;                   // the draw [DP]
+    double* ts = xs + DP;                   // [8]
 
     double acc[TPW][2];
 #pragma unroll
@@ -289,76 +298,184 @@ struct RowKernel {
       }
     }
 
-    // ---- Λ* (index-reversed, packed lower) and rhs row into shared memory ---------------------------------
+    // ---- Λ* = Λ + αG in the accumulators; rhs = Λμ + α·Σv·r in shared memory; identity on the padding ----------
     const double alpha = p.alpha;
     warp_dispatch(warp, [&](auto w) {
       for_acc<decltype(w)::value>(acc, lane, [&](int, int i, int j, double& v) {
-        if (j <= i) {
-          if (i < D) {
-            const int a = D - 1 - j, b = D - 1 - i;
-            M[tri(a) + b] = fma(alpha, v, __ldg(p.Lambda + i + (size_t)j * D));
-          } else if (i == D && j < D) {
-            M[tri(D) + (D - 1 - j)] = fma(alpha, v, lmu[j]);
-          }
+        if (i < D && j < D) {
+          v = fma(alpha, v, __ldg(p.Lambda + (i > j ? i + (size_t)j * D : j + (size_t)i * D)));
+        } else {
+          if (i == D && j < D) rhs[j] = fma(alpha, v, lmu[j]);  // augmented row = Σ v·r
+          v = (i == j) ? 1.0 : 0.0;
         }
       });
     });
-    if (!aug && tid < D) M[tri(D) + (D - 1 - tid)] = fma(alpha, bsum, lmu[tid]);
+    if (!aug && tid < D) rhs[tid] = fma(alpha, bsum, lmu[tid]);
+    if (tid >= D && tid < DP) rhs[tid] = 0.0;
 
-    // ---- in-place factorisation: unscaled columns l~_ij = L_ij·sqrt(d_j), pivots d_j on the diagonal ----------
-    constexpr int TY = NTHR / 16;
+    // ---- blocked UL factorisation: block rows p = NB-1 … 0 --------------------------------------------------------
     bool bad = false;
-    for (int j = 0; j < D; j++) {
+    for (int pb = NB - 1; pb >= 0; pb--) {
+      double* Pp = Pn + 32 * pb * pb;
+      const int SP = 8 * pb + 4;
+      // (a) the warp that owns the diagonal tile (pb,pb) factors it in registers, in the DMMA accumulator layout
+      //     (lane = 4·row + q holds columns 2q, 2q+1): A_pp = W·Wᵀ with W upper, by elimination from the last column
+      //     to the first, carrying an identity block that ends up as W⁻¹. Owners of the panel tiles (pb,J<pb) park
+      //     their raw tiles in shared memory meanwhile.
+      double a0 = 0.0, a1 = 0.0;
+      bool own = false;
+      warp_dispatch(warp, [&](auto w) {
+        constexpr int W = decltype(w)::value;
+        static_for<C::ntiles(W)>([&](auto t) {
+          constexpr int T = decltype(t)::value;
+          using ti = TI<C, W, T>;
+          if (ti::I == pb) {
+            if (ti::J == ti::I) {
+              a0 = acc[T][0];
+              a1 = acc[T][1];
+              own = true;
+            } else {
+              *reinterpret_cast<double2*>(Pp + (lane >> 2) * SP + 8 * ti::J + 2 * (lane & 3)) = make_double2(acc[T][0], acc[T][1]);
+            }
+          }
+        });
+      });
+      if (own) {
+        const int r = lane >> 2, q = lane & 3;
+        double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+          const int jq = j >> 1;
+          const double sel = (j & 1) ? a1 : a0;
+          const double piv = __shfl_sync(0xffffffffu, sel, 4 * j + jq);
+          if (!(piv > 0.0)) bad = true;
+          const double sc = rsqrt(piv);
+          const double wij = __shfl_sync(0xffffffffu, sel, (lane & ~3) | jq) * sc;  // w_ij of this lane's row
+          const double rj0 = __shfl_sync(0xffffffffu, a0, 4 * j + q) * sc;          // w_kj for this lane's two columns
+          const double rj1 = __shfl_sync(0xffffffffu, a1, 4 * j + q) * sc;
+          const double ej0 = __shfl_sync(0xffffffffu, e0, 4 * j + q) * sc;          // row j of W⁻¹
+          const double ej1 = __shfl_sync(0xffffffffu, e1, 4 * j + q) * sc;
+          if (r < j) {
+            a0 = fma(-wij, rj0, a0);
+            a1 = fma(-wij, rj1, a1);
+            e0 = fma(-wij, ej0, e0);
+            e1 = fma(-wij, ej1, e1);
+          } else if (r == j) {
+            e0 = ej0;
+            e1 = ej1;
+          }
+        }
+        *reinterpret_cast<double2*>(Wv + pb * 64 + r * 8 + 2 * q) = make_double2(e0, e1);
+      }
       __syncthreads();
-      const double d = M[tri(j) + j];
-      if (!(d > 0.0)) bad = true;
-      const double id = 1.0 / d;
-      for (int i = j + 1 + tr; i <= D; i += TY) {
-        const double lij = M[tri(i) + j] * id;
-        const int kmax = i < D ? i : D - 1;
-        double* Mi = M + tri(i);
-        for (int k = j + 1 + tq; k <= kmax; k += 16) Mi[k] = fma(-lij, M[tri(k) + j], Mi[k]);
+      // (b)
+      // scale this warp's panel tiles: R_pJ = W_pp⁻¹·A_pJ (= W_Jpᵀ), one DMMA pair per tile, written back in place
+      {
+        const double wa0 = Wv[pb * 64 + (lane >> 2) * 8 + (lane & 3)];
+        const double wa1 = Wv[pb * 64 + (lane >> 2) * 8 + 4 + (lane & 3)];
+        warp_dispatch(warp, [&](auto w) {
+          constexpr int W = decltype(w)::value;
+          static_for<C::ntiles(W)>([&](auto t) {
+            constexpr int T = decltype(t)::value;
+            using ti = TI<C, W, T>;
+            if (ti::I == pb && ti::J < ti::I) {
+              const double b0 = Pp[(lane & 3) * SP + 8 * ti::J + (lane >> 2)];
+              const double b1 = Pp[(4 + (lane & 3)) * SP + 8 * ti::J + (lane >> 2)];
+              double c2[2] = {0.0, 0.0};
+              dmma884(c2, wa0, b0);
+              dmma884(c2, wa1, b1);
+              *reinterpret_cast<double2*>(Pp + (lane >> 2) * SP + 8 * ti::J + 2 * (lane & 3)) = make_double2(c2[0], c2[1]);
+            }
+          });
+        });
+      }
+      __syncthreads();
+      // (c) trailing update of the tiles above the panel: A_IJ −= R_pIᵀ·R_pJ  (I, J < pb)
+      if (pb > 0) {
+        warp_dispatch(warp, [&](auto w) {
+          constexpr int W = decltype(w)::value;
+          constexpr int NF = C::nfrag(W);
+          constexpr int NTW = C::ntiles(W);
+          if constexpr (NTW > 0) {
+            const double* base = Pp + (lane & 3) * SP + (lane >> 2);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              double f[NF];
+              static_for<NF>([&](auto r) {
+                constexpr int R = decltype(r)::value;
+                constexpr int blk = FI<C, W, R>::blk;
+                f[R] = (blk < pb) ? base[h * 4 * SP + 8 * blk] : 0.0;
+              });
+              static_for<NTW>([&](auto t) {
+                constexpr int T = decltype(t)::value;
+                using ti = TI<C, W, T>;
+                if (ti::I < pb) dmma884(acc[T], -f[ti::fa], f[ti::fb]);
+              });
+            }
+          }
+        });
       }
     }
+    if (bad && lane == 0) atomicOr(p.err_flag, 1);
     __syncthreads();
-    if (bad && tid == 0) atomicOr(p.err_flag, 1);
 
-    // ---- back substitution by warp 0:  x'_j = (g_j − Σ_{i>j} l~_ij x'_i) / d_j,  g_j = l~_Dj + z'_j·sqrt(d_j) -----
+    // ---- substitutions by warp 0: y = W⁻¹·rhs (last block first), x = W⁻ᵀ(y + z) (first block first) --------------
     if (warp == 0) {
-      constexpr int NS = (DP + 31) / 32;
-      double g[NS], rd[NS];
+      const int r8 = lane & 7;
       const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
+      for (int J = NB - 1; J >= 0; J--) {
+        const double* Pj = Pn + 32 * J * J;
+        const int SP = 8 * J + 4;
+        double y0 = 0.0, y1 = 0.0;
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        const int j = lane + 32 * s;
-        g[s] = 0.0;
-        rd[s] = 0.0;
-        if (j < D) {
-          const double d = M[tri(j) + j];
-          const int jo = D - 1 - j;  // original latent index
-          const double z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + jo) : philox_normal(p.seed, p.sweep, p.entity, grow, jo);
-          g[s] = fma(z, sqrt(d), M[tri(D) + j]);
-          rd[s] = 1.0 / d;
+        for (int k = 0; k < 8; k += 2) {
+          y0 = fma(Wv[J * 64 + r8 * 8 + k], rhs[8 * J + k], y0);
+          y1 = fma(Wv[J * 64 + r8 * 8 + k + 1], rhs[8 * J + k + 1], y1);
         }
+        if (lane < 8) ys[8 * J + r8] = y0 + y1;
+        __syncwarp();
+        for (int c = lane; c < 8 * J; c += 32) {
+          double s0 = rhs[c], s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            s0 = fma(-Pj[k * SP + c], ys[8 * J + k], s0);
+            s1 = fma(-Pj[(k + 1) * SP + c], ys[8 * J + k + 1], s1);
+          }
+          rhs[c] = s0 + s1;
+        }
+        __syncwarp();
       }
-      for (int i = D - 1; i >= 0; i--) {
-        const int ol = i & 31, os = i >> 5;
-        double xi = 0.0;
-#pragma unroll
-        for (int s = 0; s < NS; s++)
-          if (s == os) xi = g[s] * rd[s];
-        xi = __shfl_sync(0xffffffffu, xi, ol);
-        const double* Mi = M + tri(i);
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-          const int j = lane + 32 * s;
-          if (j < i) g[s] = fma(-Mi[j], xi, g[s]);
-        }
-        if (lane == ol) xs[i] = xi;
+      for (int c = lane; c < DP; c += 32) {
+        double z = 0.0;
+        if (c < D) z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + c) : philox_normal(p.seed, p.sweep, p.entity, grow, c);
+        ys[c] += z;
       }
       __syncwarp();
+      for (int I = 0; I < NB; I++) {
+        const double* Pi = Pn + 32 * I * I;
+        const int SP = 8 * I + 4;
+        const int k = lane >> 2, q = lane & 3;
+        double s0 = 0.0, s1 = 0.0;
+        for (int c = q; c < 8 * I; c += 8) {
+          s0 = fma(Pi[k * SP + c], xs[c], s0);
+          s1 = fma(Pi[k * SP + c + 4], xs[c + 4], s1);
+        }
+        double sacc = s0 + s1;
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (q == 0) ts[k] = ys[8 * I + k] - sacc;
+        __syncwarp();
+        double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk += 2) {
+          x0 = fma(Wv[I * 64 + kk * 8 + r8], ts[kk], x0);
+          x1 = fma(Wv[I * 64 + (kk + 1) * 8 + r8], ts[kk + 1], x1);
+        }
+        if (lane < 8) xs[8 * I + r8] = x0 + x1;
+        __syncwarp();
+      }
       double* out = p.Uout + (size_t)slot * p.ld;
-      for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[D - 1 - j] : 0.0;
+      for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[j] : 0.0;
     }
   }
 };
