@@ -38,6 +38,7 @@ SIGNATURES = {
     "bdf_get_hyper": (C.c_int, [H, C.c_int, c_dp, c_dp]),
     "bdf_set_hyper": (C.c_int, [H, C.c_int, c_dp, c_dp]),
     "bdf_debug_row_noise": (C.c_int, [H, C.c_int, C.c_uint64, c_dp]),
+    "bdf_debug_phase_clocks": (C.c_int, [H, C.c_int, c_dp, c_i64p]),
     "bdf_sweep_counter": (C.c_int64, [H]),
     "bdf_synchronize": (C.c_int, [H]),
     "bdf_launch_count": (C.c_int64, [H]),

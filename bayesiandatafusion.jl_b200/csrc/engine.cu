@@ -254,7 +254,10 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr
   return ensure_ws(h, std::max<size_t>(sizeof(double) * (size_t)slots * h->pst, sizeof(double) * 296 * (size_t)tri(h->D + 1)));
 }
 
-int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev) {
+void prep_lambda(bdf_t* h, const double* Lambda, const double* mu, int D, int DP, double* LT, double* lmu);
+
+int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev,
+                  long long* dbg = nullptr) {
   EntityS& e = h->ents[entity];
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
   if (e.uses.size() > 1) FAIL(BDF_ERR_INVALID, "entities in several relations are not supported yet (SURVEY §8f N4)");
@@ -269,9 +272,16 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
   p.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr;
   p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper;
   p.Lambda = Lambda_dev; p.mu = mu_dev; p.mu_ld = mu_ld; p.Z = Z_dev;
+  p.LT = h->lt; p.lmu = mu_ld ? nullptr : h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2;
+  prep_lambda(h, Lambda_dev, mu_ld ? nullptr : mu_dev, h->D, h->DP, h->lt, h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2);
+  h->launches++;
   p.alpha = rel.alpha; p.mean = rel.mean; p.D = h->D; p.rank = h->rank; p.world = h->world;
-  p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag;
+  p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag; p.dbg = dbg;
   return launch_rows(h, p, mi.n_items, rel.K > 2);
+}
+
+void prep_lambda(bdf_t* h, const double* Lambda, const double* mu, int D, int DP, double* LT, double* lmu) {
+  prep_lambda_kernel<<<8, 256, 0, h->stream>>>(Lambda, mu, D, DP, LT, lmu);
 }
 
 int stats_entity(bdf_t* h, int entity) {
@@ -331,6 +341,7 @@ int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
   if ((ce = cudaMalloc((void**)&h->err_flag, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
   cudaMemset(h->err_flag, 0, sizeof(int));
   if ((ce = cudaMalloc((void**)&h->scratch, sizeof(double) * ((size_t)4 * num_latent * num_latent + 4 * num_latent))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&h->lt, sizeof(double) * (64 * (size_t)(h->DP / 8) * (h->DP / 8 + 1) / 2 + h->DP))) != cudaSuccess) return bail(ce, "cudaMalloc");
   h->ws_bytes = sizeof(double) * 296 * (size_t)tri(num_latent + 1);
   if ((ce = cudaMalloc((void**)&h->ws, h->ws_bytes)) != cudaSuccess) return bail(ce, "cudaMalloc");
   *out = h;
@@ -351,7 +362,7 @@ int bdf_destroy(bdf_t* h) {
       cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk);
       cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
     }
-  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag);
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return BDF_OK;
@@ -670,6 +681,35 @@ int bdf_debug_row_noise(bdf_t* h, int entity, uint64_t sweep, double* z) {
   cudaStreamSynchronize(h->stream);
   cudaFree(d);
   if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  return BDF_OK;
+}
+
+int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, int64_t* n_items) {
+  CHECK_H(); CHECK_ENT(entity);
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
+  const int ni = h->rels[e.uses[0].first].modes[e.uses[0].second].n_items;
+  long long* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(long long) * 8 * (size_t)std::max(ni, 1)));
+  CU(cudaMemsetAsync(d, 0, sizeof(long long) * 8 * (size_t)std::max(ni, 1), h->stream));
+  int rc = sample_entity(h, entity, e.mu, 0, e.Lambda, nullptr, d);
+  std::vector<long long> hbuf((size_t)8 * std::max(ni, 1));
+  cudaMemcpyAsync(hbuf.data(), d, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (rc) return rc;
+  for (int k = 0; k < 7; k++) mean_cycles[k] = 0.0;
+  int64_t cnt = 0;
+  for (int i = 0; i < ni; i++) {
+    const long long* t = &hbuf[(size_t)i * 8];
+    if (t[6] == 0) continue;  // split-row chunk that did not finalise
+    for (int k = 1; k < 7; k++) mean_cycles[k - 1] += (double)(t[k] - t[k - 1]);
+    mean_cycles[6] += (double)(t[6] - t[0]);
+    cnt++;
+  }
+  for (int k = 0; k < 7; k++) mean_cycles[k] /= (double)std::max<int64_t>(cnt, 1);
+  if (n_items) *n_items = cnt;
   return BDF_OK;
 }
 

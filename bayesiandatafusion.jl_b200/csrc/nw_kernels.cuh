@@ -8,6 +8,25 @@
 
 namespace bdf {
 
+// Once per half-sweep: Λ in the tile order the row kernel factors in (identity on the padding), and Λ·μ for a shared μ.
+__global__ void prep_lambda_kernel(const double* __restrict__ Lambda, const double* __restrict__ mu, int D, int DP, double* __restrict__ LT,
+                                   double* __restrict__ lmu) {
+  const int NB = DP / 8, NT = NB * (NB + 1) / 2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 64 * NT; e += gridDim.x * blockDim.x) {
+    int I, J;
+    tri_coords(e >> 6, I, J);
+    const int i = 8 * I + ((e >> 3) & 7), j = 8 * J + (e & 7);
+    LT[e] = (i < D && j < D) ? Lambda[i > j ? i + (size_t)j * D : j + (size_t)i * D] : (i == j ? 1.0 : 0.0);
+  }
+  if (mu)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < DP; j += gridDim.x * blockDim.x) {
+      double s = 0.0;
+      if (j < D)
+        for (int i = 0; i < D; i++) s = fma(Lambda[j + (size_t)i * D], mu[i], s);
+      lmu[j] = s;
+    }
+}
+
 // sum the partials in block order; emit [N, NU(D), NS(D×D, symmetric, column-major)]
 __global__ void stats_reduce_kernel(const double* __restrict__ ws, int nblk, int D, double count, double* __restrict__ stats) {
   const int ne = tri(D + 1);

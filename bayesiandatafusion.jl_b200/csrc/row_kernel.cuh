@@ -47,6 +47,8 @@ struct RowParams {
   double* Uout;  // factor buffer being sampled
   int64_t slot_base;  // slot of local row 0 (= rank * Nper)
   const double* Lambda;  // D×D column-major
+  const double* LT;      // Λ in tile order (64 doubles per tile t = tri(I)+J, identity on the padding), see prep_lambda_kernel
+  const double* lmu;     // Λ·μ (DP doubles) when μ is shared by all rows, else nullptr
   const double* mu;      // D (mu_ld == 0) or slot-major matrix (mu_ld == ld)
   int64_t mu_ld;
   const double* Z;  // injected normals, slot-major (ld pitch), or nullptr → Philox
@@ -56,6 +58,7 @@ struct RowParams {
   uint64_t seed, sweep;
   int entity;
   int* err_flag;
+  long long* dbg;  // optional per-item phase clocks [n_items][8] (bdf_debug_phase_clocks), else nullptr
 };
 
 template <int N, class F, int... Is>
@@ -74,6 +77,14 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 }
 
 __host__ __device__ constexpr int tri(int i) { return i * (i + 1) / 2; }
+// inverse of t = tri(I) + J, 0 <= J <= I (t < 2^20)
+__device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
+  int i = (int)((sqrtf((float)(8 * t + 1)) - 1.0f) * 0.5f);
+  if (tri(i + 1) <= t) i++;
+  if (tri(i) > t) i--;
+  I = i;
+  J = t - tri(i);
+}
 
 template <int DP_, int NW_, bool TENSOR_>
 struct RowKernel {
@@ -90,10 +101,10 @@ struct RowKernel {
   static constexpr int TPW = C::TPW;
   static constexpr int PST = NW * TPW * 64 + DP;         // doubles per parked partial
   static constexpr int NB = C::NB;
-  static constexpr int PSZ = 32 * NB * NB;               // scaled panels: block row p = 8 × 8p doubles at pitch 8p+4, offset 32p²
+  static constexpr int PSZ = 64 * C::NT;                 // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
   static constexpr int BUFSZ = 2 * KS * S + 2 * KS;
-  static constexpr int REGSZ = PSZ > BUFSZ ? PSZ : BUFSZ;  // panels alias the (dead) stage buffers
-  static constexpr int SMEM_DOUBLES = REGSZ + 64 + NB * 64 + 4 * DP + 8;
+  static constexpr int REGSZ = PSZ > BUFSZ ? PSZ : BUFSZ;  // the tiles alias the (dead) stage buffers
+  static constexpr int SMEM_DOUBLES = REGSZ + NB * 64 + 4 * DP + 8;
   static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
 
   struct Pre {
@@ -215,33 +226,37 @@ struct RowKernel {
 
     double* bufs = smem;                    // [2][KS*S]
     double* rss = smem + 2 * KS * S;        // [2][KS]
-    double* Pn = smem;                      // scaled panels, alias the stage buffers after the main loop
-    double* Dg = smem + REGSZ;              // current 8×8 diagonal block
-    double* Wv = Dg + 64;                   // inverse diagonal blocks W_pp⁻¹ [NB][8][8]
-    double* rhs = Wv + NB * 64;             // [DP]
+    double* Tl = smem;                      // Λ* / factor tiles, alias the stage buffers after the main loop
+    double* WvT = smem + REGSZ;             // inverse diagonal blocks, transposed: WvT[p][k][m] = (W_pp⁻¹)[m][k]
+    double* rhs = WvT + NB * 64;            // [DP]
     double* lmu = rhs + DP;                 // Λ·μ [DP]
     double* ys = lmu + DP;                  // W⁻¹·rhs (+ z) [DP]
     double* xs = ys + DP;                   // the draw [DP]
     double* ts = xs + DP;                   // [8]
 
+#define BDF_STAMP(k)                                                   \
+  if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + (k)] = clock64()
+    BDF_STAMP(0);
     double acc[TPW][2];
 #pragma unroll
     for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
     double bsum = 0.0;  // Σ v_tid · r  (used when !aug)
 
-    // Λ·μ for this row (thread j < D), independent of the gather
-    {
-      const double* mu = p.mu + (p.mu_ld ? slot * p.mu_ld : 0);
-      if (tid < DP) {
-        double s = 0.0;
-        if (tid < D)
-          for (int i = 0; i < D; i++) s = fma(__ldg(p.Lambda + tid + (size_t)i * D), __ldg(mu + i), s);
-        lmu[tid] = s;
+    // Λ·μ: precomputed when μ is shared; per-row μ (side features, src/macau.jl:102-107) is multiplied here
+    if (tid < DP) {
+      double s = 0.0;
+      if (p.lmu) {
+        s = __ldg(p.lmu + tid);
+      } else if (tid < D) {
+        const double* mu = p.mu + slot * p.mu_ld;
+        for (int i = 0; i < D; i++) s = fma(__ldg(p.Lambda + tid + (size_t)i * D), __ldg(mu + i), s);
       }
+      lmu[tid] = s;
     }
 
     const int nst = (len + KS - 1) / KS;
     Pre pre;
+    BDF_STAMP(1);
     if (nst > 0) {
       prefetch(p, obeg, oend, tr, tq, pre);
       store_stage(D, bufs, rss, tr, tq, pre, aug);
@@ -263,6 +278,7 @@ struct RowKernel {
       __syncthreads();
     }
 
+    BDF_STAMP(2);
     // ---- split rows: park the partial, last arriver reduces in chunk order -------------------------------
     if (split >= 0) {
       const int nch = p.split_nchunks[split];
@@ -298,153 +314,162 @@ struct RowKernel {
       }
     }
 
-    // ---- Λ* = Λ + αG in the accumulators; rhs = Λμ + α·Σv·r in shared memory; identity on the padding ----------
-    const double alpha = p.alpha;
+    BDF_STAMP(3);
+    // ---- park the Gram tiles in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles) -----------
     warp_dispatch(warp, [&](auto w) {
-      for_acc<decltype(w)::value>(acc, lane, [&](int, int i, int j, double& v) {
-        if (i < D && j < D) {
-          v = fma(alpha, v, __ldg(p.Lambda + (i > j ? i + (size_t)j * D : j + (size_t)i * D)));
-        } else {
-          if (i == D && j < D) rhs[j] = fma(alpha, v, lmu[j]);  // augmented row = Σ v·r
-          v = (i == j) ? 1.0 : 0.0;
-        }
+      constexpr int W = decltype(w)::value;
+      static_for<C::ntiles(W)>([&](auto t) {
+        constexpr int T = decltype(t)::value;
+        using ti = TI<C, W, T>;
+        *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + 2 * lane) = make_double2(acc[T][0], acc[T][1]);
       });
     });
-    if (!aug && tid < D) rhs[tid] = fma(alpha, bsum, lmu[tid]);
+    if (!aug && tid < D) rhs[tid] = fma(p.alpha, bsum, lmu[tid]);
     if (tid >= D && tid < DP) rhs[tid] = 0.0;
-
-    // ---- blocked UL factorisation: block rows p = NB-1 … 0 --------------------------------------------------------
-    bool bad = false;
-    for (int pb = NB - 1; pb >= 0; pb--) {
-      double* Pp = Pn + 32 * pb * pb;
-      const int SP = 8 * pb + 4;
-      // (a) the warp that owns the diagonal tile (pb,pb) factors it in registers, in the DMMA accumulator layout
-      //     (lane = 4·row + q holds columns 2q, 2q+1): A_pp = W·Wᵀ with W upper, by elimination from the last column
-      //     to the first, carrying an identity block that ends up as W⁻¹. Owners of the panel tiles (pb,J<pb) park
-      //     their raw tiles in shared memory meanwhile.
-      double a0 = 0.0, a1 = 0.0;
-      bool own = false;
-      warp_dispatch(warp, [&](auto w) {
-        constexpr int W = decltype(w)::value;
-        static_for<C::ntiles(W)>([&](auto t) {
-          constexpr int T = decltype(t)::value;
-          using ti = TI<C, W, T>;
-          if (ti::I == pb) {
-            if (ti::J == ti::I) {
-              a0 = acc[T][0];
-              a1 = acc[T][1];
-              own = true;
-            } else {
-              *reinterpret_cast<double2*>(Pp + (lane >> 2) * SP + 8 * ti::J + 2 * (lane & 3)) = make_double2(acc[T][0], acc[T][1]);
-            }
-          }
-        });
-      });
-      if (own) {
-        const int r = lane >> 2, q = lane & 3;
-        double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
-#pragma unroll
-        for (int j = 7; j >= 0; j--) {
-          const int jq = j >> 1;
-          const double sel = (j & 1) ? a1 : a0;
-          const double piv = __shfl_sync(0xffffffffu, sel, 4 * j + jq);
-          if (!(piv > 0.0)) bad = true;
-          const double sc = rsqrt(piv);
-          const double wij = __shfl_sync(0xffffffffu, sel, (lane & ~3) | jq) * sc;  // w_ij of this lane's row
-          const double rj0 = __shfl_sync(0xffffffffu, a0, 4 * j + q) * sc;          // w_kj for this lane's two columns
-          const double rj1 = __shfl_sync(0xffffffffu, a1, 4 * j + q) * sc;
-          const double ej0 = __shfl_sync(0xffffffffu, e0, 4 * j + q) * sc;          // row j of W⁻¹
-          const double ej1 = __shfl_sync(0xffffffffu, e1, 4 * j + q) * sc;
-          if (r < j) {
-            a0 = fma(-wij, rj0, a0);
-            a1 = fma(-wij, rj1, a1);
-            e0 = fma(-wij, ej0, e0);
-            e1 = fma(-wij, ej1, e1);
-          } else if (r == j) {
-            e0 = ej0;
-            e1 = ej1;
-          }
+    __syncthreads();
+    // ---- Λ* = Λ + αG, rhs = Λμ + α·Σv·r (augmented row), identity on the padding — same code for every warp -------
+    {
+      const double alpha = p.alpha;
+      const int r = lane >> 2, q = lane & 3;
+#pragma unroll 4
+      for (int t = warp; t < C::NT; t += NW) {
+        int I, J;
+        tri_coords(t, I, J);
+        const int i = 8 * I + r, j = 8 * J + 2 * q;
+        const double2 g = *reinterpret_cast<const double2*>(Tl + 64 * t + 2 * lane);
+        double2 v = __ldg(reinterpret_cast<const double2*>(p.LT + 64 * t + 2 * lane));
+        if (i < D) {
+          if (j < D) v.x = fma(alpha, g.x, v.x);
+          if (j + 1 < D) v.y = fma(alpha, g.y, v.y);
+        } else if (i == D) {
+          if (j < D) rhs[j] = fma(alpha, g.x, lmu[j]);
+          if (j + 1 < D) rhs[j + 1] = fma(alpha, g.y, lmu[j + 1]);
         }
-        *reinterpret_cast<double2*>(Wv + pb * 64 + r * 8 + 2 * q) = make_double2(e0, e1);
-      }
-      __syncthreads();
-      // (b)
-      // scale this warp's panel tiles: R_pJ = W_pp⁻¹·A_pJ (= W_Jpᵀ), one DMMA pair per tile, written back in place
-      {
-        const double wa0 = Wv[pb * 64 + (lane >> 2) * 8 + (lane & 3)];
-        const double wa1 = Wv[pb * 64 + (lane >> 2) * 8 + 4 + (lane & 3)];
-        warp_dispatch(warp, [&](auto w) {
-          constexpr int W = decltype(w)::value;
-          static_for<C::ntiles(W)>([&](auto t) {
-            constexpr int T = decltype(t)::value;
-            using ti = TI<C, W, T>;
-            if (ti::I == pb && ti::J < ti::I) {
-              const double b0 = Pp[(lane & 3) * SP + 8 * ti::J + (lane >> 2)];
-              const double b1 = Pp[(4 + (lane & 3)) * SP + 8 * ti::J + (lane >> 2)];
-              double c2[2] = {0.0, 0.0};
-              dmma884(c2, wa0, b0);
-              dmma884(c2, wa1, b1);
-              *reinterpret_cast<double2*>(Pp + (lane >> 2) * SP + 8 * ti::J + 2 * (lane & 3)) = make_double2(c2[0], c2[1]);
-            }
-          });
-        });
-      }
-      __syncthreads();
-      // (c) trailing update of the tiles above the panel: A_IJ −= R_pIᵀ·R_pJ  (I, J < pb)
-      if (pb > 0) {
-        warp_dispatch(warp, [&](auto w) {
-          constexpr int W = decltype(w)::value;
-          constexpr int NF = C::nfrag(W);
-          constexpr int NTW = C::ntiles(W);
-          if constexpr (NTW > 0) {
-            const double* base = Pp + (lane & 3) * SP + (lane >> 2);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              double f[NF];
-              static_for<NF>([&](auto r) {
-                constexpr int R = decltype(r)::value;
-                constexpr int blk = FI<C, W, R>::blk;
-                f[R] = (blk < pb) ? base[h * 4 * SP + 8 * blk] : 0.0;
-              });
-              static_for<NTW>([&](auto t) {
-                constexpr int T = decltype(t)::value;
-                using ti = TI<C, W, T>;
-                if (ti::I < pb) dmma884(acc[T], -f[ti::fa], f[ti::fb]);
-              });
-            }
-          }
-        });
+        *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = v;
       }
     }
-    if (bad && lane == 0) atomicOr(p.err_flag, 1);
     __syncthreads();
+    BDF_STAMP(4);
 
-    // ---- substitutions by warp 0: y = W⁻¹·rhs (last block first), x = W⁻ᵀ(y + z) (first block first) --------------
-    if (warp == 0) {
-      const int r8 = lane & 7;
-      const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
-      for (int J = NB - 1; J >= 0; J--) {
-        const double* Pj = Pn + 32 * J * J;
-        const int SP = 8 * J + 4;
-        double y0 = 0.0, y1 = 0.0;
+    // ---- blocked UL factorisation Λ* = W·Wᵀ (W upper), block rows pb = NB-1 … 0, on the shared-memory tiles --------
+    // Per panel: (b) the panel tiles are scaled, R_pJ = W_pp⁻¹·A_pJ, by one DMMA pair each; (c) the tiles above the
+    // panel get A_IJ −= R_pIᵀ·R_pJ, again DMMA; warp 0 takes the next diagonal tile first and factors it while the
+    // other warps finish the trailing update (look-ahead), so the serial 8×8 factorisations overlap the updates.
+    bool bad = false;
+    auto factor_diag = [&](int pb) {
+      // A_pp = W·Wᵀ by elimination from the last column to the first, in the DMMA accumulator layout (lane = 4·row+q
+      // holds columns 2q, 2q+1); an identity block carried along ends up as W⁻¹, stored transposed in WvT[pb].
+      const int r = lane >> 2, q = lane & 3;
+      const double2 av = *reinterpret_cast<const double2*>(Tl + 64 * (tri(pb) + pb) + 2 * lane);
+      double a0 = av.x, a1 = av.y;
+      double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          y0 = fma(Wv[J * 64 + r8 * 8 + k], rhs[8 * J + k], y0);
-          y1 = fma(Wv[J * 64 + r8 * 8 + k + 1], rhs[8 * J + k + 1], y1);
+      for (int j = 7; j >= 0; j--) {
+        const int jq = j >> 1;
+        const double sel = (j & 1) ? a1 : a0;
+        const double piv = __shfl_sync(0xffffffffu, sel, 4 * j + jq);
+        if (!(piv > 0.0)) bad = true;
+        const double sc = rsqrt(piv);
+        const double wij = __shfl_sync(0xffffffffu, sel, (lane & ~3) | jq) * sc;  // w_ij of this lane's row
+        const double rj0 = __shfl_sync(0xffffffffu, a0, 4 * j + q) * sc;          // w_kj for this lane's two columns
+        const double rj1 = __shfl_sync(0xffffffffu, a1, 4 * j + q) * sc;
+        const double ej0 = __shfl_sync(0xffffffffu, e0, 4 * j + q) * sc;          // row j of W⁻¹
+        const double ej1 = __shfl_sync(0xffffffffu, e1, 4 * j + q) * sc;
+        if (r < j) {
+          a0 = fma(-wij, rj0, a0);
+          a1 = fma(-wij, rj1, a1);
+          e0 = fma(-wij, ej0, e0);
+          e1 = fma(-wij, ej1, e1);
+        } else if (r == j) {
+          e0 = ej0;
+          e1 = ej1;
         }
-        if (lane < 8) ys[8 * J + r8] = y0 + y1;
-        __syncwarp();
+      }
+      WvT[pb * 64 + (2 * q) * 8 + r] = e0;
+      WvT[pb * 64 + (2 * q + 1) * 8 + r] = e1;
+    };
+    // fragment of a row-major 8×8 tile as DMMA A (row.col: A[m][k]=tile[k][m]) or B (B[k][n]=tile[k][n]) operand, k-half h
+    const int fo = 8 * (lane & 3) + (lane >> 2);
+    auto update_tile = [&](int pb, int t) {
+      int I, J;
+      tri_coords(t, I, J);
+      const double* RI = Tl + 64 * (tri(pb) + I) + fo;
+      const double* RJ = Tl + 64 * (tri(pb) + J) + fo;
+      double2 cv = *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane);
+      double c2[2] = {cv.x, cv.y};
+      dmma884(c2, -RI[0], RJ[0]);
+      dmma884(c2, -RI[32], RJ[32]);
+      *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = make_double2(c2[0], c2[1]);
+    };
+
+    // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
+    // rhs[c] −= Σ_k R_J[k][c]·y_J[k] for c < 8J. One warp; rides along with the trailing update.
+    auto backsub_step = [&](int J, bool update) {
+      const int r8 = lane & 7;
+      double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        y0 = fma(WvT[J * 64 + k * 8 + r8], rhs[8 * J + k], y0);
+        y1 = fma(WvT[J * 64 + (k + 1) * 8 + r8], rhs[8 * J + k + 1], y1);
+      }
+      if (lane < 8) ys[8 * J + r8] = y0 + y1;
+      __syncwarp();
+      if (update) {
         for (int c = lane; c < 8 * J; c += 32) {
+          const double* tp = Tl + 64 * (tri(J) + (c >> 3)) + (c & 7);  // R_J[k][c] = tile(J, c/8)[k][c%8]
           double s0 = rhs[c], s1 = 0.0;
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
-            s0 = fma(-Pj[k * SP + c], ys[8 * J + k], s0);
-            s1 = fma(-Pj[(k + 1) * SP + c], ys[8 * J + k + 1], s1);
+            s0 = fma(-tp[8 * k], ys[8 * J + k], s0);
+            s1 = fma(-tp[8 * k + 8], ys[8 * J + k + 1], s1);
           }
           rhs[c] = s0 + s1;
         }
         __syncwarp();
       }
+    };
+
+    if (warp == 0) factor_diag(NB - 1);
+    __syncthreads();
+    for (int pb = NB - 1; pb > 0; pb--) {
+      // (b) scale the panel tiles (pb, J < pb) in place
+      {
+        const double wa0 = WvT[pb * 64 + fo], wa1 = WvT[pb * 64 + 32 + fo];
+        for (int J = warp; J < pb; J += NW) {
+          double* tp = Tl + 64 * (tri(pb) + J);
+          const double b0 = tp[fo], b1 = tp[32 + fo];
+          double c2[2] = {0.0, 0.0};
+          dmma884(c2, wa0, b0);
+          dmma884(c2, wa1, b1);
+          *reinterpret_cast<double2*>(tp + 2 * lane) = make_double2(c2[0], c2[1]);
+        }
+      }
+      __syncthreads();
+      // (c) trailing update of tiles t < tri(pb) (block rows < pb); warp 0: next diagonal tile first, then factor it
+      const int ntr = tri(pb);
+      if (NW == 1) {
+        backsub_step(pb, true);
+        for (int t = 0; t < ntr; t++) update_tile(pb, t);
+        __syncwarp();
+        factor_diag(pb - 1);
+      } else if (warp == 0) {
+        update_tile(pb, ntr - 1);
+        __syncwarp();
+        factor_diag(pb - 1);
+      } else {
+        if (warp == 1) backsub_step(pb, true);
+        for (int t = warp - 1; t < ntr - 1; t += NW - 1) update_tile(pb, t);
+      }
+      __syncthreads();
+    }
+    if (bad && lane == 0) atomicOr(p.err_flag, 1);
+    BDF_STAMP(5);
+
+    // ---- warp 0: last block of y = W⁻¹·rhs, then x = W⁻ᵀ(y + z) by forward substitution over the block rows ---------
+    if (warp == 0) {
+      const int r8 = lane & 7;
+      const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
+      backsub_step(0, false);
       for (int c = lane; c < DP; c += 32) {
         double z = 0.0;
         if (c < D) z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + c) : philox_normal(p.seed, p.sweep, p.entity, grow, c);
@@ -452,13 +477,12 @@ struct RowKernel {
       }
       __syncwarp();
       for (int I = 0; I < NB; I++) {
-        const double* Pi = Pn + 32 * I * I;
-        const int SP = 8 * I + 4;
         const int k = lane >> 2, q = lane & 3;
         double s0 = 0.0, s1 = 0.0;
         for (int c = q; c < 8 * I; c += 8) {
-          s0 = fma(Pi[k * SP + c], xs[c], s0);
-          s1 = fma(Pi[k * SP + c + 4], xs[c + 4], s1);
+          const double* tp = Tl + 64 * (tri(I) + (c >> 3)) + 8 * k + (c & 7);  // R_I[k][c], R_I[k][c+4]
+          s0 = fma(tp[0], xs[c], s0);
+          s1 = fma(tp[4], xs[c + 4], s1);
         }
         double sacc = s0 + s1;
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
@@ -468,16 +492,19 @@ struct RowKernel {
         double x0 = 0.0, x1 = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 8; kk += 2) {
-          x0 = fma(Wv[I * 64 + kk * 8 + r8], ts[kk], x0);
-          x1 = fma(Wv[I * 64 + (kk + 1) * 8 + r8], ts[kk + 1], x1);
+          x0 = fma(WvT[I * 64 + r8 * 8 + kk], ts[kk], x0);
+          x1 = fma(WvT[I * 64 + r8 * 8 + kk + 1], ts[kk + 1], x1);
         }
         if (lane < 8) xs[8 * I + r8] = x0 + x1;
         __syncwarp();
       }
       double* out = p.Uout + (size_t)slot * p.ld;
       for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[j] : 0.0;
+      __syncwarp();
+      BDF_STAMP(6);
     }
   }
+#undef BDF_STAMP
 };
 
 template <class K>

@@ -170,6 +170,12 @@ class Engine:
         self._ck(self.lib.bdf_debug_row_noise(self.h, entity, C.c_uint64(sweep), _dp(z)))
         return z
 
+    def debug_phase_clocks(self, entity: int):
+        out = np.zeros(7)
+        n = C.c_int64()
+        self._ck(self.lib.bdf_debug_phase_clocks(self.h, entity, _dp(out), C.byref(n)))
+        return dict(zip(["setup", "syrk", "split", "build", "factor", "solve", "total"], out)), n.value
+
     def predict(self, rel: int, ids):
         ids = np.asfortranarray(ids, dtype=np.int64)
         out = np.zeros(ids.shape[0])

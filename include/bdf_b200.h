@@ -97,6 +97,9 @@ int bdf_set_hyper(bdf_t* h, int entity, const double* mu, const double* Lambda);
 /* The standard normals the device Philox stream yields for (entity, sweep): D×N column-major. Lets a test feed
  * the oracle the very noise a Philox-mode half-sweep used. */
 int bdf_debug_row_noise(bdf_t* h, int entity, uint64_t sweep, double* z);
+/* Profiling hook: one Philox half-sweep of `entity` with per-work-item phase clocks; returns the mean SM cycles of
+ * [setup, gather+syrk, split-reduce, build, factorisation, substitutions, total] over the items that finalised a row. */
+int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles, int64_t* n_items);
 int64_t bdf_sweep_counter(const bdf_t* h);
 int bdf_synchronize(bdf_t* h);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */

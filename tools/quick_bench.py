@@ -42,6 +42,8 @@ def run(n1, n2, nnz, D, sweeps=3, skew=2.5):
     flops = 2 * nnz * (D * (D + 1) + 2 * D) + (n1 + n2) * (D**3 / 3 + 2 * D * D)
     print(f"D={D} n=({n1},{n2}) nnz={nnz} skew={skew}: ingest {t1-t0:.2f}s, sweep {dt*1e3:.2f} ms, {1/dt:.2f} sweeps/s, "
           f"{flops/dt/1e12:.2f} TFLOP/s alg; parts(ms): " + ", ".join(f"e{e}.{n}={t:.2f}" for e, n, t in ts), flush=True)
+    for e in (e1, e2):
+        print('   phase clocks', e, {k: int(v) for k, v in eng.debug_phase_clocks(e)[0].items()}, flush=True)
     eng.close()
 
 
