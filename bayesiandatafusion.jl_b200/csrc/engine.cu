@@ -331,7 +331,7 @@ int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
   bdf_t* h = new bdf_t();
   h->device = device; h->D = num_latent; h->rank = rank; h->world = world;
   h->ld = round_up(num_latent, 4);
-  h->DP = (num_latent % 8 == 0) ? num_latent : round_up(num_latent, 8);
+  h->DP = round_up(num_latent, 8);
   h->NW = h->DP <= 32 ? 1 : (h->DP <= 64 ? 4 : 8);
   h->pst = pst_of(h->DP);
   auto bail = [&](cudaError_t e, const char* what) { g_create_err = std::string(what) + ": " + cudaGetErrorString(e); delete h; return BDF_ERR_CUDA; };

@@ -50,12 +50,12 @@ int CAT(bdf_launch_rows_, BDF_DP)(bdf_t* h, const RowParams& p, int n_items, boo
 int CAT(bdf_launch_stats_, BDF_DP)(bdf_t* h, const double* U, const double* uhat, int64_t slot0, int64_t nrows) {
   using K = RowKernel<kDP, kNW, false>;
   static bool attr_done = false;
-  const size_t smem = sizeof(double) * K::BUFSZ;
+  const size_t smem = sizeof(double) * K::SBUFSZ;
   if (!attr_done) {
     CU(cudaFuncSetAttribute(stats_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  int64_t nblk = (nrows + 4 * K::KS - 1) / (4 * K::KS);
+  int64_t nblk = (nrows + 4 * K::SKS - 1) / (4 * K::SKS);
   if (nblk > 296) nblk = 296;
   if (nblk < 1) nblk = 1;
   const int64_t rpb = (nrows + nblk - 1) / nblk;

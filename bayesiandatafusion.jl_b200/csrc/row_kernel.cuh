@@ -2,19 +2,21 @@
 // sample_latent_all2!/sample_latent_range, :149-198) as one fused sm_100a kernel.
 //
 // One CTA (NW warps) owns one work item = (row, chunk of that row's observations):
-//   1. gather the partner factor rows of the chunk (Hadamard product of two partners for 3-mode tensors) into a
-//      double-buffered shared-memory tile, KS observations per stage, software-prefetched through registers;
+//   1. gather the partner factor rows of the chunk into a 3-deep ring of shared-memory stages with cp.async
+//      (LDGSTS, 16 B per thread, zero-fill past the row end), KS observations per stage, two stages in flight, one
+//      barrier per stage; for 3-mode tensors both partners are staged and multiplied while forming the fragments;
 //   2. accumulate the lower triangle of G = Σ v vᵀ with FP64 tensor-core MMAs (DMMA.8x8x4, mma.sync m8n8k4 f64),
 //      8×8 tiles dealt to the warps at compile time (tiles.cuh); the rhs Σ v·r rides along as one more column
-//      of the tile when D is not a multiple of 8, else it is a DFMA side-sum;
+//      of the tile when D is even and not a multiple of 8 ("aug"), else it is a DFMA side-sum;
 //   3. rows split over several CTAs park their partial in a workspace; the last CTA to arrive adds the partials
 //      in chunk order (deterministic);
-//   4. Λ* = Λ + αG stays in the accumulator registers and is factored there as Λ* = W·Wᵀ with W UPPER triangular
-//      ("UL" Cholesky, block rows eliminated from the last to the first): per 8-row panel every warp factors the
-//      8×8 diagonal block (shuffle-based, with its inverse), the panel tiles are scaled by one DMMA pair each and
-//      parked in shared memory, and the trailing update is again a DMMA syrk with the sign flipped;
-//   5. warp 0 runs the two blocked substitutions and stores the draw x = W⁻ᵀ(z + W⁻¹·rhs) — algebraically
-//      identical, for the same z, to the reference's chol(inv(Λ*))ᵀ·z + inv(Λ*)·rhs (DESIGN.md §"draw formula").
+//   4. the Gram tiles are parked in shared memory (row-major 8×8 blocks), Λ* = Λ + αG is formed there and factored
+//      as Λ* = W·Wᵀ with W UPPER triangular ("UL" Cholesky, block rows eliminated from the last to the first): per
+//      8-row panel warp 0 factors the 8×8 diagonal block with shuffles (carrying its inverse), the panel tiles are
+//      scaled by one DMMA pair each, the trailing update is a DMMA syrk with the sign flipped, and warp 0 factors
+//      the next diagonal block while the other warps finish the update (look-ahead); y = W⁻¹·rhs rides along;
+//   5. warp 0 runs the forward substitution and stores the draw x = W⁻ᵀ(z + W⁻¹·rhs) — algebraically identical,
+//      for the same z, to the reference's chol(inv(Λ*))ᵀ·z + inv(Λ*)·rhs (DESIGN.md §"draw formula").
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -76,6 +78,19 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// the rhs Σ v·r is carried as tile column D when that column is free and 16-byte pieces never straddle it
+__host__ __device__ constexpr bool use_aug(int D) { return (D & 1) == 0 && (D & 7) != 0; }
+
 __host__ __device__ constexpr int tri(int i) { return i * (i + 1) / 2; }
 // inverse of t = tri(I) + J, 0 <= J <= I (t < 2^20)
 __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
@@ -94,61 +109,33 @@ struct RowKernel {
   using C = TileCfg<DP, NW>;
   static constexpr int NTHR = NW * 32;
   static constexpr int S = DP + 4;  // smem row pitch: ≡ 4 or 12 (mod 16) doubles → conflict-free DMMA fragment loads
-  static constexpr int OPP = NTHR / 16;                  // observations fetched per pass (16 threads per row)
-  static constexpr int PASSES = TENSOR ? (NW == 8 ? 1 : (NW == 4 ? 2 : 4)) : (NW == 8 ? 2 : (NW == 4 ? 4 : 8));
-  static constexpr int KS = OPP * PASSES;                // observations per stage
-  static constexpr int JP = (DP / 2 + 15) / 16;          // 16-byte pieces per thread per observation
+  static constexpr int OPP = NTHR / 16;          // observations fetched per pass (16 threads per factor row)
+  static constexpr int JP = (DP / 2 + 15) / 16;  // 16-byte pieces per thread per observation
   static constexpr int TPW = C::TPW;
-  static constexpr int PST = NW * TPW * 64 + DP;         // doubles per parked partial
   static constexpr int NB = C::NB;
-  static constexpr int PSZ = 64 * C::NT;                 // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
-  static constexpr int BUFSZ = 2 * KS * S + 2 * KS;
-  static constexpr int REGSZ = PSZ > BUFSZ ? PSZ : BUFSZ;  // the tiles alias the (dead) stage buffers
+  static constexpr int PST = NW * TPW * 64 + DP;  // doubles per parked partial
+  // gather ring of the row kernel
+  static constexpr int GP = NW == 8 ? 1 : (NW == 4 ? 2 : 8);  // passes per stage
+  static constexpr int KS = OPP * GP;                          // observations per stage (16)
+  static constexpr int NBUF = 3;
+  static constexpr int STG = KS * S * (TENSOR ? 2 : 1) + KS;   // doubles per stage: tile(s) + residuals
+  static constexpr int PSZ = 64 * C::NT;  // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
+  static constexpr int REGSZ = PSZ > NBUF * STG ? PSZ : NBUF * STG;  // the tiles alias the (dead) stage ring
   static constexpr int SMEM_DOUBLES = REGSZ + NB * 64 + 4 * DP + 8;
   static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
+  // register-staged loader of the statistics kernel (stats_kernel.cuh)
+  static constexpr int SPASSES = NW == 8 ? 2 : (NW == 4 ? 4 : 8);
+  static constexpr int SKS = OPP * SPASSES;
+  static constexpr int SBUFSZ = 2 * SKS * S + 2 * SKS;
 
   struct Pre {
-    double2 a[PASSES][JP];
-    double r[PASSES];
+    double2 a[SPASSES][JP];
+    double r[SPASSES];
   };
-
-  // ---- gather one stage into registers -------------------------------------------------------------------
-  static __device__ __forceinline__ void prefetch(const RowParams& p, int64_t o0, int64_t oend, int tr, int tq, Pre& pre) {
-    const int ppr = p.ld >> 1;
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ps++) {
-      const int64_t o = o0 + tr + ps * OPP;
-      const bool ok = o < oend;
-      int c0 = 0, c1 = 0;
-      double v = 0.0;
-      if (ok) {
-        c0 = __ldg(p.col0 + o);
-        if (TENSOR) c1 = __ldg(p.col1 + o);
-        v = __ldg(p.val + o);
-      }
-      pre.r[ps] = ok ? v - p.mean : 0.0;
-      const double2* r0 = reinterpret_cast<const double2*>(p.P0 + (size_t)c0 * p.ld);
-      const double2* r1 = TENSOR ? reinterpret_cast<const double2*>(p.P1 + (size_t)c1 * p.ld) : nullptr;
-#pragma unroll
-      for (int j = 0; j < JP; j++) {
-        const int pc = tq + 16 * j;
-        double2 x = make_double2(0.0, 0.0);
-        if (ok && pc < ppr) {
-          x = __ldg(r0 + pc);
-          if (TENSOR) {
-            const double2 y = __ldg(r1 + pc);
-            x.x *= y.x;
-            x.y *= y.y;
-          }
-        }
-        pre.a[ps][j] = x;
-      }
-    }
-  }
 
   static __device__ __forceinline__ void store_stage(const int D, double* buf, double* rs, int tr, int tq, const Pre& pre, bool aug) {
 #pragma unroll
-    for (int ps = 0; ps < PASSES; ps++) {
+    for (int ps = 0; ps < SPASSES; ps++) {
       const int k = tr + ps * OPP;
 #pragma unroll
       for (int j = 0; j < JP; j++) {
@@ -167,7 +154,7 @@ struct RowKernel {
   }
 
   // ---- DMMA accumulate of one stage, specialised per warp -------------------------------------------------
-  template <int W>
+  template <int W, bool PROD>
   static __device__ __forceinline__ void compute(double (&acc)[TPW][2], const double* buf, int nk4, int lane) {
     constexpr int NF = C::nfrag(W);
     constexpr int NTW = C::ntiles(W);
@@ -178,6 +165,7 @@ struct RowKernel {
         static_for<NF>([&](auto r) {
           constexpr int R = decltype(r)::value;
           f[R] = base[k4 * 4 * S + 8 * FI<C, W, R>::blk];
+          if (PROD) f[R] *= base[KS * S + k4 * 4 * S + 8 * FI<C, W, R>::blk];  // second partner (3-mode tensor)
         });
         static_for<NTW>([&](auto t) {
           constexpr int T = decltype(t)::value;
@@ -215,7 +203,7 @@ struct RowKernel {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = tid >> 4, tq = tid & 15;
     const int D = p.D;
-    const bool aug = D < DP;
+    const bool aug = use_aug(D);
     const int item = blockIdx.x;
     const int lrow = p.item_row[item];
     const int64_t obeg = p.item_beg[item];
@@ -224,9 +212,8 @@ struct RowKernel {
     const int split = p.item_split[item];
     const int64_t slot = p.slot_base + lrow;
 
-    double* bufs = smem;                    // [2][KS*S]
-    double* rss = smem + 2 * KS * S;        // [2][KS]
-    double* Tl = smem;                      // Λ* / factor tiles, alias the stage buffers after the main loop
+    double* ring = smem;                    // [NBUF][STG]: tile (KS×S), [second tile], residuals (KS)
+    double* Tl = smem;                      // Λ* / factor tiles, alias the ring after the main loop
     double* WvT = smem + REGSZ;             // inverse diagonal blocks, transposed: WvT[p][k][m] = (W_pp⁻¹)[m][k]
     double* rhs = WvT + NB * 64;            // [DP]
     double* lmu = rhs + DP;                 // Λ·μ [DP]
@@ -254,29 +241,83 @@ struct RowKernel {
       lmu[tid] = s;
     }
 
+    // ---- gather ring -----------------------------------------------------------------------------------------
     const int nst = (len + KS - 1) / KS;
-    Pre pre;
-    BDF_STAMP(1);
-    if (nst > 0) {
-      prefetch(p, obeg, oend, tr, tq, pre);
-      store_stage(D, bufs, rss, tr, tq, pre, aug);
+    const int npc = (D + 1) >> 1;  // 16-byte pieces that carry latent columns; columns ≥ 2·npc are zeroed once
+    {
+      const int c0 = 2 * npc;
+      if (c0 < DP)
+        for (int e = tid; e < NBUF * (TENSOR ? 2 : 1) * KS * (DP - c0); e += NTHR) {
+          const int row = e / (DP - c0), col = c0 + e % (DP - c0);
+          const int b = row / ((TENSOR ? 2 : 1) * KS), rr = row % ((TENSOR ? 2 : 1) * KS);
+          ring[b * STG + rr * S + col] = (TENSOR && rr >= KS && col == D) ? 1.0 : 0.0;  // second partner's aug column = 1
+        }
     }
-    __syncthreads();
+    int cn0[GP], cn1[GP];  // partner slots of the stage that is issued next
+    double rn[GP];          // its residuals (threads with tq == 0)
+    // Metadata (partner slots, values) is fetched one stage ahead of its use with clamped addresses and NO dependent
+    // instruction, so the in-order issue never waits on these loads inside the stage loop.
+    auto load_meta = [&](int s) {
+#pragma unroll
+      for (int ps = 0; ps < GP; ps++) {
+        int64_t o = obeg + (int64_t)s * KS + tr + ps * OPP;
+        if (o >= oend) o = oend - 1;
+        if (o < obeg) o = obeg;
+        cn0[ps] = __ldg(p.col0 + o);
+        if (TENSOR) cn1[ps] = __ldg(p.col1 + o);
+        rn[ps] = __ldg(p.val + o);
+      }
+    };
+    auto issue = [&](int s) {
+      double* st = ring + (s % NBUF) * STG;
+#pragma unroll
+      for (int ps = 0; ps < GP; ps++) {
+        const int k = tr + ps * OPP;
+        const bool ok = s * KS + k < len;
+        const double* src0 = p.P0 + (size_t)cn0[ps] * p.ld;
+        const double* src1 = TENSOR ? p.P1 + (size_t)cn1[ps] * p.ld : nullptr;
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+          const int pc = tq + 16 * j;
+          if (pc < npc) {
+            cp_async16(st + k * S + 2 * pc, src0 + 2 * pc, ok ? 16 : 0);
+            if (TENSOR) cp_async16(st + (KS + k) * S + 2 * pc, src1 + 2 * pc, ok ? 16 : 0);
+          }
+        }
+        if (tq == 0) {
+          const double r = ok ? rn[ps] - p.mean : 0.0;
+          st[(TENSOR ? 2 : 1) * KS * S + k] = r;
+          if (aug) st[k * S + D] = r;
+        }
+      }
+      cp_async_commit();
+    };
+    BDF_STAMP(1);
+    __syncthreads();  // ring zero-fill visible before any stage is consumed
+    if (nst > 0) { load_meta(0); issue(0); }
+    if (nst > 1) { load_meta(1); issue(1); } else cp_async_commit();
+    if (nst > 2) load_meta(2);
     for (int s = 0; s < nst; s++) {
-      const double* buf = bufs + (s & 1) * KS * S;
-      const double* rs = rss + (s & 1) * KS;
-      const bool more = s + 1 < nst;
-      if (more) prefetch(p, obeg + (int64_t)(s + 1) * KS, oend, tr, tq, pre);
+      cp_async_wait<1>();
+      __syncthreads();  // stage s has landed for every thread; everyone is done with stage s-1
+      if (s + 2 < nst) issue(s + 2); else cp_async_commit();
+      if (s + 3 < nst) load_meta(s + 3);
+      const double* buf = ring + (s % NBUF) * STG;
+      const double* rs = buf + (TENSOR ? 2 : 1) * KS * S;
       int rem = len - s * KS;
       if (rem > KS) rem = KS;
       const int nk4 = (rem + 3) >> 2;
-      warp_dispatch(warp, [&](auto w) { compute<decltype(w)::value>(acc, buf, nk4, lane); });
+      warp_dispatch(warp, [&](auto w) { compute<decltype(w)::value, TENSOR>(acc, buf, nk4, lane); });
       if (!aug && tid < DP) {
-        for (int k = 0; k < nk4 * 4; k++) bsum = fma(buf[k * S + tid], rs[k], bsum);
+        for (int k = 0; k < nk4 * 4; k++) {
+          double v = buf[k * S + tid];
+          if (TENSOR) v *= buf[(KS + k) * S + tid];
+          bsum = fma(v, rs[k], bsum);
+        }
       }
-      if (more) store_stage(D, bufs + ((s + 1) & 1) * KS * S, rss + ((s + 1) & 1) * KS, tr, tq, pre, aug);
-      __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();  // the ring is dead from here on
 
     BDF_STAMP(2);
     // ---- split rows: park the partial, last arriver reduces in chunk order -------------------------------
@@ -341,7 +382,7 @@ struct RowKernel {
         if (i < D) {
           if (j < D) v.x = fma(alpha, g.x, v.x);
           if (j + 1 < D) v.y = fma(alpha, g.y, v.y);
-        } else if (i == D) {
+        } else if (aug && i == D) {
           if (j < D) rhs[j] = fma(alpha, g.x, lmu[j]);
           if (j + 1 < D) rhs[j + 1] = fma(alpha, g.y, lmu[j + 1]);
         }
@@ -353,9 +394,10 @@ struct RowKernel {
 
     // ---- blocked UL factorisation Λ* = W·Wᵀ (W upper), block rows pb = NB-1 … 0, on the shared-memory tiles --------
     // Per panel: (b) the panel tiles are scaled, R_pJ = W_pp⁻¹·A_pJ, by one DMMA pair each; (c) the tiles above the
-    // panel get A_IJ −= R_pIᵀ·R_pJ, again DMMA; warp 0 takes the next diagonal tile first and factors it while the
-    // other warps finish the trailing update (look-ahead), so the serial 8×8 factorisations overlap the updates.
+    // panel get A_IJ −= R_pIᵀ·R_pJ, again DMMA, one block row per warp at a time; warp 0 takes the next diagonal tile
+    // first and factors it while the other warps finish the trailing update (look-ahead).
     bool bad = false;
+    const int fo = 8 * (lane & 3) + (lane >> 2);  // fragment offset in a row-major 8×8 tile: A[m][k]=B[k][m]=tile[k][m]
     auto factor_diag = [&](int pb) {
       // A_pp = W·Wᵀ by elimination from the last column to the first, in the DMMA accumulator layout (lane = 4·row+q
       // holds columns 2q, 2q+1); an identity block carried along ends up as W⁻¹, stored transposed in WvT[pb].
@@ -363,7 +405,7 @@ struct RowKernel {
       const double2 av = *reinterpret_cast<const double2*>(Tl + 64 * (tri(pb) + pb) + 2 * lane);
       double a0 = av.x, a1 = av.y;
       double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
-#pragma unroll
+#pragma unroll 1
       for (int j = 7; j >= 0; j--) {
         const int jq = j >> 1;
         const double sel = (j & 1) ? a1 : a0;
@@ -388,20 +430,21 @@ struct RowKernel {
       WvT[pb * 64 + (2 * q) * 8 + r] = e0;
       WvT[pb * 64 + (2 * q + 1) * 8 + r] = e1;
     };
-    // fragment of a row-major 8×8 tile as DMMA A (row.col: A[m][k]=tile[k][m]) or B (B[k][n]=tile[k][n]) operand, k-half h
-    const int fo = 8 * (lane & 3) + (lane >> 2);
-    auto update_tile = [&](int pb, int t) {
-      int I, J;
-      tri_coords(t, I, J);
-      const double* RI = Tl + 64 * (tri(pb) + I) + fo;
-      const double* RJ = Tl + 64 * (tri(pb) + J) + fo;
-      double2 cv = *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane);
-      double c2[2] = {cv.x, cv.y};
-      dmma884(c2, -RI[0], RJ[0]);
-      dmma884(c2, -RI[32], RJ[32]);
-      *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = make_double2(c2[0], c2[1]);
+    // trailing update of block row I above panel pb: tiles (I, J), J = j0 … I
+    auto update_row = [&](int pb, int I, int j0, int j1) {
+      const double* Pp = Tl + 64 * tri(pb) + fo;
+      const double na0 = -Pp[64 * I], na1 = -Pp[64 * I + 32];
+      double* trow = Tl + 64 * tri(I) + 2 * lane;
+#pragma unroll 2
+      for (int J = j0; J <= j1; J++) {
+        const double b0 = Pp[64 * J], b1 = Pp[64 * J + 32];
+        const double2 cv = *reinterpret_cast<const double2*>(trow + 64 * J);
+        double c2[2] = {cv.x, cv.y};
+        dmma884(c2, na0, b0);
+        dmma884(c2, na1, b1);
+        *reinterpret_cast<double2*>(trow + 64 * J) = make_double2(c2[0], c2[1]);
+      }
     };
-
     // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
     // rhs[c] −= Σ_k R_J[k][c]·y_J[k] for c < 8J. One warp; rides along with the trailing update.
     auto backsub_step = [&](int J, bool update) {
@@ -445,20 +488,25 @@ struct RowKernel {
         }
       }
       __syncthreads();
-      // (c) trailing update of tiles t < tri(pb) (block rows < pb); warp 0: next diagonal tile first, then factor it
-      const int ntr = tri(pb);
+      // (c) trailing update of block rows I < pb; rows are dealt to warps 1…NW-1 in a snake so the triangle balances
       if (NW == 1) {
         backsub_step(pb, true);
-        for (int t = 0; t < ntr; t++) update_tile(pb, t);
+        for (int I = 0; I < pb; I++) update_row(pb, I, 0, I);
         __syncwarp();
         factor_diag(pb - 1);
       } else if (warp == 0) {
-        update_tile(pb, ntr - 1);
+        update_row(pb, pb - 1, pb - 1, pb - 1);
         __syncwarp();
         factor_diag(pb - 1);
       } else {
         if (warp == 1) backsub_step(pb, true);
-        for (int t = warp - 1; t < ntr - 1; t += NW - 1) update_tile(pb, t);
+        constexpr int NWC = NW > 1 ? NW - 1 : 1;
+        for (int n = 0; n < pb; n++) {
+          const int I = pb - 1 - n;
+          const int ph = n % (2 * NWC);
+          const int wo = 1 + (ph < NWC ? ph : 2 * NWC - 1 - ph);
+          if (wo == warp) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
+        }
       }
       __syncthreads();
     }
@@ -508,7 +556,7 @@ struct RowKernel {
 };
 
 template <class K>
-__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? 16 : (K::NW == 4 ? 4 : 2))) row_kernel(const RowParams p) {
+__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? 16 : (K::NW == 4 ? (K::TENSOR ? 4 : 6) : (K::TENSOR ? 2 : 3)))) row_kernel(const RowParams p) {
   extern __shared__ __align__(16) double smem_dyn[];
   K::run(p, smem_dyn);
 }

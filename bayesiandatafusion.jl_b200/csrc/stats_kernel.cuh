@@ -5,14 +5,37 @@
 
 namespace bdf {
 
+// DMMA accumulate over a stage laid out with the statistics kernel's own stage height
+template <class K, int W>
+__device__ __forceinline__ void stats_compute(double (&acc)[K::TPW][2], const double* buf, int nk4, int lane) {
+  using C = typename K::C;
+  constexpr int NF = C::nfrag(W);
+  constexpr int NTW = C::ntiles(W);
+  if constexpr (NTW > 0) {
+    const double* base = buf + (lane & 3) * K::S + (lane >> 2);
+    for (int k4 = 0; k4 < nk4; k4++) {
+      double f[NF];
+      static_for<NF>([&](auto r) {
+        constexpr int R = decltype(r)::value;
+        f[R] = base[k4 * 4 * K::S + 8 * FI<C, W, R>::blk];
+      });
+      static_for<NTW>([&](auto t) {
+        constexpr int T = decltype(t)::value;
+        using ti = TI<C, W, T>;
+        dmma884(acc[T], f[ti::fa], f[ti::fb]);
+      });
+    }
+  }
+}
+
 // ---- statistics: each CTA reduces a contiguous range of rows into a dense packed partial ---------------------
 template <class K>
 __global__ void __launch_bounds__(K::NTHR) stats_kernel(const double* __restrict__ U, const double* __restrict__ uhat, int ld, int D,
                                                         int64_t slot0, int64_t nrows, int64_t rows_per_blk, double* __restrict__ ws) {
   extern __shared__ __align__(16) double smem_dyn[];
-  constexpr int KS = K::KS, S = K::S, DP = K::DP, OPP = K::OPP, PASSES = K::PASSES, JP = K::JP, TPW = K::TPW;
+  constexpr int KS = K::SKS, S = K::S, DP = K::DP, OPP = K::OPP, PASSES = K::SPASSES, JP = K::JP, TPW = K::TPW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tr = tid >> 4, tq = tid & 15;
-  const bool aug = D < DP;
+  const bool aug = use_aug(D);
   double* bufs = smem_dyn;
   double* rss = smem_dyn + 2 * KS * S;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_blk;
@@ -66,7 +89,7 @@ __global__ void __launch_bounds__(K::NTHR) stats_kernel(const double* __restrict
     int64_t rem = len - (int64_t)s * KS;
     if (rem > KS) rem = KS;
     const int nk4 = (int)((rem + 3) >> 2);
-    K::warp_dispatch(warp, [&](auto w) { K::template compute<decltype(w)::value>(acc, buf, nk4, lane); });
+    K::warp_dispatch(warp, [&](auto w) { stats_compute<K, decltype(w)::value>(acc, buf, nk4, lane); });
     if (!aug && tid < DP)
       for (int k = 0; k < nk4 * 4; k++) bsum = fma(buf[k * S + tid], rs[k], bsum);
     if (more) K::store_stage(D, bufs + ((s + 1) & 1) * KS * S, rss + ((s + 1) & 1) * KS, tr, tq, pre, aug);
