@@ -35,6 +35,7 @@ SIGNATURES = {
     "bdf_step_nw_stats": (C.c_int, [H, C.c_int]),
     "bdf_step_nw_draw": (C.c_int, [H, C.c_int]),
     "bdf_sweep": (C.c_int, [H, C.c_int]),
+    "bdf_advance_sweep": (C.c_int, [H]),
     "bdf_get_hyper": (C.c_int, [H, C.c_int, c_dp, c_dp]),
     "bdf_set_hyper": (C.c_int, [H, C.c_int, c_dp, c_dp]),
     "bdf_debug_row_noise": (C.c_int, [H, C.c_int, C.c_uint64, c_dp]),

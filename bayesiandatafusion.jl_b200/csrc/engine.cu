@@ -649,6 +649,8 @@ int bdf_sweep(bdf_t* h, int nsweeps) {
   return BDF_OK;
 }
 
+int bdf_advance_sweep(bdf_t* h) { CHECK_H(); h->sweep++; return BDF_OK; }
+
 int bdf_get_hyper(bdf_t* h, int entity, double* mu, double* Lambda) {
   CHECK_H(); CHECK_ENT(entity);
   CU(cudaSetDevice(h->device));

@@ -156,6 +156,9 @@ class Engine:
     def sweep(self, n: int = 1):
         self._ck(self.lib.bdf_sweep(self.h, n))
 
+    def advance_sweep(self):
+        self._ck(self.lib.bdf_advance_sweep(self.h))
+
     def get_hyper(self, entity: int):
         mu = np.zeros(self.D)
         Lam = np.zeros((self.D, self.D), order="F")

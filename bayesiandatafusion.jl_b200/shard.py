@@ -1,0 +1,104 @@
+"""Multi-GPU plumbing: one process per GPU, rows of every entity dealt cyclically to ranks (row i → rank i % world, the
+reference's worker shards `i:Nprocs:N`, src/sampling.jl:154). Each half-sweep a rank samples only its own rows; the
+collectives are torch.distributed's (NCCL over NVLink on GPUs, gloo in the CPU tests):
+
+  all-gather of the freshly sampled factor slice  — replaces the per-half-sweep broadcast of `sample_m`, src/sampling.jl:165
+  all-reduce of the (1 + D + D²) Normal-Wishart statistics — the reductions of src/sampling.jl:117-119
+
+The device buffers belong to libbdf_b200.so; they are wrapped zero-copy as torch tensors through the CUDA array interface.
+`ShardPlan` is pure host logic (which rank owns which row, where a row lives in the slot-ordered buffer) and is what the
+gloo tests exercise together with the collective layout.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Slot layout of an entity with `count` rows over `world` ranks: row i (0-based) lives at slot
+    (i % world) * nper + i // world, so every rank's rows are one contiguous block of `nper` slots (the last block may
+    be partly padding) and an all-gather of equal-sized blocks assembles the whole factor matrix."""
+    count: int
+    world: int
+
+    @property
+    def nper(self) -> int:
+        return (self.count + self.world - 1) // self.world
+
+    def owner(self, i):
+        return np.asarray(i) % self.world
+
+    def slot(self, i):
+        i = np.asarray(i)
+        return (i % self.world) * self.nper + i // self.world
+
+    def nlocal(self, rank: int) -> int:
+        return max(0, (self.count - rank + self.world - 1) // self.world)
+
+    def local_rows(self, rank: int):
+        return np.arange(rank, self.count, self.world)
+
+    def to_slots(self, U):
+        """(count, D) row-ordered matrix → (world*nper, D) slot-ordered buffer (padding rows zero)."""
+        U = np.asarray(U)
+        out = np.zeros((self.world * self.nper,) + U.shape[1:], dtype=U.dtype)
+        out[self.slot(np.arange(self.count))] = U
+        return out
+
+    def from_slots(self, S):
+        return np.asarray(S)[self.slot(np.arange(self.count))]
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can view a raw device pointer without copying."""
+
+    def __init__(self, ptr: int, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def device_view(ptr: int, shape, device):
+    import torch
+
+    return torch.as_tensor(_DevArray(ptr, shape), device=device)
+
+
+class DistributedSweep:
+    """Drives device-resident Gibbs sweeps over `world` GPUs: the loop body of src/macau.jl:96-134 with the collectives
+    between the kernels. With world == 1 it degenerates to the same kernel sequence without communication."""
+
+    def __init__(self, engine, entities, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.eng = engine
+        self.entities = list(entities)
+        self.world = engine.world
+        self.group = group
+        self.dist = dist if engine.world > 1 else None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.views = {}
+        for e in self.entities:
+            ptr, nper, ld = engine.factors_dev(e)
+            sptr, scount = engine.stats_dev(e)
+            self.views[e] = (device_view(ptr, (engine.world * nper * ld,), dev), nper * ld, device_view(sptr, (scount,), dev))
+
+    def half_sweep(self, e):
+        eng = self.eng
+        eng.step_sample(e)
+        U, blk, stats = self.views[e]
+        if self.dist is not None:
+            mine = U[eng.rank * blk:(eng.rank + 1) * blk]
+            self.dist.all_gather_into_tensor(U, mine, group=self.group)
+        eng.step_nw_stats(e)
+        if self.dist is not None:
+            self.dist.all_reduce(stats, group=self.group)
+        eng.step_nw_draw(e)
+
+    def sweep(self, n: int = 1):
+        for _ in range(n):
+            for e in self.entities:
+                self.half_sweep(e)
+            self.eng.advance_sweep()

@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — Gibbs sweeps/sec on the Netflix-scale BPMF workload of BASELINE.json (configs[1]: 480k users × 17.8k items,
+100M ratings), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--latent D] [--scale S] [--impl ours|reference]
+
+A "step" is one Gibbs sweep = loop body of src/macau.jl:96-134 for BPMF: for each entity {row draws → Normal-Wishart
+statistics → (mu, Lambda) draw}. Default workload: D=100 (the configuration BASELINE.json's target is quoted on).
+
+  value         device-resident sweeps/s (inputs in HBM, Philox noise, CUDA events on the engine's stream, max over ranks)
+  e2e           sweeps/s through the public host API (`macau()`-style sequence of C-ABI calls with HOST buffers: mu/Lambda
+                H2D, Normal-Wishart statistics and hyper-parameters D2H, test-set ids H2D and predictions D2H every sweep)
+  roofline      the row-draw kernel: algorithmic FP64 flops per launch (SURVEY §8d formula) ÷ its CUDA-event duration,
+                against the FP64 DMMA peak measured on this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no
+                FP64 figure)
+  cpu_baseline  the restated-reference CPU oracle (oracle/, C + OpenMP, cyclic row shards like src/sampling.jl:154) timed
+                on a bounded 1/100-scale sample of the same generator, extrapolated linearly in nnz — a reported baseline
+--impl reference times only that CPU arm (Julia is not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_USERS, N_ITEMS, NNZ = 480_000, 17_800, 100_000_000
+ALPHA = 1.5
+SEED = 20161017 + 1  # seed 20161017 + config index
+FP64_PEAK_FALLBACK = 37.07  # TFLOP/s, DMMA, measured on this pool (profiles/fp64_peak_r01.json)
+
+
+def synth(n1, n2, nnz, seed, skew=2.5, d0=8, chunk=10_000_000):
+    """Seeded synthetic ratings: skewed marginals idx = floor(N·u^skew) (heavy-tailed degrees, duplicates allowed), planted
+    rank-d0 model + N(0, 1/alpha) noise. Returns 1-based ids (nnz×2, Fortran order) and values."""
+    rng = np.random.default_rng(seed)
+    U0 = (rng.standard_normal((n1, d0)) / np.sqrt(np.sqrt(d0))).astype(np.float32)
+    V0 = (rng.standard_normal((n2, d0)) / np.sqrt(np.sqrt(d0))).astype(np.float32)
+    ids = np.empty((nnz, 2), dtype=np.int64, order="F")
+    vals = np.empty(nnz, dtype=np.float64)
+    for a in range(0, nnz, chunk):
+        b = min(nnz, a + chunk)
+        i1 = np.minimum((n1 * rng.random(b - a) ** skew).astype(np.int64), n1 - 1)
+        i2 = np.minimum((n2 * rng.random(b - a) ** skew).astype(np.int64), n2 - 1)
+        ids[a:b, 0] = i1 + 1
+        ids[a:b, 1] = i2 + 1
+        vals[a:b] = np.einsum("ij,ij->i", U0[i1], V0[i2]) + rng.standard_normal(b - a) / np.sqrt(ALPHA)
+    return ids, vals
+
+
+def alg_flops(nnz, n_rows, D, K=2):
+    """per mode nnz·(D(D+1) + 2D + (K−2)·D) + N_m·(D³/3 + 2D²)."""
+    return nnz * (D * (D + 1) + 2 * D + (K - 2) * D) + n_rows * (D ** 3 / 3.0 + 2 * D * D)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": reasons}
+
+
+def fp64_peak():
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))
+        return float(j["dmma_sustained_tflops"]), "measured: profiles/fp64_peak_r01.json (DMMA.8x8x4 loop, this pool's B200)"
+    except Exception:
+        return FP64_PEAK_FALLBACK, "fallback constant (profiles/fp64_peak_r01.json missing)"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_sweeps(D, scale, steps, warmup, threads=None):
+    """The restated-reference CPU path (oracle) on a bounded sample: same generator at `scale`, all host threads."""
+    from oracle import oracle as orc
+
+    threads = threads or orc.max_threads()
+    # both modes shrink by `scale`, so the per-row degrees (208 / 5618 on average) and hence the per-row work stay those
+    # of the full workload and the cost is exactly linear in the sample size
+    n1, n2, nnz = max(64, int(N_USERS * scale)), max(16, int(N_ITEMS * scale)), max(1000, int(NNZ * scale))
+    ids, vals = synth(n1, n2, nnz, SEED)
+    dims = [n1, n2]
+    idf = orc.FastIDF(ids, vals, dims)
+    rng = np.random.default_rng(1)
+    U = [np.zeros((d, D)) for d in dims]
+    mu = [np.zeros(D), np.zeros(D)]
+    Lam = [5.0 * np.eye(D), 5.0 * np.eye(D)]
+    mean = float(vals.mean())
+
+    def sweep():
+        for m in range(2):
+            Z = rng.standard_normal((dims[m], D))
+            orc.sample_latent_all(idf, m, U, ALPHA, mean, mu[m], Lam[m], Z, nshards=threads)
+            N, NU, NS = orc.nw_stats(U[m])
+            mu_N, beta_N, T_N, nu_N = orc.cond_normal_wishart(N, NU, NS, np.zeros(D), 2.0, np.eye(D), float(D))
+            mu[m], Lam[m] = orc.nw_rand(mu_N, beta_N, T_N, orc.bartlett_factor(rng, D, nu_N), rng.standard_normal(D))
+
+    for _ in range(warmup):
+        sweep()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sweep()
+    dt = (time.perf_counter() - t0) / steps
+    full = (1.0 / dt) * (nnz / NNZ)  # sweeps/s extrapolated linearly in nnz to the full workload
+    return {"value": full, "unit": "sweeps/s", "cores": threads, "kind": "port",
+            "sample": f"1/{round(1 / scale)}-scale sample of the same generator ({n1} users x {n2} items, {nnz} ratings, D={D}): "
+                      f"{dt:.3f} s/sweep measured, sweeps/s extrapolated linearly in nnz to 100M ratings"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb, dt = cpu_sweeps(args.latent, args.cpu_scale, steps, min(warmup, 1))
+    line = {
+        "impl": "reference", "metric": f"Gibbs sweeps/sec (Netflix-100M, D={args.latent})", "value": cb["value"], "unit": "sweeps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1), "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BPMF synthetic Netflix-scale {N_USERS}x{N_ITEMS}, {NNZ} ratings, D={args.latent}"},
+        "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated-reference CPU path (oracle/, C+OpenMP); Julia is not installable in this image",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    import bdf_b200
+    from bdf_b200.shard import DistributedSweep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D = args.latent
+    n1, n2, nnz = max(64, int(N_USERS * args.scale)), N_ITEMS, max(1000, int(NNZ * args.scale))
+    ids, vals = synth(n1, n2, nnz, SEED)
+    ntest = min(1_000_000, nnz // 100)
+    test_ids, test_vals = ids[:ntest], vals[:ntest]
+    tr_ids, tr_vals = ids[ntest:], vals[ntest:]
+    nnz_tr = nnz - ntest
+    mean = float(tr_vals.mean())
+
+    # a non-default torch stream is made current and handed to the engine, so torch.cuda.Event timing, the engine's
+    # kernels and torch.distributed's collectives are all ordered on ONE stream (the default stream's handle is NULL,
+    # which bdf_set_stream reads as "use the engine's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = bdf_b200.Engine(D, device=local, rank=rank, world=world)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_seed(SEED)
+    e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
+    rel = eng.add_relation([e1, e2], tr_ids, tr_vals)
+    eng.set_relation_params(rel, ALPHA, mean)
+    ds = DistributedSweep(eng, [e1, e2])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident sweeps ("value") --------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ds.sweep(1)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    ds.sweep(args.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = args.steps / (ms / 1e3)
+
+    # ---- the row-draw kernel alone (roofline), CUDA events around each launch ---------------------------------------
+    peak, peak_src = fp64_peak()
+    kt = {e1: [], e2: []}
+    for _ in range(max(2, min(args.steps, 5))):
+        for e in (e1, e2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.step_sample(e)
+            b.record()
+            b.synchronize()
+            kt[e].append(a.elapsed_time(b))
+            if world > 1:
+                ds.half_sweep(e)  # keep the replicas consistent
+    rows = {e1: n1, e2: n2}
+    fl = {e: alg_flops(nnz_tr, rows[e], D) / world for e in (e1, e2)}
+    t_k = {e: float(np.mean(kt[e][1:])) for e in (e1, e2)}
+    tot_fl, tot_t = fl[e1] + fl[e2], (t_k[e1] + t_k[e2]) / 1e3
+    achieved = tot_fl / tot_t / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "row_kernel (FP64 DMMA.8x8x4 per-row draw)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_flops_per_launch": {"users": fl[e1], "items": fl[e2]}, "ms_per_launch": {"users": t_k[e1], "items": t_k[e2]},
+        "share_of_step": (t_k[e1] + t_k[e2]) / (ms / args.steps),
+    }
+
+    # ---- end to end through the host-facing C ABI ("e2e") -----------------------------------------------------------
+    e2e = None
+    if world == 1:
+        hyper = {e: (np.zeros(D), 5.0 * np.eye(D)) for e in (e1, e2)}
+        mu0, WI = np.zeros(D), np.eye(D)
+        pin_ids = torch.from_numpy(np.asfortranarray(test_ids).T.copy()).pin_memory()  # (2, ntest) C-order = ntest×2 column-major
+        pin_ids_np = pin_ids.numpy().T
+        acc = np.zeros(ntest)
+
+        def host_sweep():
+            for e in (e1, e2):
+                mu, Lam = hyper[e]
+                eng.sample_mode(e, mu, Lam, None)                 # H2D mu, Lambda; row draws on the device
+                N, NU, NS = eng.nw_stats(e)                       # D2H 1+D+D² doubles
+                hyper[e] = eng.nw_sample(e, mu0, 2.0, WI, float(D))  # H2D hyper-priors, D2H (mu, Lambda)
+            eng.advance_sweep()
+            return eng.predict(rel, pin_ids_np)                   # H2D test ids, D2H predictions
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            host_sweep()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            acc += host_sweep()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        rmse = float(np.sqrt(np.mean((acc / args.steps - test_vals) ** 2)))
+        h2d = 2 * (D + D * D) * 8 + 2 * (D + D * D) * 8 + ntest * 2 * 8
+        d2h = 2 * (1 + D + D * D) * 8 + 2 * (D + D * D) * 8 + ntest * 8
+        e2e = {"value": 1.0 / dt, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "test_rmse_running_mean": rmse,
+               "path": "bdf_sample_mode + bdf_nw_stats + bdf_nw_sample per entity, bdf_predict on the held-out 1% per sweep (host buffers)"}
+    else:
+        e2e = {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "path": "multi-GPU runs are device-resident (DistributedSweep); the host-buffer path is measured at N=1"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_sweeps(D, args.cpu_scale, 1, 0)
+
+    if rank == 0:
+        line = {
+            "metric": f"Gibbs sweeps/sec (Netflix-100M, D={D})", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BPMF synthetic Netflix-scale {n1}x{n2}, {nnz_tr} training ratings (+{ntest} held out), D={D}",
+                       "alpha": ALPHA, "skew": 2.5, "seed": SEED, "noise": "device Philox",
+                       "l2": "inputs (ratings 1.2 GB/mode + factors) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"rows cyclic over {world} GPU(s); all-gather factors + all-reduce NW stats per half-sweep" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "fp64_frac_of_peak_whole_sweep": (2 * alg_flops(nnz_tr, 0, D) + alg_flops(0, n1 + n2, D)) / (ms / args.steps / 1e3) / 1e12 / peak,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--latent", type=int, default=100)
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 480k-user / 100M-rating workload (1.0 = the judged config)")
+    ap.add_argument("--cpu-scale", type=float, default=0.01, help="bounded sample for the CPU arm")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,9 @@ int bdf_step_nw_stats(bdf_t* h, int entity);
 int bdf_step_nw_draw(bdf_t* h, int entity);
 /* Whole sweeps on one GPU (world == 1): for each entity {sample, stats, draw}. */
 int bdf_sweep(bdf_t* h, int nsweeps);
+/* Advance the Philox sweep counter by one (drivers that sequence the bdf_step_* / host-pointer entries themselves call
+ * this once per Gibbs iteration; bdf_sweep does it internally). */
+int bdf_advance_sweep(bdf_t* h);
 int bdf_get_hyper(bdf_t* h, int entity, double* mu, double* Lambda);
 int bdf_set_hyper(bdf_t* h, int entity, const double* mu, const double* Lambda);
 /* The standard normals the device Philox stream yields for (entity, sweep): D×N column-major. Lets a test feed
