@@ -6,8 +6,8 @@ C ABI of libbdf_b200.so (include/bdf_b200.h). Importing this package does not ne
 from . import _lib  # noqa: F401
 from .engine import BDFError, Engine  # noqa: F401
 from .macau import AUC_ROC, macau, read_binary_float32, write_binary_matrix  # noqa: F401
-from .relation_data import (Entity, IndexedDF, Relation, RelationData, assignToTest, setPrecision,  # noqa: F401
-                            setTest)
+from .relation_data import (Entity, IndexedDF, Relation, RelationData, SparseBinMatrix, assignToTest,  # noqa: F401
+                            setPrecision, setTest)
 
 __all__ = ["Engine", "BDFError", "macau", "RelationData", "Relation", "Entity", "IndexedDF", "assignToTest", "setTest",
-           "setPrecision", "AUC_ROC"]
+           "setPrecision", "AUC_ROC", "SparseBinMatrix"]

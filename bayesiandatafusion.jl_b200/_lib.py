@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libbdf_b200.so")
 c_dp = C.POINTER(C.c_double)
 c_i64p = C.POINTER(C.c_int64)
 c_ip = C.POINTER(C.c_int)
+c_i32p = C.POINTER(C.c_int32)
 H = C.c_void_p
 
 # name -> (restype, argtypes); must list every symbol include/bdf_b200.h declares (tests/test_abi.py checks)
@@ -44,6 +45,19 @@ SIGNATURES = {
     "bdf_synchronize": (C.c_int, [H]),
     "bdf_launch_count": (C.c_int64, [H]),
     "bdf_predict": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp]),
+    "bdf_set_features_sbm": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, c_i32p, c_i32p]),
+    "bdf_debug_features_csr": (C.c_int, [H, C.c_int, C.c_int, c_i32p, c_i32p]),
+    "bdf_spmm": (C.c_int, [H, C.c_int, C.c_int, c_dp, C.c_int, c_dp]),
+    "bdf_ata_mul": (C.c_int, [H, C.c_int, c_dp, C.c_double, c_dp]),
+    "bdf_cg_solve": (C.c_int, [H, C.c_int, c_dp, C.c_int, C.c_double, C.c_double, C.c_int64, c_dp, c_ip]),
+    "bdf_set_beta": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_get_beta": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_update_uhat": (C.c_int, [H, C.c_int, c_dp, c_dp]),
+    "bdf_sample_mode_uhat": (C.c_int, [H, C.c_int, c_dp, c_dp]),
+    "bdf_nw_stats_uhat": (C.c_int, [H, C.c_int, c_dp, c_dp, c_dp]),
+    "bdf_beta_gram": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_sample_beta": (C.c_int, [H, C.c_int, c_dp, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip]),
+    "bdf_sample_lambda_beta": (C.c_int, [H, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, c_dp, c_dp]),
 }
 
 _lib = None

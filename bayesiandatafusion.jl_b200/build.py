@@ -52,7 +52,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if ptxas_v else []
-    jobs = [(os.path.join(CSRC, "engine.cu"), os.path.join(OBJ, "engine.o"), extra)]
+    jobs = [(os.path.join(CSRC, "engine.cu"), os.path.join(OBJ, "engine.o"), extra),
+            (os.path.join(CSRC, "features.cu"), os.path.join(OBJ, "features.o"), extra)]
     for dp in DPS:
         jobs.append((os.path.join(CSRC, "row_inst.cu"), os.path.join(OBJ, f"row_inst_{dp}.o"), [f"-DBDF_DP={dp}", *extra]))
     jobs = [j for j in jobs if force or _stale(j[1], deps)]
@@ -62,7 +63,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
                 print(f"[bdf build] {os.path.basename(obj)}")
                 if ptxas_v:
                     print(log)
-    objs = [os.path.join(OBJ, "engine.o")] + [os.path.join(OBJ, f"row_inst_{dp}.o") for dp in DPS]
+    objs = [os.path.join(OBJ, "engine.o"), os.path.join(OBJ, "features.o")] + [os.path.join(OBJ, f"row_inst_{dp}.o") for dp in DPS]
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

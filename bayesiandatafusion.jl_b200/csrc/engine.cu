@@ -1,5 +1,6 @@
 // libbdf_b200.so — C ABI (include/bdf_b200.h) over the sm_100a kernels. No CPU fallback: every numeric entry
 // launches device kernels; host code only validates arguments, moves buffers and builds launch metadata.
+#include "../../include/bdf_b200.h"
 #include "engine.cuh"
 
 #include <algorithm>
@@ -15,24 +16,6 @@
 using namespace bdf;
 
 static thread_local std::string g_create_err;
-
-#define CU(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
-      return BDF_ERR_CUDA;                                                                         \
-    }                                                                                              \
-  } while (0)
-#define FAIL(code, msg)  \
-  do {                   \
-    h->err = (msg);      \
-    return (code);       \
-  } while (0)
-#define CHECK_H()  \
-  if (!h) return BDF_ERR_INVALID
-#define CHECK_ENT(e) \
-  if ((e) < 0 || (e) >= (int)h->ents.size()) FAIL(BDF_ERR_INVALID, "entity id out of range")
 
 // ---- kernel dispatch over the padded latent dimension (instances live in row_inst.cu, one object per DP) ----------
 #define DP_CASES(X) X(8) X(16) X(24) X(32) X(40) X(48) X(56) X(64) X(72) X(80) X(88) X(96) X(104) X(112) X(120) X(128)
@@ -284,6 +267,22 @@ void prep_lambda(bdf_t* h, const double* Lambda, const double* mu, int D, int DP
   prep_lambda_kernel<<<8, 256, 0, h->stream>>>(Lambda, mu, D, DP, LT, lmu);
 }
 
+}  // namespace
+
+// statistics of an arbitrary row-major (rows × ld) buffer into a [count, colsum(D), Gram(D×D)] stats block (features.cu uses it for betaᵀbeta)
+int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, int64_t nrows, double* stats) {
+  const int nblk = launch_stats_partials(h, X, sub, slot0, nrows);
+  if (nblk < 0) return nblk;
+  stats_reduce_kernel<<<8, 256, 0, h->stream>>>(h->ws, nblk, h->D, (double)nrows, stats);
+  h->launches++;
+  CU(cudaGetLastError());
+  return BDF_OK;
+}
+int bdf_check_err_flag(bdf_t* h) { return check_err_flag(h); }
+int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
+
+namespace {
+
 int stats_entity(bdf_t* h, int entity) {
   EntityS& e = h->ents[entity];
   const int nblk = launch_stats_partials(h, e.U, nullptr, (int64_t)h->rank * e.Nper, e.nlocal);
@@ -293,6 +292,12 @@ int stats_entity(bdf_t* h, int entity) {
   CU(cudaGetLastError());
   return BDF_OK;
 }
+
+}  // namespace
+int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev) {
+  return sample_entity(h, entity, mu_dev, mu_ld, Lambda_dev, Z_dev);
+}
+namespace {
 
 int draw_entity(bdf_t* h, int entity, const double* mu0_dev, double b0, const double* Tinv_dev, double nu, const double* A_dev,
                 const double* z_dev) {
@@ -354,6 +359,7 @@ int bdf_destroy(bdf_t* h) {
   cudaStreamSynchronize(h->stream);
   for (auto& e : h->ents) {
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
+    cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
   }
   for (auto& r : h->rels)
     for (int m = 0; m < r.K; m++) {

@@ -51,9 +51,38 @@ struct EntityS {
   std::vector<double> mu0, WI;
   double b0 = 2.0, nu0 = 0.0;
   std::vector<std::pair<int, int>> uses;  // (relation, mode) pairs this entity takes part in
+  // side features (Macau): sparse binary F (N × numF) as CSR and CSC index lists, link matrix beta (numF × ld, row-major)
+  int64_t numF = 0, fnnz = 0;
+  int64_t* f_rowptr = nullptr;  // [N+1]   rows of F
+  int32_t* f_colind = nullptr;  // [fnnz]  0-based feature ids, stored order = stable sort of the COO list by row
+  int64_t* f_colptr = nullptr;  // [numF+1] rows of Fᵀ
+  int32_t* f_rowind = nullptr;  // [fnnz]  0-based row ids, stored order = stable sort of the COO list by column
+  double* beta = nullptr;       // numF × ld
+  double* uhat = nullptr;       // slots × ld, (F·beta)
+  double* cgbuf = nullptr;      // CG work vectors
+  double* btb = nullptr;        // [numF, colsum(D), betaᵀbeta(D×D)] in the stats layout
 };
 
 }  // namespace bdf
+
+// shared by the translation units that implement the C ABI
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+      return BDF_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+#define FAIL(code, msg)  \
+  do {                   \
+    h->err = (msg);      \
+    return (code);       \
+  } while (0)
+#define CHECK_H()  \
+  if (!h) return BDF_ERR_INVALID
+#define CHECK_ENT(e) \
+  if ((e) < 0 || (e) >= (int)h->ents.size()) FAIL(BDF_ERR_INVALID, "entity id out of range")
 
 struct bdf_handle {
   int device = 0, D = 0, ld = 0, DP = 0, NW = 1, rank = 0, world = 1;

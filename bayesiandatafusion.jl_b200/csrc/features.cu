@@ -1,0 +1,675 @@
+// Macau link-matrix (beta) path on the device — SURVEY §8a A8–A15:
+//   sparse-binary feature matrix F as CSR + CSC index lists  (SparseBinMatrix src/parallel_matrix.jl:9-24,
+//                                                              SparseBinMatrixCSR src/sparsebin_csr.jl:6-37)
+//   Y = F·X, Y = Fᵀ·X for D right-hand sides at once          (A_mul_B! / At_mul_B! :242-267, sparsebin_csr.jl:49-63)
+//   (FᵀF + λI)·X                                               (AtA_mul_B!, src/parallel_cg.jl:7-14)
+//   batched conjugate gradients with per-column scalars/masks   (cg_AtA src/parallel_cg.jl:63-94, solve_cg2 parallel_matrix.jl:488-507)
+//   sample_beta / update_beta! / sample_lambda_beta             (src/sampling.jl:291-312, 361-370, 136-142)
+//   F_mul_beta → uhat, mu .+ uhat                               (src/RelationData.jl:314-320, src/macau.jl:102-104)
+// A 0/1 matrix needs no multiplies: both products are gathers of D-vectors summed in stored order (the reference's
+// order), one warp per output row, indices read 128 bits at a time, the D columns spread over the lanes.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/bdf_b200.h"
+#include "engine.cuh"
+#include "nw_device.cuh"
+#include "row_kernel.cuh"
+
+using namespace bdf;
+
+int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, int64_t nrows, double* stats);
+int bdf_check_err_flag(bdf_t* h);
+int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
+
+namespace {
+
+inline int grid_for(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- Y[r,:] = init + Σ_{e in row r} X[idx[e],:]  (one warp per row, lanes over the columns, sum in stored order) -----
+// init: 0, or lam·P[r,:] (the "+λx" of AtA_mul_B!, src/parallel_cg.jl:10-12 — added last, as the reference does).
+__global__ void __launch_bounds__(256) spbin_gather_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nrows,
+                                                           const double* __restrict__ X, double* __restrict__ Y, int ld, double lam,
+                                                           const double* __restrict__ P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int npair = ld >> 1;  // double2 pieces per row (ld is a multiple of 4)
+  for (int64_t r = warp0; r < nrows; r += nwarps) {
+    const int64_t b = ptr[r], e = ptr[r + 1];
+    double2 acc[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};  // ld ≤ 128 → ≤ 64 pairs → ≤ 2 per lane
+    for (int64_t o = b; o < e; o += 32) {
+      const int n = (int)min((int64_t)32, e - o);
+      const int mine = lane < n ? __ldg(idx + o + lane) : 0;
+      for (int j = 0; j < n; j++) {
+        const int c = __shfl_sync(0xffffffffu, mine, j);
+        const double2* src = reinterpret_cast<const double2*>(X + (size_t)c * ld);
+        if (lane < npair) { const double2 v = __ldg(src + lane); acc[0].x += v.x; acc[0].y += v.y; }
+        if (lane + 32 < npair) { const double2 v = __ldg(src + lane + 32); acc[1].x += v.x; acc[1].y += v.y; }
+      }
+    }
+    double2* dst = reinterpret_cast<double2*>(Y + (size_t)r * ld);
+    if (P) {
+      const double2* pp = reinterpret_cast<const double2*>(P + (size_t)r * ld);
+      if (lane < npair) { const double2 v = pp[lane]; acc[0].x += lam * v.x; acc[0].y += lam * v.y; }
+      if (lane + 32 < npair) { const double2 v = pp[lane + 32]; acc[1].x += lam * v.x; acc[1].y += lam * v.y; }
+    }
+    if (lane < npair) dst[lane] = acc[0];
+    if (lane + 32 < npair) dst[lane + 32] = acc[1];
+  }
+}
+
+// ---- column-wise dot products over a (rows × ld) pair, deterministic two-stage reduction ----------------------------
+__global__ void __launch_bounds__(256) coldot_partial_kernel(const double* __restrict__ A, const double* __restrict__ B, int64_t rows, int ld,
+                                                             int D, double* __restrict__ part) {
+  // thread (ty, d): d = threadIdx.x % 32 … covers columns d, d+32, d+64, d+96; ty = threadIdx.x / 32 strides rows
+  const int d0 = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t r = (int64_t)blockIdx.x * 8 + ty; r < rows; r += (int64_t)gridDim.x * 8) {
+    const double* a = A + (size_t)r * ld;
+    const double* b = B + (size_t)r * ld;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int d = d0 + 32 * k;
+      if (d < D) s[k] = fma(a[d], b[d], s[k]);
+    }
+  }
+  __shared__ double sh[8][128];
+#pragma unroll
+  for (int k = 0; k < 4; k++) sh[ty][d0 + 32 * k] = s[k];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) t += sh[y][threadIdx.x];
+    part[(size_t)blockIdx.x * 128 + threadIdx.x] = t;
+  }
+}
+
+// CG scalars for every column — one block. mode 0: bknum = r·r, convergence test, bk, bkden (src/parallel_cg.jl:74-84);
+// mode 1: ak = bknum / (z·p) (:89).
+struct CGState {
+  double* bknum;   // [128]
+  double* bkden;   // [128]
+  double* coef;    // [128]  bk (mode 0) or ak (mode 1); 0 for inactive columns
+  double* tolv;    // [128]  tol·‖b‖ per column
+  int* active;     // [128]  column still iterating
+  int* iters;      // [128]  operator applications so far
+  int* nactive;    // [1]
+};
+
+__global__ void cg_scalars_kernel(const double* __restrict__ part, int nblk, int D, int mode, int iter, CGState st) {
+  const int d = threadIdx.x;
+  if (d < D) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; b++) s += part[(size_t)b * 128 + d];
+    if (mode == 2) {  // ‖b‖ → tolerance (src/parallel_cg.jl:65)
+      st.tolv[d] = st.tolv[d] * sqrt(s);
+    } else if (mode == 0) {
+      double bk = 0.0;
+      if (st.active[d]) {
+        if (sqrt(s) < st.tolv[d]) {
+          st.active[d] = 0;  // err < tol && return x
+        } else {
+          if (iter > 1) bk = s / st.bkden[d];
+          st.bkden[d] = s;
+          st.bknum[d] = s;
+          st.iters[d] += 1;
+        }
+      }
+      st.coef[d] = bk;
+    } else {
+      st.coef[d] = st.active[d] ? st.bknum[d] / s : 0.0;
+    }
+  }
+  __syncthreads();
+  if (mode == 0 && threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < D; k++) n += st.active[k];
+    *st.nactive = n;
+  }
+}
+
+// p = bk·p + r on the active columns (prod_add!, src/parallel_cg.jl:28-32); iter 1 keeps p = r
+__global__ void cg_update_p_kernel(double* __restrict__ P, const double* __restrict__ R, int64_t rows, int ld, int D, const double* __restrict__ bk,
+                                   const int* __restrict__ active, int iter) {
+  const int64_t n = rows * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(e % ld);
+    if (d < D && active[d] && iter > 1) P[e] = bk[d] * P[e] + R[e];
+  }
+}
+
+// x += ak·p ; r −= ak·z on the active columns (add_prod!/sub_prod!, src/parallel_cg.jl:34-46)
+__global__ void cg_update_xr_kernel(double* __restrict__ X, double* __restrict__ R, const double* __restrict__ P, const double* __restrict__ Z,
+                                    int64_t rows, int ld, int D, const double* __restrict__ ak, const int* __restrict__ active) {
+  const int64_t n = rows * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(e % ld);
+    if (d < D && active[d]) {
+      const double a = ak[d];
+      X[e] += a * P[e];
+      R[e] -= a * Z[e];
+    }
+  }
+}
+
+// column-major host layout (rows × ncol) ↔ row-major device layout (rows × ld)
+__global__ void to_rowmajor_kernel(const double* __restrict__ cm, int64_t rows, int ncol, int ld, double* __restrict__ rm) {
+  const int64_t n = rows * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / ld;
+    const int d = (int)(e % ld);
+    rm[e] = d < ncol ? cm[r + (size_t)d * rows] : 0.0;
+  }
+}
+__global__ void to_colmajor_kernel(const double* __restrict__ rm, int64_t rows, int ncol, int ld, double* __restrict__ cm) {
+  const int64_t n = rows * ncol;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % rows;
+    const int d = (int)(e / rows);
+    cm[e] = rm[(size_t)r * ld + d];
+  }
+}
+
+// C = chol_lower(inv(Λ)) (the colouring matrix of MvNormal(0, inv(PDMat(Λ))), src/sampling.jl:298): J·Λ·J = L·Lᵀ ⇒
+// C = J·L⁻ᵀ·J. Single CTA; scratch = 2·D·D doubles. Output C column-major.
+__global__ void __launch_bounds__(256) color_matrix_kernel(const double* __restrict__ Lambda, int D, double* scratch, double* __restrict__ Cout,
+                                                           int* err_flag) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* Lm = scratch;
+  double* Y = scratch + (size_t)D * D;
+  for (int e = tid; e < D * D; e += nt) {
+    int i = e % D, j = e / D;
+    const int a = D - 1 - i, b = D - 1 - j;
+    if (i > j) { const int t = i; i = j; j = t; }
+    Lm[a + (size_t)b * D] = Lambda[i + (size_t)j * D];  // Symmetric(Λ) reads the upper triangle
+    Y[e] = (e % D == e / D) ? 1.0 : 0.0;
+  }
+  const bool ok = cta_chol_lower(Lm, D);
+  // Y = L⁻ᵀ (columns of the identity, back substitution), thread per column
+  for (int c = tid; c < D; c += nt) {
+    double* y = Y + (size_t)c * D;
+    for (int i = D - 1; i >= 0; i--) {
+      double s = y[i];
+      for (int k = i + 1; k < D; k++) s -= Lm[k + (size_t)i * D] * y[k];
+      y[i] = s / Lm[i + (size_t)i * D];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < D * D; e += nt) {
+    const int i = e % D, j = e / D;
+    Cout[e] = Y[(D - 1 - i) + (size_t)(D - 1 - j) * D];
+  }
+  if (!ok && tid == 0) atomicOr(err_flag, 4);
+}
+
+// T[r,:] = (U[r,:] − mu) + C·e_r   (sample_u_c' + rand(mv,N)', src/sampling.jl:300) or scale·C·e_r when U == nullptr;
+// e_r: injected standard normals (row-major rows × ld) or the Philox stream `stream`.
+__global__ void __launch_bounds__(128) colored_rows_kernel(const double* __restrict__ U, const double* __restrict__ mu, const double* __restrict__ Cm,
+                                                           const double* __restrict__ E, int64_t rows, int ld, int D, double scale,
+                                                           uint64_t seed, uint64_t sweep, uint32_t stream, double* __restrict__ T, int accumulate) {
+  extern __shared__ double sh[];  // C (D×D col-major) + per-warp noise vectors
+  double* Cs = sh;
+  double* es = sh + (size_t)D * D;
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) Cs[e] = Cm[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* ev = es + (size_t)w * D;
+  for (int64_t r = (int64_t)blockIdx.x * nw + w; r < rows; r += (int64_t)gridDim.x * nw) {
+    for (int k = lane; k < D; k += 32) ev[k] = E ? E[(size_t)r * ld + k] : philox_normal(seed, sweep, stream, (uint64_t)r, k);
+    __syncwarp();
+    for (int i = lane; i < ld; i += 32) {
+      double s = 0.0;
+      if (i < D) {
+        for (int k = 0; k <= i; k++) s = fma(Cs[i + (size_t)k * D], ev[k], s);  // C lower triangular
+        s *= scale;
+        if (U) s += U[(size_t)r * ld + i] - mu[i];
+        if (accumulate) s += T[(size_t)r * ld + i];
+      }
+      T[(size_t)r * ld + i] = s;
+    }
+    __syncwarp();
+  }
+}
+
+// lambda_beta ~ Gamma(shape νx/2, scale 2μx/νx), νx = ν + numF·D, μx = μ·νx/(ν + μ·tr((βᵀβ)Λ)) — src/sampling.jl:136-142
+__global__ void lambda_beta_kernel(const double* __restrict__ btb_stats, const double* __restrict__ Lambda, int D, double numF, double nu, double mu,
+                                   double g_inj, uint64_t seed, uint64_t sweep, uint32_t stream, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double* BtB = btb_stats + 1 + D;
+    double tr = 0.0;
+    for (int i = 0; i < D; i++)
+      for (int k = 0; k < D; k++) tr += BtB[i + (size_t)k * D] * Lambda[k + (size_t)i * D];
+    const double nux = nu + numF * D;
+    const double mux = mu * nux / (nu + mu * tr);
+    const double b = nux / 2.0, c = 2.0 * mux / nux;
+    const double g = g_inj == g_inj ? g_inj : gamma_mt(b, seed, sweep, stream, 0);
+    out[0] = c * g;
+    out[1] = b;
+  }
+}
+
+__global__ void add_mu_kernel(const double* __restrict__ uhat, const double* __restrict__ mu, int64_t rows, int ld, int D, double* __restrict__ out) {
+  const int64_t n = rows * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(e % ld);
+    out[e] = d < D ? uhat[e] + mu[d] : 0.0;
+  }
+}
+
+__global__ void sort_keys_kernel(const int32_t* a, int64_t n, int32_t maxv, uint32_t* keys, uint32_t* idx, int* bad) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = a[o];
+    if (v < 1 || v > maxv) { *bad = 1; keys[o] = 0; } else keys[o] = (uint32_t)(v - 1);
+    idx[o] = (uint32_t)o;
+  }
+}
+__global__ void count_keys_kernel(const uint32_t* keys, int64_t n, unsigned long long* counts) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) atomicAdd(counts + keys[o], 1ULL);
+}
+__global__ void gather_other_kernel(const uint32_t* perm, int64_t n, const int32_t* other, int32_t* out) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) out[o] = other[perm[o]] - 1;
+}
+
+template <class T>
+int dalloc(bdf_t* h, T** p, size_t n) {
+  *p = nullptr;
+  CU(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  return BDF_OK;
+}
+
+// one orientation of F: stable sort of the COO list by `key` (rows for CSR, cols for CSC) — the reference's
+// sortperm(rows) in SparseBinMatrixCSR (src/sparsebin_csr.jl:23) — then the pointer array by counting.
+int build_orientation(bdf_t* h, const int32_t* d_key, const int32_t* d_other, int64_t nnz, int64_t nkeys, int32_t other_max, int64_t** ptr_out,
+                      int32_t** ind_out) {
+  uint32_t *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *idx2 = nullptr;
+  int* d_bad = nullptr; unsigned long long* cnt = nullptr; void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(idx2); cudaFree(d_bad); cudaFree(cnt); cudaFree(tmp); };
+#define TRYC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return BDF_ERR_CUDA; } } while (0)
+  const size_t n1 = std::max<int64_t>(nnz, 1);
+  TRYC(cudaMalloc((void**)&keys, n1 * 4)); TRYC(cudaMalloc((void**)&keys2, n1 * 4)); TRYC(cudaMalloc((void**)&idx, n1 * 4)); TRYC(cudaMalloc((void**)&idx2, n1 * 4));
+  TRYC(cudaMalloc((void**)&d_bad, 4)); TRYC(cudaMalloc((void**)&cnt, (nkeys + 1) * 8));
+  TRYC(cudaMemsetAsync(d_bad, 0, 4, h->stream));
+  TRYC(cudaMemsetAsync(cnt, 0, (nkeys + 1) * 8, h->stream));
+  sort_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(d_key, nnz, (int32_t)nkeys, keys, idx, d_bad);
+  // `other` range check rides on the same flag
+  sort_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(d_other, nnz, other_max, keys2, idx2, d_bad);
+  int bits = 1;
+  while ((1LL << bits) < nkeys) bits++;
+  size_t tb = 0, sb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, idx, idx2, (int)n1, 0, bits, h->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, sb, cnt, (int64_t*)nullptr, (int)(nkeys + 1), h->stream);
+  tb = std::max(tb, sb);
+  TRYC(cudaMalloc(&tmp, std::max<size_t>(tb, 16)));
+  sort_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(d_key, nnz, (int32_t)nkeys, keys, idx, d_bad);
+  if (nnz) TRYC(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, idx, idx2, (int)nnz, 0, bits, h->stream));
+  count_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(keys2, nnz, cnt);
+  int rc;
+  if ((rc = dalloc(h, ptr_out, (size_t)nkeys + 1))) { cleanup(); return rc; }
+  if ((rc = dalloc(h, ind_out, n1))) { cleanup(); return rc; }
+  TRYC(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, *ptr_out, (int)(nkeys + 1), h->stream));
+  gather_other_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(idx2, nnz, d_other, *ind_out);
+  int bad = 0;
+  TRYC(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream));
+  TRYC(cudaStreamSynchronize(h->stream));
+  cleanup();
+#undef TRYC
+  if (bad) FAIL(BDF_ERR_INVALID, "feature row/column index outside 1..m / 1..n");
+  return BDF_OK;
+}
+
+int need_features(bdf_t* h, int entity) {
+  if (h->ents[entity].numF <= 0) FAIL(BDF_ERR_STATE, "entity has no feature matrix (bdf_set_features_sbm)");
+  return BDF_OK;
+}
+
+void spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr) {
+  const int64_t rows = transpose ? e.numF : e.N;
+  int64_t g = (rows * 32 + 255) / 256;
+  g = std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 8);
+  spbin_gather_kernel<<<(int)g, 256, 0, h->stream>>>(transpose ? e.f_colptr : e.f_rowptr, transpose ? e.f_rowind : e.f_colind, rows, X, Y, h->ld, lam, P);
+  h->launches++;
+}
+
+// batched CG on (FᵀF + λI)X = B, all D columns at once; B, X device row-major (numF × ld). Returns per-column iteration counts.
+int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda, double tol, int64_t maxiter, int* iters_host) {
+  const int D = h->D, ld = h->ld;
+  const int64_t n = e.numF, m = e.N;
+  const size_t vn = (size_t)n * ld, vm = (size_t)m * ld;
+  const int NBLK = 296;
+  if (!e.cgbuf) {
+    int rc = dalloc(h, &e.cgbuf, 3 * vn + vm + (size_t)NBLK * 128 + 4 * 128 + 4 * 128);
+    if (rc) return rc;
+  }
+  double* R = e.cgbuf; double* P = R + vn; double* Z = P + vn; double* T = Z + vn; double* part = T + vm;
+  CGState st;
+  st.bknum = part + (size_t)NBLK * 128; st.bkden = st.bknum + 128; st.coef = st.bkden + 128; st.tolv = st.coef + 128;
+  st.active = reinterpret_cast<int*>(st.tolv + 128); st.iters = st.active + 128; st.nactive = st.iters + 128;
+  std::vector<double> tolh(128, tol);
+  std::vector<int> acth(128, 0), zero(128, 0);
+  for (int d = 0; d < D; d++) acth[d] = 1;
+  CU(cudaMemcpyAsync(st.tolv, tolh.data(), 128 * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(st.active, acth.data(), 128 * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(st.iters, zero.data(), 128 * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(X, 0, vn * 8, h->stream));                                        // x = 0
+  CU(cudaMemcpyAsync(R, B, vn * 8, cudaMemcpyDeviceToDevice, h->stream));              // r = b
+  CU(cudaMemcpyAsync(P, B, vn * 8, cudaMemcpyDeviceToDevice, h->stream));              // p = r
+  coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(B, B, n, ld, D, part);
+  cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 2, 0, st);                // tol ← tol·‖b‖
+  h->launches += 2;
+  int nact = D;
+  for (int64_t iter = 1; iter <= maxiter && nact > 0; iter++) {
+    coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(R, R, n, ld, D, part);
+    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 0, (int)iter, st);
+    cg_update_p_kernel<<<grid_for(vn), 256, 0, h->stream>>>(P, R, n, ld, D, st.coef, st.active, (int)iter);
+    spmm(h, e, false, P, T);                      // T = F·P
+    spmm(h, e, true, T, Z, lambda, P);            // Z = Fᵀ·T + λ·P
+    coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(Z, P, n, ld, D, part);
+    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 1, (int)iter, st);
+    cg_update_xr_kernel<<<grid_for(vn), 256, 0, h->stream>>>(X, R, P, Z, n, ld, D, st.coef, st.active);
+    h->launches += 6;
+    if ((iter & 3) == 0 || iter == maxiter) {  // the all-converged test costs a sync; take it every 4th iteration
+      CU(cudaMemcpyAsync(&nact, st.nactive, 4, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+  CU(cudaGetLastError());
+  if (iters_host) {
+    std::vector<int> it(128);
+    CU(cudaMemcpyAsync(it.data(), st.iters, 128 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(iters_host, it.data(), sizeof(int) * D);
+  }
+  return BDF_OK;
+}
+
+int upload_rowmajor(bdf_t* h, const double* host_cm, int64_t rows, int ncol, double* dev_rm) {
+  double* stage = nullptr;
+  CU(cudaMalloc((void**)&stage, sizeof(double) * (size_t)rows * ncol));
+  CU(cudaMemcpyAsync(stage, host_cm, sizeof(double) * (size_t)rows * ncol, cudaMemcpyHostToDevice, h->stream));
+  to_rowmajor_kernel<<<grid_for(rows * h->ld), 256, 0, h->stream>>>(stage, rows, ncol, h->ld, dev_rm);
+  cudaError_t ce = cudaStreamSynchronize(h->stream);
+  cudaFree(stage);
+  if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  return BDF_OK;
+}
+int download_colmajor(bdf_t* h, const double* dev_rm, int64_t rows, int ncol, double* host_cm) {
+  double* stage = nullptr;
+  CU(cudaMalloc((void**)&stage, sizeof(double) * (size_t)rows * ncol));
+  to_colmajor_kernel<<<grid_for(rows * ncol), 256, 0, h->stream>>>(dev_rm, rows, ncol, h->ld, stage);
+  cudaError_t ce = cudaMemcpyAsync(host_cm, stage, sizeof(double) * (size_t)rows * ncol, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t ce2 = cudaStreamSynchronize(h->stream);
+  cudaFree(stage);
+  if (ce != cudaSuccess || ce2 != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+  return BDF_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this round (world must be 1)");
+  EntityS& e = h->ents[entity];
+  if (m != e.N) FAIL(BDF_ERR_INVALID, "DimensionMismatch: number of feature rows must equal the entity count");  // src/RelationData.jl:263-268
+  if (n < 1 || n > 2000000000LL || nnz < 0 || nnz >= 2147483647LL) FAIL(BDF_ERR_INVALID, "bad feature matrix size");
+  if (nnz > 0 && (!rows || !cols)) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
+  e.f_rowptr = e.f_colptr = nullptr; e.f_colind = e.f_rowind = nullptr; e.beta = e.uhat = e.cgbuf = e.btb = nullptr;
+  e.numF = 0;
+  int32_t *d_rows = nullptr, *d_cols = nullptr;
+  int rc;
+  if ((rc = dalloc(h, &d_rows, (size_t)nnz)) || (rc = dalloc(h, &d_cols, (size_t)nnz))) { cudaFree(d_rows); return rc; }
+  if (nnz) {
+    CU(cudaMemcpyAsync(d_rows, rows, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_cols, cols, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = build_orientation(h, d_rows, d_cols, nnz, m, (int32_t)n, &e.f_rowptr, &e.f_colind);
+  if (!rc) rc = build_orientation(h, d_cols, d_rows, nnz, n, (int32_t)m, &e.f_colptr, &e.f_rowind);
+  cudaFree(d_rows); cudaFree(d_cols);
+  if (rc) return rc;
+  const size_t bn = (size_t)n * h->ld, un = (size_t)e.Nper * h->world * h->ld;
+  if ((rc = dalloc(h, &e.beta, bn)) || (rc = dalloc(h, &e.uhat, un)) || (rc = dalloc(h, &e.btb, (size_t)1 + h->D + (size_t)h->D * h->D))) return rc;
+  CU(cudaMemsetAsync(e.beta, 0, bn * 8, h->stream));   // beta = zeros(numF, num_latent), src/RelationData.jl:76
+  CU(cudaMemsetAsync(e.uhat, 0, un * 8, h->stream));
+  if (!e.mu_rows) { if ((rc = dalloc(h, &e.mu_rows, un))) return rc; CU(cudaMemsetAsync(e.mu_rows, 0, un * 8, h->stream)); }
+  e.numF = n; e.fnnz = nnz;
+  const size_t need = sizeof(double) * 296 * (size_t)tri(h->D + 1);
+  if (h->ws_bytes < need) FAIL(BDF_ERR_STATE, "workspace too small");
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+/* debug/parity hook: the CSR the device built, in the reference's own representation (1-based Int32 row_ptr of length m+1
+ * and col_ind, src/sparsebin_csr.jl:6-11) */
+int bdf_debug_features_csr(bdf_t* h, int entity, int transpose, int32_t* ptr_out, int32_t* ind_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const int64_t nk = transpose ? e.numF : e.N;
+  std::vector<int64_t> p((size_t)nk + 1);
+  std::vector<int32_t> ind((size_t)std::max<int64_t>(e.fnnz, 1));
+  CU(cudaMemcpyAsync(p.data(), transpose ? e.f_colptr : e.f_rowptr, 8 * p.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(ind.data(), transpose ? e.f_rowind : e.f_colind, 4 * (size_t)e.fnnz, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i <= nk; i++) ptr_out[i] = (int32_t)(p[i] + 1);
+  for (int64_t i = 0; i < e.fnnz; i++) ind_out[i] = ind[i] + 1;
+  return BDF_OK;
+}
+
+int bdf_spmm(bdf_t* h, int entity, int transpose, const double* X, int ncol, double* Y) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!X || !Y || ncol < 1 || ncol > h->D) FAIL(BDF_ERR_INVALID, "DimensionMismatch: need 1 <= ncol <= num_latent");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const int64_t rin = transpose ? e.N : e.numF, rout = transpose ? e.numF : e.N;
+  double *dx = nullptr, *dy = nullptr;
+  if ((rc = dalloc(h, &dx, (size_t)rin * h->ld)) || (rc = dalloc(h, &dy, (size_t)rout * h->ld))) { cudaFree(dx); return rc; }
+  rc = upload_rowmajor(h, X, rin, ncol, dx);
+  if (!rc) { spmm(h, e, transpose != 0, dx, dy); rc = download_colmajor(h, dy, rout, ncol, Y); }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
+int bdf_ata_mul(bdf_t* h, int entity, const double* x, double lambda, double* y) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!x || !y) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  double *dx = nullptr, *dt = nullptr, *dy = nullptr;
+  if ((rc = dalloc(h, &dx, (size_t)e.numF * h->ld)) || (rc = dalloc(h, &dt, (size_t)e.N * h->ld)) || (rc = dalloc(h, &dy, (size_t)e.numF * h->ld))) { cudaFree(dx); cudaFree(dt); return rc; }
+  rc = upload_rowmajor(h, x, e.numF, 1, dx);
+  if (!rc) { spmm(h, e, false, dx, dt); spmm(h, e, true, dt, dy, lambda, dx); rc = download_colmajor(h, dy, e.numF, 1, y); }
+  cudaFree(dx); cudaFree(dt); cudaFree(dy);
+  return rc;
+}
+
+int bdf_cg_solve(bdf_t* h, int entity, const double* rhs, int ncol, double lambda, double tol, int64_t maxiter, double* x, int* iters) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!rhs || !x || ncol != h->D) FAIL(BDF_ERR_INVALID, "DimensionMismatch: rhs must have num_latent columns");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if (maxiter <= 0) maxiter = e.numF;                        // maxiter=size(rhs,1), src/parallel_matrix.jl:488
+  if (tol != tol) tol = 2.220446049250313e-16 * (double)e.numF;  // eps()·numF, src/sampling.jl:294-296
+  double *db = nullptr, *dx = nullptr;
+  if ((rc = dalloc(h, &db, (size_t)e.numF * h->ld)) || (rc = dalloc(h, &dx, (size_t)e.numF * h->ld))) { cudaFree(db); return rc; }
+  rc = upload_rowmajor(h, rhs, e.numF, ncol, db);
+  if (!rc) rc = cg_solve_dev(h, e, db, dx, lambda, tol, maxiter, iters);
+  if (!rc) rc = download_colmajor(h, dx, e.numF, ncol, x);
+  cudaFree(db); cudaFree(dx);
+  return rc;
+}
+
+int bdf_set_beta(bdf_t* h, int entity, const double* beta) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  return upload_rowmajor(h, beta, h->ents[entity].numF, h->D, h->ents[entity].beta);
+}
+int bdf_get_beta(bdf_t* h, int entity, double* beta) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  return download_colmajor(h, h->ents[entity].beta, h->ents[entity].numF, h->D, beta);
+}
+
+/* uhat = (F·beta)' and the per-row prior mean mu .+ uhat (src/macau.jl:102-104); uhat_out (D×N) may be NULL */
+int bdf_update_uhat(bdf_t* h, int entity, const double* mu, double* uhat_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!mu) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+  spmm(h, e, false, e.beta, e.uhat);
+  add_mu_kernel<<<grid_for(e.N * h->ld), 256, 0, h->stream>>>(e.uhat, e.mu, e.N, h->ld, h->D, e.mu_rows);
+  h->launches++;
+  CU(cudaGetLastError());
+  if (uhat_out) CU(cudaMemcpy2DAsync(uhat_out, sizeof(double) * h->D, e.uhat, sizeof(double) * h->ld, sizeof(double) * h->D, (size_t)e.N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+/* sample_latent_all2! with the per-row mean mu .+ uhat left on the device by bdf_update_uhat (src/macau.jl:105) */
+int bdf_sample_mode_uhat(bdf_t* h, int entity, const double* Lambda, const double* z) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!Lambda) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const size_t un = (size_t)e.Nper * h->world * h->ld;
+  CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * h->D * h->D, cudaMemcpyHostToDevice, h->stream));
+  const double* zd = nullptr;
+  if (z) {
+    if (!e.Z) { if ((rc = dalloc(h, &e.Z, un))) return rc; CU(cudaMemsetAsync(e.Z, 0, un * 8, h->stream)); }
+    CU(cudaMemcpy2DAsync(e.Z, sizeof(double) * h->ld, z, sizeof(double) * h->D, sizeof(double) * h->D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream));
+    zd = e.Z;
+  }
+  if ((rc = bdf_sample_entity_impl(h, entity, e.mu_rows, h->ld, e.Lambda, zd))) return rc;
+  return bdf_check_err_flag(h);
+}
+
+/* ConditionalNormalWishart statistics of U − uhat (src/macau.jl:124) */
+int bdf_nw_stats_uhat(bdf_t* h, int entity, double* N, double* NU, double* NS) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if ((rc = bdf_stats_of(h, e.U, e.uhat, 0, e.N, e.stats))) return rc;
+  const int D = h->D;
+  std::vector<double> buf((size_t)1 + D + (size_t)D * D);
+  CU(cudaMemcpyAsync(buf.data(), e.stats, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (N) *N = buf[0];
+  if (NU) memcpy(NU, buf.data() + 1, sizeof(double) * D);
+  if (NS) memcpy(NS, buf.data() + 1 + D, sizeof(double) * D * D);
+  return BDF_OK;
+}
+
+/* beta' * beta (D×D) — src/macau.jl:128, src/sampling.jl:138 */
+int bdf_beta_gram(bdf_t* h, int entity, double* BtB) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if ((rc = bdf_stats_of(h, e.beta, nullptr, 0, e.numF, e.btb))) return rc;
+  if (BtB) CU(cudaMemcpyAsync(BtB, e.btb + 1 + h->D, sizeof(double) * h->D * h->D, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+/* sample_beta(entity, sample_u_c, Lambda_u, lambda_beta, use_ff=false, tol) — src/sampling.jl:291-312 — with the CG solver
+ * (solve_cg2). E1 (D×N) and E2 (D×numF) are the injected standard normals behind rand(mv, N) / rand(mv, numF), consumed in
+ * that order; NULL = device Philox. Leaves beta on the device; beta_out (numF×D) / rhs_out (numF×D, the Ft_y the
+ * reference also returns) / iters_out (D) may be NULL. */
+int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda, double lambda_beta, double tol, const double* E1,
+                    const double* E2, double* beta_out, double* rhs_out, int* iters_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!mu || !Lambda) FAIL(BDF_ERR_INVALID, "null argument");
+  if (!(lambda_beta > 0.0)) FAIL(BDF_ERR_INVALID, "lambda_beta must be positive");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const int D = h->D, ld = h->ld;
+  const size_t dd = (size_t)D * D;
+  if (tol != tol) tol = 2.220446049250313e-16 * (double)e.numF;
+  CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
+  double *Cm = nullptr, *T = nullptr, *rhs = nullptr, *E1d = nullptr, *E2d = nullptr;
+  auto cleanup = [&]() { cudaFree(Cm); cudaFree(T); cudaFree(rhs); cudaFree(E1d); cudaFree(E2d); };
+  if ((rc = dalloc(h, &Cm, dd)) || (rc = dalloc(h, &T, (size_t)e.N * ld)) || (rc = dalloc(h, &rhs, (size_t)e.numF * ld))) { cleanup(); return rc; }
+  color_matrix_kernel<<<1, 256, 0, h->stream>>>(e.Lambda, D, h->scratch, Cm, h->err_flag);
+  if (E1) { if ((rc = dalloc(h, &E1d, (size_t)e.N * ld))) { cleanup(); return rc; }
+            cudaMemcpy2DAsync(E1d, sizeof(double) * ld, E1, sizeof(double) * D, sizeof(double) * D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream); }
+  if (E2) { if ((rc = dalloc(h, &E2d, (size_t)e.numF * ld))) { cleanup(); return rc; }
+            cudaMemcpy2DAsync(E2d, sizeof(double) * ld, E2, sizeof(double) * D, sizeof(double) * D, (size_t)e.numF, cudaMemcpyHostToDevice, h->stream); }
+  const size_t smem = sizeof(double) * (dd + 4 * (size_t)D);
+  cudaFuncSetAttribute(colored_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const uint32_t s0 = 0x200u + 8u * (uint32_t)entity;
+  // T = (U − mu) + C·E1 ; rhs = Fᵀ·T ; rhs += sqrt(lambda_beta)·C·E2
+  colored_rows_kernel<<<grid_for(e.N, 4), 128, smem, h->stream>>>(e.U, e.mu, Cm, E1d, e.N, ld, D, 1.0, h->seed, h->sweep, s0, T, 0);
+  spmm(h, e, true, T, rhs);
+  colored_rows_kernel<<<grid_for(e.numF, 4), 128, smem, h->stream>>>(nullptr, nullptr, Cm, E2d, e.numF, ld, D, sqrt(lambda_beta), h->seed, h->sweep, s0 + 1, rhs, 1);
+  h->launches += 3;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { cleanup(); FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce)); }
+  rc = cg_solve_dev(h, e, rhs, e.beta, lambda_beta, tol, e.numF, iters_out);
+  if (!rc && beta_out) rc = download_colmajor(h, e.beta, e.numF, D, beta_out);
+  if (!rc && rhs_out) rc = download_colmajor(h, rhs, e.numF, D, rhs_out);
+  if (!rc) rc = bdf_check_err_flag(h); else cudaStreamSynchronize(h->stream);
+  cleanup();
+  return rc;
+}
+
+/* sample_lambda_beta(beta, Lambda_u, nu, mu) — src/sampling.jl:136-142. gamma_variate: the injected Gamma(shape, 1) draw
+ * behind rand(Gamma(b, c)), or NaN for the device Philox stream. */
+int bdf_sample_lambda_beta(bdf_t* h, int entity, const double* Lambda, double nu, double mu, double gamma_variate, double* lambda_beta_out,
+                           double* shape_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!Lambda || !lambda_beta_out) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * h->D * h->D, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = bdf_stats_of(h, e.beta, nullptr, 0, e.numF, e.btb))) return rc;
+  double* out = h->scratch;  // 2 doubles
+  lambda_beta_kernel<<<1, 32, 0, h->stream>>>(e.btb, e.Lambda, h->D, (double)e.numF, nu, mu, gamma_variate, h->seed, h->sweep, 0x300u + (uint32_t)entity, out);
+  h->launches++;
+  double res[2];
+  CU(cudaMemcpyAsync(res, out, sizeof(res), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *lambda_beta_out = res[0];
+  if (shape_out) *shape_out = res[1];
+  return BDF_OK;
+}
+
+}  // extern "C"

@@ -4,6 +4,7 @@
 // The statistics are a streaming DMMA syrk over the rank's factor rows (same tile machinery as the row draw);
 // the draw is a single-CTA kernel on D×D matrices.
 #pragma once
+#include "nw_device.cuh"
 #include "row_kernel.cuh"
 
 namespace bdf {
@@ -49,28 +50,6 @@ __global__ void stats_reduce_kernel(const double* __restrict__ ws, int nblk, int
 }
 
 // ---- the draw -------------------------------------------------------------------------------------------------
-// In-place lower Cholesky of a column-major n×n matrix (single CTA). Returns false on a non-positive pivot.
-__device__ inline bool cta_chol_lower(double* A, int n) {
-  bool ok = true;
-  for (int j = 0; j < n; j++) {
-    __syncthreads();
-    const double d = A[j + (size_t)j * n];
-    if (!(d > 0.0)) ok = false;
-    const double sd = sqrt(d);
-    const double is = 1.0 / sd;
-    __syncthreads();
-    for (int i = j + threadIdx.x; i < n; i += blockDim.x) A[i + (size_t)j * n] = (i == j) ? sd : A[i + (size_t)j * n] * is;
-    __syncthreads();
-    // trailing update, columns k > j
-    for (int e = threadIdx.x; e < (n - j - 1) * (n - j - 1); e += blockDim.x) {
-      const int k = j + 1 + e / (n - j - 1), i = j + 1 + e % (n - j - 1);
-      if (i >= k) A[i + (size_t)k * n] -= A[i + (size_t)j * n] * A[k + (size_t)j * n];
-    }
-  }
-  __syncthreads();
-  return ok;
-}
-
 struct NWDrawParams {
   int D;
   const double* stats;  // [N, NU, NS]
@@ -86,32 +65,6 @@ struct NWDrawParams {
   double* Lam_out;  // D×D
   int* err_flag;
 };
-
-__device__ inline double gamma_mt(double a, uint64_t seed, uint64_t sweep, uint32_t stream, uint64_t row) {
-  // Marsaglia–Tsang; Gamma(a, 1). For a < 1: Gamma(a+1)·U^(1/a).
-  double boost = 1.0;
-  uint32_t ctr = 0;
-  if (a < 1.0) {
-    double u1, u2;
-    philox_uniform2(seed, sweep, stream, row, ctr++, u1, u2);
-    boost = pow(u1, 1.0 / a);
-    a += 1.0;
-  }
-  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-  for (int it = 0; it < 64; it++) {
-    double u1, u2, u3, u4;
-    philox_uniform2(seed, sweep, stream, row, ctr++, u1, u2);
-    philox_uniform2(seed, sweep, stream, row, ctr++, u3, u4);
-    double s, co;
-    sincospi(2.0 * u2, &s, &co);
-    const double x = sqrt(-2.0 * log(u1)) * co;
-    double v = 1.0 + c * x;
-    if (v <= 0.0) continue;
-    v = v * v * v;
-    if (log(u3) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
-  }
-  return boost * d;
-}
 
 __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
   const int D = p.D, tid = threadIdx.x, nt = blockDim.x;

@@ -14,15 +14,6 @@ using namespace bdf;
 
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
-#define CU(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
-      return BDF_ERR_CUDA;                                                                         \
-    }                                                                                              \
-  } while (0)
-
 static constexpr int kDP = BDF_DP;
 static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : 8);
 

@@ -173,6 +173,101 @@ class Engine:
         self._ck(self.lib.bdf_debug_row_noise(self.h, entity, C.c_uint64(sweep), _dp(z)))
         return z
 
+    # -- Macau side features ------------------------------------------------------------------------------
+    def set_features(self, entity: int, F):
+        """F: a SparseBinMatrix-like object with .rows/.cols (1-based Int32) and .shape, or a scipy.sparse 0/1 matrix."""
+        if hasattr(F, "rows") and hasattr(F, "cols"):
+            rows, cols, (m, n) = F.rows, F.cols, F.shape
+        else:
+            coo = F.tocsc().tocoo()
+            if not np.all(coo.data == 1):
+                raise ValueError("only sparse binary (0/1) feature matrices are on the device path")
+            rows, cols, (m, n) = coo.row + 1, coo.col + 1, F.shape
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        if len(rows) != len(cols):
+            raise ValueError("DimensionMismatch: length(rows) must equal length(cols)")  # src/parallel_matrix.jl:20
+        self._ck(self.lib.bdf_set_features_sbm(self.h, entity, m, n, len(rows), rows.ctypes.data_as(_lib.c_i32p), cols.ctypes.data_as(_lib.c_i32p)))
+        self.numF = getattr(self, "numF", {})
+        self.numF[entity] = int(n)
+
+    def debug_features_csr(self, entity: int, transpose: bool, nnz: int):
+        nk = self.numF[entity] if transpose else self.counts[entity]
+        ptr = np.zeros(nk + 1, dtype=np.int32)
+        ind = np.zeros(max(nnz, 1), dtype=np.int32)
+        self._ck(self.lib.bdf_debug_features_csr(self.h, entity, int(transpose), ptr.ctypes.data_as(_lib.c_i32p), ind.ctypes.data_as(_lib.c_i32p)))
+        return ptr, ind[:nnz]
+
+    def spmm(self, entity: int, X, transpose: bool = False):
+        X = np.asfortranarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1, order="F")
+        rout = self.numF[entity] if transpose else self.counts[entity]
+        Y = np.zeros((rout, X.shape[1]), order="F")
+        self._ck(self.lib.bdf_spmm(self.h, entity, int(transpose), _dp(X), X.shape[1], _dp(Y)))
+        return Y
+
+    def ata_mul(self, entity: int, x, lam: float):
+        x = _f64(x)
+        y = np.zeros(self.numF[entity])
+        self._ck(self.lib.bdf_ata_mul(self.h, entity, _dp(x), lam, _dp(y)))
+        return y
+
+    def cg_solve(self, entity: int, rhs, lam: float, tol: float = float("nan"), maxiter: int = 0):
+        rhs = np.asfortranarray(rhs, dtype=np.float64)
+        x = np.zeros(rhs.shape, order="F")
+        iters = np.zeros(rhs.shape[1], dtype=np.int32)
+        self._ck(self.lib.bdf_cg_solve(self.h, entity, _dp(rhs), rhs.shape[1], lam, tol, maxiter, _dp(x), iters.ctypes.data_as(_lib.c_ip)))
+        return x, iters
+
+    def set_beta(self, entity: int, beta):
+        self._ck(self.lib.bdf_set_beta(self.h, entity, _dp(np.asfortranarray(beta, dtype=np.float64))))
+
+    def get_beta(self, entity: int):
+        beta = np.zeros((self.numF[entity], self.D), order="F")
+        self._ck(self.lib.bdf_get_beta(self.h, entity, _dp(beta)))
+        return beta
+
+    def update_uhat(self, entity: int, mu, want: bool = False):
+        out = np.zeros((self.counts[entity], self.D)) if want else None
+        self._ck(self.lib.bdf_update_uhat(self.h, entity, _dp(_f64(mu)), _dp(out)))
+        return out
+
+    def sample_mode_uhat(self, entity: int, Lambda, z=None):
+        zz = _f64(z) if z is not None else None
+        self._ck(self.lib.bdf_sample_mode_uhat(self.h, entity, _dp(np.asfortranarray(Lambda, dtype=np.float64)), _dp(zz)))
+
+    def nw_stats_uhat(self, entity: int):
+        D = self.D
+        N = C.c_double()
+        NU = np.zeros(D)
+        NS = np.zeros((D, D), order="F")
+        self._ck(self.lib.bdf_nw_stats_uhat(self.h, entity, C.cast(C.byref(N), _lib.c_dp), _dp(NU), _dp(NS)))
+        return N.value, NU, NS
+
+    def beta_gram(self, entity: int):
+        B = np.zeros((self.D, self.D), order="F")
+        self._ck(self.lib.bdf_beta_gram(self.h, entity, _dp(B)))
+        return B
+
+    def sample_beta(self, entity: int, mu, Lambda, lambda_beta: float, tol: float = float("nan"), E1=None, E2=None, want_rhs: bool = False):
+        n = self.numF[entity]
+        beta = np.zeros((n, self.D), order="F")
+        rhs = np.zeros((n, self.D), order="F") if want_rhs else None
+        iters = np.zeros(self.D, dtype=np.int32)
+        e1 = _f64(E1) if E1 is not None else None
+        e2 = _f64(E2) if E2 is not None else None
+        self._ck(self.lib.bdf_sample_beta(self.h, entity, _dp(_f64(mu)), _dp(np.asfortranarray(Lambda, dtype=np.float64)), lambda_beta, tol,
+                                          _dp(e1), _dp(e2), _dp(beta), _dp(rhs), iters.ctypes.data_as(_lib.c_ip)))
+        return (beta, rhs, iters) if want_rhs else (beta, iters)
+
+    def sample_lambda_beta(self, entity: int, Lambda, nu: float, mu: float, gamma_variate: float = float("nan")):
+        out = C.c_double()
+        shape = C.c_double()
+        self._ck(self.lib.bdf_sample_lambda_beta(self.h, entity, _dp(np.asfortranarray(Lambda, dtype=np.float64)), nu, mu, gamma_variate,
+                                                 C.cast(C.byref(out), _lib.c_dp), C.cast(C.byref(shape), _lib.c_dp)))
+        return out.value, shape.value
+
     def debug_phase_clocks(self, entity: int):
         out = np.zeros(7)
         n = C.c_int64()

@@ -114,16 +114,16 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         for e, en in zip(ents, rel.entities):
             mj = en.model
             if en.hasFeatures():
-                mu_matrix = eng.mu_plus_uhat(e, mj.mu)  # uhat = (F·beta)', mu .+ uhat, on the device (:102-104)
-                eng.sample_mode_dev_mu(e, mj.Lambda)
+                eng.update_uhat(e, mj.mu)               # uhat = (F·beta)', mu_matrix = mu .+ uhat, on the device (:102-104)
+                eng.sample_mode_uhat(e, mj.Lambda, None)
             else:
                 eng.sample_mode(e, mj.mu, mj.Lambda, None)
             nu, Tinv = mj.nu0, mj.WI
             if en.hasFeatures():
-                N, NU, NS = eng.nw_stats(e, subtract_uhat=True)
+                N, NU, NS = eng.nw_stats_uhat(e)
                 if full_lambda_u:
                     nu = nu + mj.beta.shape[0]
-                    Tinv = Tinv + eng.btb(e) * en.lambda_beta
+                    Tinv = Tinv + eng.beta_gram(e) * en.lambda_beta
             else:
                 N, NU, NS = eng.nw_stats(e)
             if host_noise is not None:
@@ -135,8 +135,12 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         # update_beta! — src/macau.jl:138-140, src/sampling.jl:361-370
         for e, en in zip(ents, rel.entities):
             if en.hasFeatures():
-                en.lambda_beta = eng.update_beta(e, en.model.mu, en.model.Lambda, en.lambda_beta, en.use_FF, tol_arg,
-                                                 en.lambda_beta_sample, en.nu, en.mu, host_noise)
+                eng.sample_beta(e, en.model.mu, en.model.Lambda, en.lambda_beta, tol_arg)
+                if en.lambda_beta_sample:
+                    g = float("nan")
+                    if host_noise is not None:
+                        g = host_noise.standard_gamma((en.nu + en.F.shape[1] * D) / 2.0)
+                    en.lambda_beta, _ = eng.sample_lambda_beta(e, en.model.Lambda, en.nu, en.mu, g)
         eng.advance_sweep()
 
         probe_rat = eng.predict(r_id, rel.test_ids) if ntest else np.zeros(0)

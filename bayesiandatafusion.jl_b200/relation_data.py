@@ -227,3 +227,25 @@ class RelationData:
                 en.use_FF = en.F.shape[1] <= compute_ff_size
         for r in self.relations:
             r.model.mean_value = r.data.valueMean()
+
+
+class SparseBinMatrix:
+    """src/parallel_matrix.jl:9-24 — a 0/1 matrix held as COO index lists (Int32, 1-based, no values). m, n default to
+    the largest index (:23). Passing it as `feat1=` / `Entity(F=…)` puts the feature products and the beta CG solve on
+    the device."""
+
+    def __init__(self, rows, cols, m=None, n=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        if len(rows) != len(cols):
+            raise ValueError("DimensionMismatch: length(rows) must equal length(cols)")
+        self.rows, self.cols = rows, cols
+        self.m = int(rows.max()) if m is None else int(m)
+        self.n = int(cols.max()) if n is None else int(n)
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def size(self, d=None):
+        return self.shape if d is None else self.shape[d - 1]

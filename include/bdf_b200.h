@@ -112,6 +112,49 @@ int64_t bdf_launch_count(const bdf_t* h);
  * + mean_value. ids: ntest×K column-major, 1-based. */
 int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yhat);
 
+/* ---- Macau side features: the link-matrix (beta) path ------------------------------------------------------------- */
+
+/* Entity(F = SparseBinMatrix(m, n, rows, cols)) — src/parallel_matrix.jl:9-24: registers a sparse 0/1 feature matrix given
+ * as COO index lists (Int32, 1-based, any order, duplicates counted twice). Builds the CSR of F (the SparseBinMatrixCSR
+ * constructor, src/sparsebin_csr.jl:22-37: stable sort by row) and of Fᵀ on the device, allocates beta = zeros(n, D)
+ * (src/RelationData.jl:76). m must equal the entity count (src/RelationData.jl:263-268). */
+int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols);
+/* Parity hook: the device CSR in the reference's representation — row_ptr (m+1, or n+1 for the transpose) and col_ind
+ * (nnz), Int32, 1-based (fields of SparseBinMatrixCSR, src/sparsebin_csr.jl:6-11). */
+int bdf_debug_features_csr(bdf_t* h, int entity, int transpose, int32_t* ptr_out, int32_t* ind_out);
+/* The feature-operator duck type (src/RelationData.jl:314-329): F*X (transpose == 0, X is n×ncol → Y m×ncol) and
+ * At_mul_B(F, X) (transpose != 0, X is m×ncol → Y n×ncol); A_mul_B!/At_mul_B! of src/parallel_matrix.jl:242-267 and
+ * src/sparsebin_csr.jl:49-63 for ncol columns at once. Column-major host matrices, ncol <= num_latent. */
+int bdf_spmm(bdf_t* h, int entity, int transpose, const double* X, int ncol, double* Y);
+/* AtA_mul_B!(y, F, x, lambda): y = Fᵀ(F·x) + lambda·x — src/parallel_cg.jl:7-14. */
+int bdf_ata_mul(bdf_t* h, int entity, const double* x, double lambda, double* y);
+/* solve_cg2(Frefs, rhs, lambda; tol, maxiter) — src/parallel_matrix.jl:488-507 — one cg_AtA (src/parallel_cg.jl:63-94) per
+ * column, all num_latent columns advanced together with per-column scalars and convergence masks. rhs, x: n×ncol
+ * column-major, ncol == num_latent; tol NaN → eps()·n (src/sampling.jl:294-296); maxiter <= 0 → n; iters (ncol) may be NULL. */
+int bdf_cg_solve(bdf_t* h, int entity, const double* rhs, int ncol, double lambda, double tol, int64_t maxiter, double* x, int* iters);
+/* model.beta in / out (n × num_latent, column-major). */
+int bdf_set_beta(bdf_t* h, int entity, const double* beta);
+int bdf_get_beta(bdf_t* h, int entity, double* beta);
+/* mj.uhat = F_mul_beta(en)'; mu_matrix = mj.mu .+ mj.uhat — src/macau.jl:102-104, src/RelationData.jl:314-320. The per-row mean
+ * stays on the device for bdf_sample_mode_uhat; uhat_out (D×N) may be NULL. */
+int bdf_update_uhat(bdf_t* h, int entity, const double* mu, double* uhat_out);
+/* sample_latent_all2!(..., mu_matrix, Lambda) — src/macau.jl:105 — with the mu_matrix of the last bdf_update_uhat. */
+int bdf_sample_mode_uhat(bdf_t* h, int entity, const double* Lambda, const double* z);
+/* ConditionalNormalWishart reductions of U = mj.sample - mj.uhat — src/macau.jl:124. */
+int bdf_nw_stats_uhat(bdf_t* h, int entity, double* N, double* NU, double* NS);
+/* mj.beta' * mj.beta (D×D) — src/macau.jl:128, src/sampling.jl:138. */
+int bdf_beta_gram(bdf_t* h, int entity, double* BtB);
+/* sample_beta(entity, sample .- mu, Lambda_u, lambda_beta, use_ff = false, tol) — src/sampling.jl:291-312, via update_beta!
+ * (:361-370): rhs = Fᵀ((U - mu)ᵀ + E1c) + sqrt(lambda_beta)·E2c with E·c = chol_lower(inv(Lambda))·E, then CG. E1 (D×N) and
+ * E2 (D×n) are the injected standard normals behind rand(mv, N) and rand(mv, numF) (consumed in that order); NULL → Philox.
+ * beta stays on the device; beta_out / rhs_out (n×D, column-major) and iters_out (D) may be NULL. */
+int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda, double lambda_beta, double tol, const double* E1,
+                    const double* E2, double* beta_out, double* rhs_out, int* iters_out);
+/* sample_lambda_beta(beta, Lambda_u, nu, mu) — src/sampling.jl:136-142. gamma_variate = the injected Gamma(shape, 1) draw behind
+ * rand(Gamma(b, c)), NaN → Philox. shape_out may be NULL. */
+int bdf_sample_lambda_beta(bdf_t* h, int entity, const double* Lambda, double nu, double mu, double gamma_variate, double* lambda_beta_out,
+                           double* shape_out);
+
 #ifdef __cplusplus
 }
 #endif
