@@ -1,0 +1,117 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no CUDA calls)."""
+import math
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import bdf_b200
+from bdf_b200.shard import ShardPlan
+
+
+def test_indexed_df_known_answers():
+    # test/basic.jl:7-49
+    X = bdf_b200.IndexedDF(np.array([[2, 1], [2, 3], [3, 4]]), [0.0, -1.0, 0.5], [4, 4])
+    assert X.nnz() == 3 and X.size() == (4, 4)
+    assert X.getCount(1, 2) == 2 and X.getCount(1, 1) == 0 and X.getCount(2, 2) == 0
+    X2a = bdf_b200.IndexedDF(np.array([[2, 1], [2, 1], [3, 4]]), [0.4, -1, -9])
+    assert X2a.size() == (3, 4)
+    X3 = X.removeSamples([2])
+    assert X3.nnz() == 2 and X3.size() == (4, 4) and X3.getCount(1, 2) == 1
+    with pytest.raises(IndexError):
+        bdf_b200.IndexedDF(np.array([[5, 1]]), [1.0], [4, 4])
+
+
+def test_relation_and_entities():
+    # test/basic.jl:51-90
+    ids = np.array([[1, 1], [2, 3], [2, 1], [3, 4], [2, 4]])
+    vals = np.array([0.4, 1.0, -1.9, 1.4, 0.85])
+    e1, e2, e3 = bdf_b200.Entity("e1"), bdf_b200.Entity("e2"), bdf_b200.Entity("e3")
+    r2 = bdf_b200.Relation(bdf_b200.IndexedDF(ids, vals), "r2", [e1, e2])
+    assert e1.count == 3 and e2.count == 4 and r2.size() == (3, 4)
+    bdf_b200.setTest(r2, np.array([[1, 3], [2, 4]]), [0.1, -0.2])
+    assert r2.numTest() == 2 and r2.numData() == 5
+    bdf_b200.setPrecision(r2, 1.75)
+    assert r2.model.alpha == 1.75
+    r3 = bdf_b200.Relation(bdf_b200.IndexedDF(np.array([[1, 5]]), [0.1]), "r3", [e2, e3])
+    assert e3.count == 5 and r3.size() == (4, 5)
+    with pytest.raises(ValueError):
+        bdf_b200.Relation(bdf_b200.IndexedDF(np.array([[5, 4]]), [0.1]), "r4", [e1, e3])
+
+
+def test_relation_data_from_sparse_and_test_split():
+    rng = np.random.default_rng(0)
+    Y = sp.random(15, 10, 0.3, random_state=1, format="csc")
+    rd = bdf_b200.RelationData(Y, class_cut=0.5)
+    rel = rd.relations[0]
+    n0 = rel.numData()
+    bdf_b200.assignToTest(rel, 2, rng)
+    assert rel.numTest() == 2 and len(rel.test_label) == 2 and rel.numData() == n0 - 2
+    assert [e.count for e in rd.entities] == [15, 10]
+    rd.reset(4)
+    m = rd.entities[0].model
+    # initModel! — src/RelationData.jl:66-90
+    assert m.sample.shape == (15, 4) and not m.sample.any() and np.array_equal(m.Lambda, 5 * np.eye(4))
+    assert m.b0 == 2.0 and m.nu0 == 4 and np.array_equal(m.WI, np.eye(4))
+    assert rd.entities[0].modes == [1] and rd.entities[1].modes_other == [[1]]
+    assert abs(rel.model.mean_value - rel.data.values.mean()) < 1e-15
+    with pytest.raises(ValueError):
+        bdf_b200.RelationData(Y, feat1=sp.identity(3, format="csc"))
+    # tensor form (DataFrame constructor, src/RelationData.jl:278-289)
+    ids = np.stack([rng.integers(1, 6, 30), rng.integers(1, 5, 30), rng.integers(1, 3, 30)], 1)
+    rdt = bdf_b200.RelationData((ids, rng.standard_normal(30), [5, 4, 2]), names=["A", "B", "C"])
+    assert [e.name for e in rdt.entities] == ["A", "B", "C"] and len(rdt.relations[0].entities) == 3
+
+
+def test_sparse_bin_matrix_and_errors():
+    rows = np.concatenate([np.arange(1, 201), np.arange(151, 351)])
+    cols = np.concatenate([np.arange(151, 351), np.arange(1, 400, 2)])
+    sbm = bdf_b200.SparseBinMatrix(rows, cols)
+    assert sbm.shape == (350, 399) and sbm.rows.dtype == np.int32  # test/parallel_matrix.jl:47-48
+    with pytest.raises(ValueError):
+        bdf_b200.SparseBinMatrix(np.append(rows, 1), cols)          # test/parallel_matrix.jl:64
+
+
+def test_auc_clamp_and_binary_io():
+    assert bdf_b200.AUC_ROC([True, True, False, False], [0.9, 0.8, 0.3, 0.1]) == 1.0
+    assert bdf_b200.AUC_ROC([True, False, True, False], [0.9, 0.8, 0.3, 0.1]) == 0.75
+    assert bdf_b200.AUC_ROC([True, False], [0.5, 0.5]) == 0.5
+    assert math.isnan(bdf_b200.AUC_ROC([True, True], [0.1, 0.2]))
+    from bdf_b200.macau import makeClamped
+
+    assert list(makeClamped(np.array([0.0, 3.0, 9.0]), [1.0, 5.0])) == [1.0, 3.0, 5.0]
+    X = np.arange(12, dtype=np.float32).reshape(4, 3)  # 4 instances × 3 latents
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.binary")
+        bdf_b200.write_binary_matrix(p, X)
+        hdr = np.fromfile(p, dtype=np.int64, count=2)
+        assert list(hdr) == [3, 4]                        # Int64 nrows (latents), ncols (instances): src/data_reading.jl:93-99
+        assert np.array_equal(bdf_b200.read_binary_float32(p), X)
+
+
+def test_macau_rejects_what_is_not_on_the_device_path():
+    Y = sp.random(15, 10, 0.3, random_state=1, format="csc")
+    rd = bdf_b200.RelationData(Y, alpha_sample=True)
+    with pytest.raises(NotImplementedError):
+        bdf_b200.macau(rd, burnin=1, psamples=1, verbose=False)
+    with pytest.raises(ValueError):
+        bdf_b200.macau(bdf_b200.RelationData(Y), backend="julia")
+
+
+def test_shard_plan_is_the_reference_cyclic_split():
+    for count, world in ((10, 1), (10, 3), (7, 8), (480000, 8)):
+        plan = ShardPlan(count, world)
+        rows = [plan.local_rows(r) for r in range(world)]
+        # ranges i:Nprocs:N of src/sampling.jl:154 (1-based there)
+        for r in range(world):
+            assert np.array_equal(rows[r], np.arange(r, count, world))
+            assert plan.nlocal(r) == len(rows[r])
+        assert sorted(np.concatenate(rows)) == list(range(count))
+        slots = plan.slot(np.arange(count))
+        assert len(set(slots)) == count and slots.max() < world * plan.nper
+        for r in range(world):
+            assert np.array_equal(np.sort(slots[rows[r]]), np.arange(r * plan.nper, r * plan.nper + len(rows[r])))
+        U = np.random.default_rng(0).standard_normal((count, 3))
+        assert np.array_equal(plan.from_slots(plan.to_slots(U)), U)
