@@ -1,0 +1,116 @@
+# BDFCuda.jl — reference-side binding of libbdf_b200.so (include/bdf_b200.h) for BayesianDataFusion.jl.
+#
+# NOT runnable in the build image (no Julia there); the ABI it binds is pinned by tests/test_abi.py and exercised
+# through the identical ctypes table in bayesiandatafusion.jl_b200/_lib.py. Written for Julia 0.4/0.5 syntax like the
+# reference (`Ptr{Void}`; on Julia >= 0.7 replace with `Ptr{Cvoid}`).
+#
+# Usage inside src/macau.jl (see INTEGRATION.md): `macau(data; backend = :cuda, devices = [0])` swaps
+#   sample_latent_all2!      -> BDFCuda.sample_mode!
+#   ConditionalNormalWishart -> BDFCuda.nw_stats + BDFCuda.nw_sample
+#   update_beta!             -> BDFCuda.sample_beta! / BDFCuda.sample_lambda_beta
+#   pred                     -> BDFCuda.predict
+module BDFCuda
+
+const LIB = get(ENV, "BDF_B200_LIB", "libbdf_b200.so")
+
+type Handle
+  ptr::Ptr{Void}
+end
+
+function check(h::Handle, rc::Cint)
+  if rc != 0
+    msg = bytestring(ccall((:bdf_last_error, LIB), Ptr{UInt8}, (Ptr{Void},), h.ptr))
+    rc == -1 && throw(ArgumentError(msg))   # BDF_ERR_INVALID ~ DimensionMismatch / ArgumentError in the reference
+    error("libbdf_b200 ($rc): $msg")
+  end
+  nothing
+end
+
+function create(num_latent::Int; device::Int = 0, rank::Int = 0, world::Int = 1)
+  out = Ref{Ptr{Void}}(C_NULL)
+  rc = ccall((:bdf_create, LIB), Cint, (Ptr{Ptr{Void}}, Cint, Cint, Cint, Cint), out, device, num_latent, rank, world)
+  rc == 0 || error(bytestring(ccall((:bdf_last_error, LIB), Ptr{UInt8}, (Ptr{Void},), C_NULL)))
+  h = Handle(out[])
+  finalizer(h, x -> ccall((:bdf_destroy, LIB), Cint, (Ptr{Void},), x.ptr))
+  return h
+end
+
+add_entity(h::Handle, count::Integer) = ccall((:bdf_add_entity, LIB), Cint, (Ptr{Void}, Int64), h.ptr, count)
+
+## FastIDF(rel.data) — ids is nnz x K Int64 (1-based), values Float64
+function add_relation(h::Handle, entities::Vector{Cint}, ids::Matrix{Int64}, values::Vector{Float64})
+  r = ccall((:bdf_add_relation, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cint}, Int64, Ptr{Int64}, Ptr{Cdouble}),
+            h.ptr, size(ids, 2), entities, size(ids, 1), ids, values)
+  r >= 0 || check(h, r)
+  return r
+end
+
+set_relation_params(h::Handle, rel, alpha, mean_value) =
+  check(h, ccall((:bdf_set_relation_params, LIB), Cint, (Ptr{Void}, Cint, Cdouble, Cdouble), h.ptr, rel, alpha, mean_value))
+
+## model.sample (D x N, column-major) in / out
+set_factors(h::Handle, entity, U::Matrix{Float64}) = check(h, ccall((:bdf_set_factors, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, entity, U))
+get_factors!(h::Handle, entity, U::Matrix{Float64}) = check(h, ccall((:bdf_get_factors, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, entity, U))
+
+## sample_latent_all2!(rel, dataRefs, procs, mode, mu_u, Lambda_u) — src/sampling.jl:149
+function sample_mode!(h::Handle, entity, mu_u::Vector{Float64}, Lambda_u::Matrix{Float64}; z = C_NULL)
+  check(h, ccall((:bdf_sample_mode, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+                 h.ptr, entity, mu_u, 0, Lambda_u, z))
+end
+function sample_mode!(h::Handle, entity, mu_u::Matrix{Float64}, Lambda_u::Matrix{Float64}; z = C_NULL)
+  check(h, ccall((:bdf_sample_mode, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+                 h.ptr, entity, mu_u, size(mu_u, 1), Lambda_u, z))
+end
+
+## N, NU, NS of ConditionalNormalWishart — src/sampling.jl:117-119
+function nw_stats(h::Handle, entity, D::Int)
+  N = Ref{Cdouble}(0.0); NU = zeros(D); NS = zeros(D, D)
+  check(h, ccall((:bdf_nw_stats, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, N, NU, NS))
+  return N[], NU, NS
+end
+
+## rand(ConditionalNormalWishart(U, mu0, b0, Tinv, nu)) with the Bartlett factor A and z drawn by the caller (or C_NULL)
+function nw_sample(h::Handle, entity, mu0::Vector{Float64}, b0, Tinv::Matrix{Float64}, nu; A = C_NULL, z = C_NULL)
+  D = length(mu0); mu = zeros(D); Lambda = zeros(D, D)
+  check(h, ccall((:bdf_nw_sample, LIB), Cint,
+                 (Ptr{Void}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                 h.ptr, entity, mu0, b0, Tinv, nu, A, z, mu, Lambda))
+  return mu, Lambda
+end
+
+## Entity(F = SparseBinMatrix(m, n, rows, cols))
+set_features_sbm(h::Handle, entity, m, n, rows::Vector{Int32}, cols::Vector{Int32}) =
+  check(h, ccall((:bdf_set_features_sbm, LIB), Cint, (Ptr{Void}, Cint, Int64, Int64, Int64, Ptr{Int32}, Ptr{Int32}),
+                 h.ptr, entity, m, n, length(rows), rows, cols))
+
+## the feature-operator duck type (src/RelationData.jl:314-329): a type CudaSBM can forward *, At_mul_B, AtA_mul_B! here
+function spmm(h::Handle, entity, X::Matrix{Float64}, nout::Int; transpose::Bool = false)
+  Y = zeros(nout, size(X, 2))
+  check(h, ccall((:bdf_spmm, LIB), Cint, (Ptr{Void}, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}), h.ptr, entity, transpose, X, size(X, 2), Y))
+  return Y
+end
+
+## sample_beta(entity, sample .- mu, Lambda_u, lambda_beta, false, tol) — src/sampling.jl:291
+function sample_beta!(h::Handle, entity, mu::Vector{Float64}, Lambda::Matrix{Float64}, lambda_beta, tol, numF::Int; E1 = C_NULL, E2 = C_NULL)
+  D = length(mu); beta = zeros(numF, D); rhs = zeros(numF, D); iters = zeros(Cint, D)
+  check(h, ccall((:bdf_sample_beta, LIB), Cint,
+                 (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                 h.ptr, entity, mu, Lambda, lambda_beta, tol, E1, E2, beta, rhs, iters))
+  return beta, rhs
+end
+
+function sample_lambda_beta(h::Handle, entity, Lambda::Matrix{Float64}, nu, mu; gamma_variate = NaN)
+  out = Ref{Cdouble}(0.0)
+  check(h, ccall((:bdf_sample_lambda_beta, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                 h.ptr, entity, Lambda, nu, mu, gamma_variate, out, C_NULL))
+  return out[]
+end
+
+## pred(rel, test_vec, test_F) without relation features — src/sampling.jl:9-14
+function predict(h::Handle, rel, ids::Matrix{Int64})
+  yhat = zeros(size(ids, 1))
+  check(h, ccall((:bdf_predict, LIB), Cint, (Ptr{Void}, Cint, Int64, Ptr{Int64}, Ptr{Cdouble}), h.ptr, rel, size(ids, 1), ids, yhat))
+  return yhat
+end
+
+end # module
