@@ -240,9 +240,16 @@ def run_ours(args):
     t_k = {e: float(np.mean(kt[e][1:])) for e in (e1, e2)}
     tot_fl, tot_t = fl[e1] + fl[e2], (t_k[e1] + t_k[e2]) / 1e3
     achieved = tot_fl / tot_t / 1e12
+    traffic = None
+    try:
+        if D == 100 and args.scale == 1.0 and world == 1:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "row_kernel_r01_traffic.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "kernel": "row_kernel (FP64 DMMA.8x8x4 per-row draw)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_note": "DRAM bytes of the users launch from the ncu --set full capture in profiles/ (partner rows are L2 hits)",
+        "peak_source": peak_src,
         "algorithmic_flops_per_launch": {"users": fl[e1], "items": fl[e2]}, "ms_per_launch": {"users": t_k[e1], "items": t_k[e2]},
         "share_of_step": (t_k[e1] + t_k[e2]) / (ms / args.steps),
     }
