@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbdf_b200.so")
+LIB_PATH = os.environ.get("BDF_B200_LIB") or os.path.join(HERE, "libbdf_b200.so")
 
 c_dp = C.POINTER(C.c_double)
 c_i64p = C.POINTER(C.c_int64)

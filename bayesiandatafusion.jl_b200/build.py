@@ -48,15 +48,21 @@ def _compile(args):
 
 def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> str:
     deps = _sources()
-    if not force and not _stale(LIB, deps):
+    if not force and not os.environ.get("BDF_BUILD_DPS") and not _stale(LIB, deps):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if ptxas_v else []
-    jobs = [(os.path.join(CSRC, "engine.cu"), os.path.join(OBJ, "engine.o"), extra),
-            (os.path.join(CSRC, "features.cu"), os.path.join(OBJ, "features.o"), extra)]
+    jobs = []
+    for name in ("engine", "features"):
+        if force or _stale(os.path.join(OBJ, f"{name}.o"), deps):
+            jobs.append((os.path.join(CSRC, f"{name}.cu"), os.path.join(OBJ, f"{name}.o"), extra))
+    only = os.environ.get("BDF_BUILD_DPS")  # dev builds: recompile only these padded dimensions (others keep their objects)
+    extra_defs = os.environ.get("BDF_EXTRA_NVCC", "").split()
     for dp in DPS:
-        jobs.append((os.path.join(CSRC, "row_inst.cu"), os.path.join(OBJ, f"row_inst_{dp}.o"), [f"-DBDF_DP={dp}", *extra]))
-    jobs = [j for j in jobs if force or _stale(j[1], deps)]
+        if only and str(dp) not in only.split(",") and os.path.exists(os.path.join(OBJ, f"row_inst_{dp}.o")):
+            continue
+        jobs.append((os.path.join(CSRC, "row_inst.cu"), os.path.join(OBJ, f"row_inst_{dp}.o"), [f"-DBDF_DP={dp}", *extra, *extra_defs]))
+    jobs = [j for j in jobs if force or (only and "row_inst" in j[1]) or _stale(j[1], deps)]
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4) or 1) as ex:
         for obj, log in ex.map(_compile, jobs):
             if verbose or ptxas_v:

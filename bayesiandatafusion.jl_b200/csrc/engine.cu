@@ -260,6 +260,7 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
   h->launches++;
   p.alpha = rel.alpha; p.mean = rel.mean; p.D = h->D; p.rank = h->rank; p.world = h->world;
   p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag; p.dbg = dbg;
+  { const char* f = getenv("BDF_DEBUG_FLAGS"); p.flags = f ? atoi(f) : 0; }
   return launch_rows(h, p, mi.n_items, rel.K > 2);
 }
 
@@ -344,6 +345,8 @@ int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
   if ((ce = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   h->stream = h->own_stream;
   if ((ce = cudaMalloc((void**)&h->err_flag, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&h->work_counter, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  h->num_sms = prop.multiProcessorCount;
   cudaMemset(h->err_flag, 0, sizeof(int));
   if ((ce = cudaMalloc((void**)&h->scratch, sizeof(double) * ((size_t)4 * num_latent * num_latent + 4 * num_latent))) != cudaSuccess) return bail(ce, "cudaMalloc");
   if ((ce = cudaMalloc((void**)&h->lt, sizeof(double) * (64 * (size_t)(h->DP / 8) * (h->DP / 8 + 1) / 2 + h->DP))) != cudaSuccess) return bail(ce, "cudaMalloc");
@@ -368,7 +371,7 @@ int bdf_destroy(bdf_t* h) {
       cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk);
       cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
     }
-  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt);
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->work_counter);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return BDF_OK;

@@ -96,6 +96,8 @@ struct bdf_handle {
   size_t ws_bytes = 0;
   double* scratch = nullptr;  // 4 D×D matrices for the Normal-Wishart draw
   int* err_flag = nullptr;
+  int* work_counter = nullptr;  // work queue head of the persistent row kernel
+  int num_sms = 148;
   double* lt = nullptr;  // Λ in tile order + Λ·μ, rebuilt per half-sweep
   int64_t pst = 0;  // doubles per parked partial for this D
   std::string err;

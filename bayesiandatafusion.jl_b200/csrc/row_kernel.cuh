@@ -60,6 +60,9 @@ struct RowParams {
   uint64_t seed, sweep;
   int entity;
   int* err_flag;
+  int* work_counter;  // dynamic work queue of the persistent kernel (row_kernel_ws), zeroed before each launch
+  int n_items;
+  int flags;       // debug: bit 0 = return after the syrk (timing experiments only; results invalid)
   long long* dbg;  // optional per-item phase clocks [n_items][8] (bdf_debug_phase_clocks), else nullptr
 };
 
@@ -91,6 +94,16 @@ __device__ __forceinline__ void cp_async_wait() {
 // the rhs Σ v·r is carried as tile column D when that column is free and 16-byte pieces never straddle it
 __host__ __device__ constexpr bool use_aug(int D) { return (D & 1) == 0 && (D & 7) != 0; }
 
+// 1/sqrt(x) for x in the normal range: single-precision seed + two Newton steps in double (≈1 ulp); the pivots of a
+// positive-definite Λ* are far from the denormal/overflow range the library routine's slow path guards against.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
 __host__ __device__ constexpr int tri(int i) { return i * (i + 1) / 2; }
 // inverse of t = tri(I) + J, 0 <= J <= I (t < 2^20)
 __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
@@ -100,6 +113,19 @@ __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
   I = i;
   J = t - tri(i);
 }
+
+#ifndef BDF_K4_UNROLL
+#define BDF_K4_UNROLL 1
+#endif
+#ifndef BDF_FD_UNROLL
+#define BDF_FD_UNROLL 8
+#endif
+#ifndef BDF_BUILD_PREFETCH
+#define BDF_BUILD_PREFETCH 0
+#endif
+#ifndef BDF_UR_UNROLL
+#define BDF_UR_UNROLL 2
+#endif
 
 template <int DP_, int NW_, bool TENSOR_>
 struct RowKernel {
@@ -160,6 +186,8 @@ struct RowKernel {
     constexpr int NTW = C::ntiles(W);
     if constexpr (NTW > 0) {
       const double* base = buf + (lane & 3) * S + (lane >> 2);
+      constexpr int kUnrollK4 = BDF_K4_UNROLL;
+#pragma unroll kUnrollK4
       for (int k4 = 0; k4 < nk4; k4++) {
         double f[NF];
         static_for<NF>([&](auto r) {
@@ -356,6 +384,10 @@ struct RowKernel {
     }
 
     BDF_STAMP(3);
+    if (p.flags & 1) {
+      if (tid == 0 && acc[0][0] == 1.2345) p.Uout[0] = acc[0][1];
+      return;
+    }
     // ---- park the Gram tiles in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles) -----------
     warp_dispatch(warp, [&](auto w) {
       constexpr int W = decltype(w)::value;
@@ -367,12 +399,46 @@ struct RowKernel {
     });
     if (!aug && tid < D) rhs[tid] = fma(p.alpha, bsum, lmu[tid]);
     if (tid >= D && tid < DP) rhs[tid] = 0.0;
-    __syncthreads();
     // ---- Λ* = Λ + αG, rhs = Λμ + α·Σv·r (augmented row), identity on the padding — same code for every warp -------
+    // The pre-tiled Λ (L2 hits) is fetched for all of this warp's tiles before the barrier so the loads overlap it.
+#if BDF_BUILD_PREFETCH
+    {
+      constexpr int BT = (C::NT + NW - 1) / NW;
+      double2 lt[BT];
+#pragma unroll
+      for (int b = 0; b < BT; b++) {
+        const int t = warp + b * NW;
+        lt[b] = t < C::NT ? __ldg(reinterpret_cast<const double2*>(p.LT + 64 * t + 2 * lane)) : make_double2(0.0, 0.0);
+      }
+      __syncthreads();
+      const double alpha = p.alpha;
+      const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+      for (int b = 0; b < BT; b++) {
+        const int t = warp + b * NW;
+        if (t < C::NT) {
+          int I, J;
+          tri_coords(t, I, J);
+          const int i = 8 * I + r, j = 8 * J + 2 * q;
+          const double2 g = *reinterpret_cast<const double2*>(Tl + 64 * t + 2 * lane);
+          double2 v = lt[b];
+          if (i < D) {
+            if (j < D) v.x = fma(alpha, g.x, v.x);
+            if (j + 1 < D) v.y = fma(alpha, g.y, v.y);
+          } else if (aug && i == D) {
+            if (j < D) rhs[j] = fma(alpha, g.x, lmu[j]);
+            if (j + 1 < D) rhs[j + 1] = fma(alpha, g.y, lmu[j + 1]);
+          }
+          *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = v;
+        }
+      }
+    }
+#else
+    __syncthreads();
     {
       const double alpha = p.alpha;
       const int r = lane >> 2, q = lane & 3;
-#pragma unroll 4
+#pragma unroll 2
       for (int t = warp; t < C::NT; t += NW) {
         int I, J;
         tri_coords(t, I, J);
@@ -389,6 +455,7 @@ struct RowKernel {
         *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = v;
       }
     }
+#endif
     __syncthreads();
     BDF_STAMP(4);
 
@@ -401,22 +468,35 @@ struct RowKernel {
     auto factor_diag = [&](int pb) {
       // A_pp = W·Wᵀ by elimination from the last column to the first, in the DMMA accumulator layout (lane = 4·row+q
       // holds columns 2q, 2q+1); an identity block carried along ends up as W⁻¹, stored transposed in WvT[pb].
+      // The next pivot is formed from pre-update values as soon as the current scale is known, so its rsqrt overlaps
+      // the rank-1 update instead of waiting for it.
       const int r = lane >> 2, q = lane & 3;
       const double2 av = *reinterpret_cast<const double2*>(Tl + 64 * (tri(pb) + pb) + 2 * lane);
       double a0 = av.x, a1 = av.y;
       double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
-#pragma unroll 1
+      double piv = __shfl_sync(0xffffffffu, a1, 4 * 7 + 3);  // a_77
+      constexpr int kUnrollFD = BDF_FD_UNROLL;
+#pragma unroll kUnrollFD
       for (int j = 7; j >= 0; j--) {
         const int jq = j >> 1;
         const double sel = (j & 1) ? a1 : a0;
-        const double piv = __shfl_sync(0xffffffffu, sel, 4 * j + jq);
         if (!(piv > 0.0)) bad = true;
-        const double sc = rsqrt(piv);
+        const double sc = fast_rsqrt(piv);
+        // pre-update values needed for the next pivot: a_{j-1,j-1} and a_{j-1,j}
+        double pn = 0.0, pc = 0.0;
+        if (j > 0) {
+          pn = __shfl_sync(0xffffffffu, ((j - 1) & 1) ? a1 : a0, 4 * (j - 1) + ((j - 1) >> 1));
+          pc = __shfl_sync(0xffffffffu, sel, 4 * (j - 1) + jq);
+        }
         const double wij = __shfl_sync(0xffffffffu, sel, (lane & ~3) | jq) * sc;  // w_ij of this lane's row
         const double rj0 = __shfl_sync(0xffffffffu, a0, 4 * j + q) * sc;          // w_kj for this lane's two columns
         const double rj1 = __shfl_sync(0xffffffffu, a1, 4 * j + q) * sc;
         const double ej0 = __shfl_sync(0xffffffffu, e0, 4 * j + q) * sc;          // row j of W⁻¹
         const double ej1 = __shfl_sync(0xffffffffu, e1, 4 * j + q) * sc;
+        if (j > 0) {
+          const double w = pc * sc;
+          piv = fma(-w, w, pn);  // a_{j-1,j-1} − w_{j-1,j}²: identical to what the update below leaves in the tile
+        }
         if (r < j) {
           a0 = fma(-wij, rj0, a0);
           a1 = fma(-wij, rj1, a1);
@@ -435,7 +515,8 @@ struct RowKernel {
       const double* Pp = Tl + 64 * tri(pb) + fo;
       const double na0 = -Pp[64 * I], na1 = -Pp[64 * I + 32];
       double* trow = Tl + 64 * tri(I) + 2 * lane;
-#pragma unroll 2
+      constexpr int kUnrollUR = BDF_UR_UNROLL;
+#pragma unroll kUnrollUR
       for (int J = j0; J <= j1; J++) {
         const double b0 = Pp[64 * J], b1 = Pp[64 * J + 32];
         const double2 cv = *reinterpret_cast<const double2*>(trow + 64 * J);
@@ -524,28 +605,52 @@ struct RowKernel {
         ys[c] += z;
       }
       __syncwarp();
-      for (int I = 0; I < NB; I++) {
-        const int k = lane >> 2, q = lane & 3;
-        double s0 = 0.0, s1 = 0.0;
-        for (int c = q; c < 8 * I; c += 8) {
-          const double* tp = Tl + 64 * (tri(I) + (c >> 3)) + 8 * k + (c & 7);  // R_I[k][c], R_I[k][c+4]
-          s0 = fma(tp[0], xs[c], s0);
-          s1 = fma(tp[4], xs[c + 4], s1);
-        }
-        double sacc = s0 + s1;
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if (q == 0) ts[k] = ys[8 * I + k] - sacc;
-        __syncwarp();
-        double x0 = 0.0, x1 = 0.0;
+      // forward substitution R·x = v (R = Wᵀ, lower, block rows in the tiles): column-oriented — lane owns rows
+      // lane, lane+32, … of v in registers; once x_J is known every lane subtracts R[i][8J..8J+7]·x_J from its rows.
+      {
+        constexpr int NS = (DP + 31) / 32;
+        double vreg[NS];
 #pragma unroll
-        for (int kk = 0; kk < 8; kk += 2) {
-          x0 = fma(WvT[I * 64 + r8 * 8 + kk], ts[kk], x0);
-          x1 = fma(WvT[I * 64 + r8 * 8 + kk + 1], ts[kk + 1], x1);
+        for (int s2 = 0; s2 < NS; s2++) vreg[s2] = (lane + 32 * s2 < DP) ? ys[lane + 32 * s2] : 0.0;
+        for (int J = 0; J < NB; J++) {
+          // x_J = W_JJ⁻ᵀ·v_J : v_J sits in the registers of lanes 8J%32 … of slot 8J/32 → share it through ts
+          {
+            const int sl = (8 * J) >> 5;
+            double mine = 0.0;
+#pragma unroll
+            for (int s2 = 0; s2 < NS; s2++)
+              if (s2 == sl) mine = vreg[s2];
+            if ((lane >> 3) == ((8 * J) & 31) >> 3) ts[lane & 7] = mine;
+          }
+          __syncwarp();
+          double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 8; kk += 2) {
+            x0 = fma(WvT[J * 64 + r8 * 8 + kk], ts[kk], x0);
+            x1 = fma(WvT[J * 64 + r8 * 8 + kk + 1], ts[kk + 1], x1);
+          }
+          const double xj = x0 + x1;  // lane r8 (replicated over the 4 lane groups) holds x[8J + r8]
+          if (lane < 8) xs[8 * J + r8] = xj;
+          double xb[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) xb[k] = __shfl_sync(0xffffffffu, xj, k);
+#pragma unroll
+          for (int s2 = 0; s2 < NS; s2++) {
+            const int i = lane + 32 * s2;
+            if (i >= 8 * (J + 1) && i < DP) {
+              const double* tp = Tl + 64 * (tri(i >> 3) + J) + 8 * (i & 7);  // R[i][8J .. 8J+7]
+              const double2 t0 = *reinterpret_cast<const double2*>(tp), t1 = *reinterpret_cast<const double2*>(tp + 2);
+              const double2 t2 = *reinterpret_cast<const double2*>(tp + 4), t3 = *reinterpret_cast<const double2*>(tp + 6);
+              double a = fma(t0.x, xb[0], t0.y * xb[1]), b = fma(t1.x, xb[2], t1.y * xb[3]);
+              a = fma(t2.x, xb[4], fma(t2.y, xb[5], a));
+              b = fma(t3.x, xb[6], fma(t3.y, xb[7], b));
+              vreg[s2] -= a + b;
+            }
+          }
+          __syncwarp();
         }
-        if (lane < 8) xs[8 * I + r8] = x0 + x1;
-        __syncwarp();
       }
+      __syncwarp();
       double* out = p.Uout + (size_t)slot * p.ld;
       for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[j] : 0.0;
       __syncwarp();
@@ -555,8 +660,11 @@ struct RowKernel {
 #undef BDF_STAMP
 };
 
+#ifndef BDF_MINB
+#define BDF_MINB 3
+#endif
 template <class K>
-__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? 16 : (K::NW == 4 ? (K::TENSOR ? 4 : 6) : (K::TENSOR ? 2 : 3)))) row_kernel(const RowParams p) {
+__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? 16 : (K::NW == 4 ? (K::TENSOR ? 4 : 6) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
   extern __shared__ __align__(16) double smem_dyn[];
   K::run(p, smem_dyn);
 }
