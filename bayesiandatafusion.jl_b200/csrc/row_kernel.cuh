@@ -91,6 +91,35 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+// TMA 1-D bulk copy global → shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 // the rhs Σ v·r is carried as tile column D when that column is free and 16-byte pieces never straddle it
 __host__ __device__ constexpr bool use_aug(int D) { return (D & 1) == 0 && (D & 7) != 0; }
 
@@ -147,7 +176,7 @@ struct RowKernel {
   static constexpr int STG = KS * S * (TENSOR ? 2 : 1) + KS;   // doubles per stage: tile(s) + residuals
   static constexpr int PSZ = 64 * C::NT;  // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
   static constexpr int REGSZ = PSZ > NBUF * STG ? PSZ : NBUF * STG;  // the tiles alias the (dead) stage ring
-  static constexpr int SMEM_DOUBLES = REGSZ + NB * 64 + 4 * DP + 8;
+  static constexpr int SMEM_DOUBLES = REGSZ + NB * 64 + 4 * DP + 8 + 4;  // … + ts[8] + ring mbarriers
   static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
   // register-staged loader of the statistics kernel (stats_kernel.cuh)
   static constexpr int SPASSES = NW == 8 ? 2 : (NW == 4 ? 4 : 8);
@@ -229,7 +258,6 @@ struct RowKernel {
   // ---- the kernel body -------------------------------------------------------------------------------------
   static __device__ void run(const RowParams& p, double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tr = tid >> 4, tq = tid & 15;
     const int D = p.D;
     const bool aug = use_aug(D);
     const int item = blockIdx.x;
@@ -281,54 +309,59 @@ struct RowKernel {
           ring[b * STG + rr * S + col] = (TENSOR && rr >= KS && col == D) ? 1.0 : 0.0;  // second partner's aug column = 1
         }
     }
-    int cn0[GP], cn1[GP];  // partner slots of the stage that is issued next
-    double rn[GP];          // its residuals (threads with tq == 0)
-    // Metadata (partner slots, values) is fetched one stage ahead of its use with clamped addresses and NO dependent
-    // instruction, so the in-order issue never waits on these loads inside the stage loop.
-    auto load_meta = [&](int s) {
+    // Gather by TMA: lane k < KS of warp 0 owns observation k of a stage and moves its whole partner row (npc·16 bytes)
+    // with ONE 1-D bulk copy (cp.async.bulk → UBLKCP) that signals the stage's mbarrier by byte count; the other
+    // warps issue nothing. Partner slots / values are fetched one stage ahead of their use.
+    uint64_t* fullb = reinterpret_cast<uint64_t*>(ts + 8);
+    if (tid == 0) {
 #pragma unroll
-      for (int ps = 0; ps < GP; ps++) {
-        int64_t o = obeg + (int64_t)s * KS + tr + ps * OPP;
+      for (int b = 0; b < NBUF; b++) mbar_init(fullb + b, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t rowbytes = (uint32_t)npc * 16u;
+    int c0n = 0, c1n = 0;
+    double rvn = 0.0;
+    auto load_meta = [&](int s) {
+      if (tid < KS) {
+        int64_t o = obeg + (int64_t)s * KS + tid;
         if (o >= oend) o = oend - 1;
-        if (o < obeg) o = obeg;
-        cn0[ps] = __ldg(p.col0 + o);
-        if (TENSOR) cn1[ps] = __ldg(p.col1 + o);
-        rn[ps] = __ldg(p.val + o);
+        c0n = __ldg(p.col0 + o);
+        if (TENSOR) c1n = __ldg(p.col1 + o);
+        rvn = __ldg(p.val + o);
       }
     };
     auto issue = [&](int s) {
-      double* st = ring + (s % NBUF) * STG;
-#pragma unroll
-      for (int ps = 0; ps < GP; ps++) {
-        const int k = tr + ps * OPP;
-        const bool ok = s * KS + k < len;
-        const double* src0 = p.P0 + (size_t)cn0[ps] * p.ld;
-        const double* src1 = TENSOR ? p.P1 + (size_t)cn1[ps] * p.ld : nullptr;
-#pragma unroll
-        for (int j = 0; j < JP; j++) {
-          const int pc = tq + 16 * j;
-          if (pc < npc) {
-            cp_async16(st + k * S + 2 * pc, src0 + 2 * pc, ok ? 16 : 0);
-            if (TENSOR) cp_async16(st + (KS + k) * S + 2 * pc, src1 + 2 * pc, ok ? 16 : 0);
+      if (tid < KS) {
+        const int b = s % NBUF;
+        double* st = ring + b * STG;
+        int nvalid = len - s * KS;
+        if (nvalid > KS) nvalid = KS;
+        const bool ok = tid < nvalid;
+        if (tid == 0) mbar_arrive_expect_tx(fullb + b, (uint32_t)nvalid * rowbytes * (TENSOR ? 2u : 1u));
+        if (ok) {
+          bulk_copy_g2s(st + tid * S, p.P0 + (size_t)c0n * p.ld, rowbytes, fullb + b);
+          if (TENSOR) bulk_copy_g2s(st + (KS + tid) * S, p.P1 + (size_t)c1n * p.ld, rowbytes, fullb + b);
+        } else if (tid < ((nvalid + 3) & ~3)) {
+          // rows of the last, partly filled k-step: zero them (only the final stage of an item ever takes this path)
+          for (int c = 0; c < 2 * npc; c += 2) {
+            *reinterpret_cast<double2*>(st + tid * S + c) = make_double2(0.0, 0.0);
+            if (TENSOR) *reinterpret_cast<double2*>(st + (KS + tid) * S + c) = make_double2(0.0, 0.0);
           }
         }
-        if (tq == 0) {
-          const double r = ok ? rn[ps] - p.mean : 0.0;
-          st[(TENSOR ? 2 : 1) * KS * S + k] = r;
-          if (aug) st[k * S + D] = r;
-        }
+        const double r = ok ? rvn - p.mean : 0.0;
+        st[(TENSOR ? 2 : 1) * KS * S + tid] = r;
+        if (aug) st[tid * S + D] = r;
       }
-      cp_async_commit();
     };
     BDF_STAMP(1);
-    __syncthreads();  // ring zero-fill visible before any stage is consumed
+    __syncthreads();  // ring zero-fill and barrier init visible before any stage is issued or consumed
     if (nst > 0) { load_meta(0); issue(0); }
-    if (nst > 1) { load_meta(1); issue(1); } else cp_async_commit();
+    if (nst > 1) { load_meta(1); issue(1); }
     if (nst > 2) load_meta(2);
     for (int s = 0; s < nst; s++) {
-      cp_async_wait<1>();
-      __syncthreads();  // stage s has landed for every thread; everyone is done with stage s-1
-      if (s + 2 < nst) issue(s + 2); else cp_async_commit();
+      mbar_wait(fullb + (s % NBUF), (s / NBUF) & 1);  // the rows of stage s have landed
+      __syncthreads();                                // everyone is done with stage s-1: its buffer may be refilled
+      if (s + 2 < nst) issue(s + 2);
       if (s + 3 < nst) load_meta(s + 3);
       const double* buf = ring + (s % NBUF) * STG;
       const double* rs = buf + (TENSOR ? 2 : 1) * KS * S;
@@ -344,7 +377,6 @@ struct RowKernel {
         }
       }
     }
-    cp_async_wait<0>();
     __syncthreads();  // the ring is dead from here on
 
     BDF_STAMP(2);
