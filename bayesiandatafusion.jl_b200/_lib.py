@@ -57,6 +57,7 @@ SIGNATURES = {
     "bdf_nw_stats_uhat": (C.c_int, [H, C.c_int, c_dp, c_dp, c_dp]),
     "bdf_beta_gram": (C.c_int, [H, C.c_int, c_dp]),
     "bdf_sample_beta": (C.c_int, [H, C.c_int, c_dp, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip]),
+    "bdf_debug_ata_time": (C.c_int, [H, C.c_int, C.c_int, c_dp]),
     "bdf_sample_lambda_beta": (C.c_int, [H, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, c_dp, c_dp]),
 }
 

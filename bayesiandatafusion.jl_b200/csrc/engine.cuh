@@ -61,6 +61,10 @@ struct EntityS {
   double* uhat = nullptr;       // slots × ld, (F·beta)
   double* cgbuf = nullptr;      // CG work vectors
   double* btb = nullptr;        // [numF, colsum(D), betaᵀbeta(D×D)] in the stats layout
+  void* sp_items[2] = {nullptr, nullptr};  // SpMM work lists (rows / SPLIT-index chunks of long rows) for F and Fᵀ
+  void* sp_long[2] = {nullptr, nullptr};   // the split rows and their partial slots
+  int sp_nitems[2] = {0, 0}, sp_nlong[2] = {0, 0};
+  void* sp_part = nullptr;                 // chunk partials (slots × ld)
 };
 
 }  // namespace bdf

@@ -35,36 +35,80 @@ inline int grid_for(int64_t n, int block = 256) {
   return (int)g;
 }
 
-// ---- Y[r,:] = init + Σ_{e in row r} X[idx[e],:]  (one warp per row, lanes over the columns, sum in stored order) -----
-// init: 0, or lam·P[r,:] (the "+λx" of AtA_mul_B!, src/parallel_cg.jl:10-12 — added last, as the reference does).
-__global__ void __launch_bounds__(256) spbin_gather_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nrows,
-                                                           const double* __restrict__ X, double* __restrict__ Y, int ld, double lam,
-                                                           const double* __restrict__ P) {
+// ---- Y[r,:] = Σ_{e in row r} X[idx[e],:] (+ lam·P[r,:])  — one warp per work item, lane l owns columns l, l+32, … -----------
+// A work item is a whole row (≤ SPLIT indices: summed strictly in stored order = the reference's order, bit-exact) or one
+// SPLIT-index chunk of a longer row (popular feature bits reach 10⁵ entries); chunk partials are added in chunk order by
+// spbin_reduce_kernel, so the result is deterministic. Indices are fetched 32 at a time (one coalesced 128-byte load per
+// warp), broadcast by shuffle, and 8 gathers are kept in flight before their in-order accumulation.
+struct SpItem {
+  int32_t row;    // output row
+  int32_t slot;   // -1: write Y[row] directly; else partial slot in the workspace
+  int64_t beg, end;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256) spbin_gather_kernel(const SpItem* __restrict__ items, int n_items, const int32_t* __restrict__ idx,
+                                                           const double* __restrict__ X, double* __restrict__ Y, double* __restrict__ part, int ld,
+                                                           double lam, const double* __restrict__ P) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int npair = ld >> 1;  // double2 pieces per row (ld is a multiple of 4)
-  for (int64_t r = warp0; r < nrows; r += nwarps) {
-    const int64_t b = ptr[r], e = ptr[r + 1];
-    double2 acc[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};  // ld ≤ 128 → ≤ 64 pairs → ≤ 2 per lane
-    for (int64_t o = b; o < e; o += 32) {
-      const int n = (int)min((int64_t)32, e - o);
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int it = warp0; it < n_items; it += nwarps) {
+    const SpItem w = items[it];
+    double acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) acc[k] = 0.0;
+    for (int64_t o = w.beg; o < w.end; o += 32) {
+      const int n = (int)min((int64_t)32, w.end - o);
       const int mine = lane < n ? __ldg(idx + o + lane) : 0;
-      for (int j = 0; j < n; j++) {
-        const int c = __shfl_sync(0xffffffffu, mine, j);
-        const double2* src = reinterpret_cast<const double2*>(X + (size_t)c * ld);
-        if (lane < npair) { const double2 v = __ldg(src + lane); acc[0].x += v.x; acc[0].y += v.y; }
-        if (lane + 32 < npair) { const double2 v = __ldg(src + lane + 32); acc[1].x += v.x; acc[1].y += v.y; }
+      for (int j0 = 0; j0 < n; j0 += 8) {
+        double v[8][NC];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int c = __shfl_sync(0xffffffffu, mine, (j0 + u) & 31);
+          const double* src = X + (size_t)c * ld + lane;
+#pragma unroll
+          for (int k = 0; k < NC; k++) v[u][k] = (j0 + u < n && lane + 32 * k < ld) ? __ldg(src + 32 * k) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+          for (int k = 0; k < NC; k++) acc[k] += v[u][k];  // +0.0 for the padded slots leaves the sum bit-identical
       }
     }
-    double2* dst = reinterpret_cast<double2*>(Y + (size_t)r * ld);
-    if (P) {
-      const double2* pp = reinterpret_cast<const double2*>(P + (size_t)r * ld);
-      if (lane < npair) { const double2 v = pp[lane]; acc[0].x += lam * v.x; acc[0].y += lam * v.y; }
-      if (lane + 32 < npair) { const double2 v = pp[lane + 32]; acc[1].x += lam * v.x; acc[1].y += lam * v.y; }
+    if (w.slot < 0) {
+      double* dst = Y + (size_t)w.row * ld + lane;
+#pragma unroll
+      for (int k = 0; k < NC; k++)
+        if (lane + 32 * k < ld) {
+          double s = acc[k];
+          if (P) s += lam * P[(size_t)w.row * ld + lane + 32 * k];
+          dst[32 * k] = s;
+        }
+    } else {
+      double* dst = part + (size_t)w.slot * ld + lane;
+#pragma unroll
+      for (int k = 0; k < NC; k++)
+        if (lane + 32 * k < ld) dst[32 * k] = acc[k];
     }
-    if (lane < npair) dst[lane] = acc[0];
-    if (lane + 32 < npair) dst[lane + 32] = acc[1];
+  }
+}
+
+// rows that were split: Y[row,:] = Σ_chunks partial (chunk order) (+ lam·P[row,:])
+struct SpLong {
+  int32_t row, nchunks;
+  int64_t slot0;
+};
+__global__ void spbin_reduce_kernel(const SpLong* __restrict__ rows, int nlong, const double* __restrict__ part, double* __restrict__ Y, int ld,
+                                    double lam, const double* __restrict__ P) {
+  for (int r = blockIdx.x; r < nlong; r += gridDim.x) {
+    const SpLong w = rows[r];
+    for (int d = threadIdx.x; d < ld; d += blockDim.x) {
+      double s = 0.0;
+      for (int c = 0; c < w.nchunks; c++) s += part[(size_t)(w.slot0 + c) * ld + d];
+      if (P) s += lam * P[(size_t)w.row * ld + d];
+      Y[(size_t)w.row * ld + d] = s;
+    }
   }
 }
 
@@ -333,12 +377,61 @@ int need_features(bdf_t* h, int entity) {
   return BDF_OK;
 }
 
-void spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr) {
-  const int64_t rows = transpose ? e.numF : e.N;
-  int64_t g = (rows * 32 + 255) / 256;
+int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr) {
+  const int o = transpose ? 1 : 0;
+  const SpItem* items = reinterpret_cast<const SpItem*>(e.sp_items[o]);
+  const int ni = e.sp_nitems[o];
+  int64_t g = ((int64_t)ni * 32 + 255) / 256;
   g = std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 8);
-  spbin_gather_kernel<<<(int)g, 256, 0, h->stream>>>(transpose ? e.f_colptr : e.f_rowptr, transpose ? e.f_rowind : e.f_colind, rows, X, Y, h->ld, lam, P);
+  const int32_t* idx = transpose ? e.f_rowind : e.f_colind;
+  const int nc = (h->ld + 31) / 32;
+  double* part = reinterpret_cast<double*>(e.sp_part);
+  switch (nc) {
+    case 1: spbin_gather_kernel<1><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
+    case 2: spbin_gather_kernel<2><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
+    case 3: spbin_gather_kernel<3><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
+    default: spbin_gather_kernel<4><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
+  }
   h->launches++;
+  if (e.sp_nlong[o] > 0) {
+    spbin_reduce_kernel<<<std::min(e.sp_nlong[o], 148 * 4), 128, 0, h->stream>>>(reinterpret_cast<const SpLong*>(e.sp_long[o]), e.sp_nlong[o], part, Y, h->ld, lam, P);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  return BDF_OK;
+}
+
+// work list of one orientation: rows with more than SPLIT indices are cut into SPLIT-index chunks
+int build_sp_items(bdf_t* h, EntityS& e, int o, const int64_t* d_ptr, int64_t nrows, int64_t* part_slots) {
+  const int64_t SPLIT = 1024;
+  std::vector<int64_t> ptr((size_t)nrows + 1);
+  CU(cudaMemcpyAsync(ptr.data(), d_ptr, 8 * ptr.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<SpItem> items;
+  std::vector<SpLong> longs;
+  int64_t slots = 0;
+  items.reserve((size_t)nrows);
+  for (int64_t r = 0; r < nrows; r++) {
+    const int64_t b = ptr[r], n = ptr[r + 1] - b;
+    if (n <= SPLIT) {
+      items.push_back({(int32_t)r, -1, b, b + n});
+    } else {
+      const int64_t nch = (n + SPLIT - 1) / SPLIT;
+      longs.push_back({(int32_t)r, (int32_t)nch, slots});
+      for (int64_t c = 0; c < nch; c++) items.push_back({(int32_t)r, (int32_t)(slots + c), b + c * SPLIT, std::min(b + n, b + (c + 1) * SPLIT)});
+      slots += nch;
+    }
+  }
+  std::stable_sort(items.begin(), items.end(), [](const SpItem& a, const SpItem& b) { return (a.end - a.beg) > (b.end - b.beg); });
+  e.sp_nitems[o] = (int)items.size();
+  e.sp_nlong[o] = (int)longs.size();
+  CU(cudaMalloc(&e.sp_items[o], std::max<size_t>(items.size(), 1) * sizeof(SpItem)));
+  CU(cudaMalloc(&e.sp_long[o], std::max<size_t>(longs.size(), 1) * sizeof(SpLong)));
+  if (!items.empty()) CU(cudaMemcpyAsync(e.sp_items[o], items.data(), items.size() * sizeof(SpItem), cudaMemcpyHostToDevice, h->stream));
+  if (!longs.empty()) CU(cudaMemcpyAsync(e.sp_long[o], longs.data(), longs.size() * sizeof(SpLong), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (slots > *part_slots) *part_slots = slots;
+  return BDF_OK;
 }
 
 // batched CG on (FᵀF + λI)X = B, all D columns at once; B, X device row-major (numF × ld). Returns per-column iteration counts.
@@ -441,6 +534,13 @@ int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz
   if (!rc) rc = build_orientation(h, d_cols, d_rows, nnz, n, (int32_t)m, &e.f_colptr, &e.f_rowind);
   cudaFree(d_rows); cudaFree(d_cols);
   if (rc) return rc;
+  {
+    int64_t slots = 0;
+    for (int o = 0; o < 2; o++) { cudaFree(e.sp_items[o]); cudaFree(e.sp_long[o]); e.sp_items[o] = e.sp_long[o] = nullptr; }
+    cudaFree(e.sp_part); e.sp_part = nullptr;
+    if ((rc = build_sp_items(h, e, 0, e.f_rowptr, m, &slots)) || (rc = build_sp_items(h, e, 1, e.f_colptr, n, &slots))) return rc;
+    CU(cudaMalloc(&e.sp_part, std::max<size_t>((size_t)slots * h->ld, 1) * sizeof(double)));
+  }
   const size_t bn = (size_t)n * h->ld, un = (size_t)e.Nper * h->world * h->ld;
   if ((rc = dalloc(h, &e.beta, bn)) || (rc = dalloc(h, &e.uhat, un)) || (rc = dalloc(h, &e.btb, (size_t)1 + h->D + (size_t)h->D * h->D))) return rc;
   CU(cudaMemsetAsync(e.beta, 0, bn * 8, h->stream));   // beta = zeros(numF, num_latent), src/RelationData.jl:76
@@ -647,6 +747,31 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   if (!rc) rc = bdf_check_err_flag(h); else cudaStreamSynchronize(h->stream);
   cleanup();
   return rc;
+}
+
+/* Profiling hook: `reps` device-resident applications of (FᵀF + λI) to the current beta (D columns at once), CUDA-event
+ * timed on the handle's stream; returns the mean milliseconds per application (two sparse-binary products). */
+int bdf_debug_ata_time(bdf_t* h, int entity, int reps, double* ms_per_apply) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  double *T = nullptr, *Z = nullptr;
+  if ((rc = dalloc(h, &T, (size_t)e.N * h->ld)) || (rc = dalloc(h, &Z, (size_t)e.numF * h->ld))) { cudaFree(T); return rc; }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  spmm(h, e, false, e.beta, T); spmm(h, e, true, T, Z, 1.0, e.beta);
+  cudaEventRecord(a, h->stream);
+  for (int i = 0; i < reps; i++) { spmm(h, e, false, e.beta, T); spmm(h, e, true, T, Z, 1.0, e.beta); }
+  cudaEventRecord(b, h->stream);
+  cudaEventSynchronize(b);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(T); cudaFree(Z);
+  if (ms_per_apply) *ms_per_apply = ms / reps;
+  return BDF_OK;
 }
 
 /* sample_lambda_beta(beta, Lambda_u, nu, mu) — src/sampling.jl:136-142. gamma_variate: the injected Gamma(shape, 1) draw

@@ -268,6 +268,11 @@ class Engine:
                                                  C.cast(C.byref(out), _lib.c_dp), C.cast(C.byref(shape), _lib.c_dp)))
         return out.value, shape.value
 
+    def debug_ata_time(self, entity: int, reps: int = 20) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.bdf_debug_ata_time(self.h, entity, reps, C.cast(C.byref(ms), _lib.c_dp)))
+        return ms.value
+
     def debug_phase_clocks(self, entity: int):
         out = np.zeros(7)
         n = C.c_int64()

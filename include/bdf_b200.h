@@ -150,6 +150,8 @@ int bdf_beta_gram(bdf_t* h, int entity, double* BtB);
  * beta stays on the device; beta_out / rhs_out (n×D, column-major) and iters_out (D) may be NULL. */
 int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda, double lambda_beta, double tol, const double* E1,
                     const double* E2, double* beta_out, double* rhs_out, int* iters_out);
+/* Profiling hook: mean milliseconds of one device-resident AtA_mul_B! (src/parallel_cg.jl:7-14) on all num_latent columns. */
+int bdf_debug_ata_time(bdf_t* h, int entity, int reps, double* ms_per_apply);
 /* sample_lambda_beta(beta, Lambda_u, nu, mu) — src/sampling.jl:136-142. gamma_variate = the injected Gamma(shape, 1) draw behind
  * rand(Gamma(b, c)), NaN → Philox. shape_out may be NULL. */
 int bdf_sample_lambda_beta(bdf_t* h, int entity, const double* Lambda, double nu, double mu, double gamma_variate, double* lambda_beta_out,

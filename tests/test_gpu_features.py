@@ -181,3 +181,24 @@ def test_macau_with_and_without_features_end_to_end():
     assert res2["RMSE"] < 0.7
     assert rd2.entities[0].model.beta.shape == (40, 6) and np.all(np.isfinite(rd2.entities[0].model.beta))
     assert rd2.entities[0].lambda_beta > 0
+
+
+def test_long_rows_are_chunked_deterministically():
+    """A popular feature bit (one column with 5000 entries > the 1024-index chunk) is summed as chunk partials added in
+    chunk order: deterministic, and equal to the reference's sequential sum to rounding."""
+    rng = np.random.default_rng(77)
+    m, n, D = 6000, 50, 32
+    rows = np.concatenate([rng.permutation(m)[:5000] + 1, rng.integers(1, m + 1, 3000)]).astype(np.int32)
+    cols = np.concatenate([np.full(5000, 7), rng.integers(1, n + 1, 3000)]).astype(np.int32)
+    eng, e1, *_ = engine_with_features(D, rows, cols, m, n, seed=3)
+    Xt = rng.standard_normal((m, D))
+    Y1 = eng.spmm(e1, Xt, transpose=True)
+    Y2 = eng.spmm(e1, Xt, transpose=True)
+    assert np.array_equal(Y1, Y2)
+    for d in (0, 5, 31):
+        want = orc.sbm_tmul(m, n, rows, cols, Xt[:, d])
+        assert rel_err(Y1[:, d], want) <= 1e-13
+        short = np.ones(n, dtype=bool)
+        short[6] = False
+        assert np.array_equal(Y1[short, d], want[short])   # rows within one chunk stay bit-exact
+    eng.close()
