@@ -703,10 +703,10 @@ int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, in
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
   const int ni = h->rels[e.uses[0].first].modes[e.uses[0].second].n_items;
   long long* d = nullptr;
-  CU(cudaMalloc((void**)&d, sizeof(long long) * 8 * (size_t)std::max(ni, 1)));
-  CU(cudaMemsetAsync(d, 0, sizeof(long long) * 8 * (size_t)std::max(ni, 1), h->stream));
+  CU(cudaMalloc((void**)&d, sizeof(long long) * 16 * (size_t)std::max(ni, 1)));
+  CU(cudaMemsetAsync(d, 0, sizeof(long long) * 16 * (size_t)std::max(ni, 1), h->stream));
   int rc = sample_entity(h, entity, e.mu, 0, e.Lambda, nullptr, d);
-  std::vector<long long> hbuf((size_t)8 * std::max(ni, 1));
+  std::vector<long long> hbuf((size_t)16 * std::max(ni, 1));
   cudaMemcpyAsync(hbuf.data(), d, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
   cudaFree(d);
@@ -721,6 +721,12 @@ int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, in
     cnt++;
   }
   for (int k = 0; k < 7; k++) mean_cycles[k] /= (double)std::max<int64_t>(cnt, 1);
+  if (getenv("BDF_DEBUG_PANEL")) {
+    double acc[8] = {0};
+    for (int i = 0; i < ni; i++) for (int k = 0; k < 8; k++) acc[k] += (double)hbuf[(size_t)ni * 8 + (size_t)i * 8 + k];
+    fprintf(stderr, "panel loop mean cycles per row: warp0 [scale %.0f, wait1 %.0f, trailing+diag %.0f, wait2 %.0f]  warp1 [scale %.0f, wait1 %.0f, backsub+trailing %.0f, wait2 %.0f]\n",
+            acc[0] / ni, acc[1] / ni, acc[2] / ni, acc[3] / ni, acc[4] / ni, acc[5] / ni, acc[6] / ni, acc[7] / ni);
+  }
   if (n_items) *n_items = cnt;
   return BDF_OK;
 }

@@ -126,7 +126,8 @@ __host__ __device__ constexpr bool use_aug(int D) { return (D & 1) == 0 && (D & 
 // 1/sqrt(x) for x in the normal range: single-precision seed + two Newton steps in double (≈1 ulp); the pivots of a
 // positive-definite Λ* are far from the denormal/overflow range the library routine's slow path guards against.
 __device__ __forceinline__ double fast_rsqrt(double x) {
-  double y = (double)rsqrtf((float)x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H seed (≈ 2^-20 relative), no conversions
   const double h = 0.5 * x;
   y = y * fma(-h * y, y, 1.5);
   y = y * fma(-h * y, y, 1.5);
@@ -153,7 +154,7 @@ __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
 #define BDF_BUILD_PREFETCH 0
 #endif
 #ifndef BDF_UR_UNROLL
-#define BDF_UR_UNROLL 2
+#define BDF_UR_UNROLL 4
 #endif
 
 template <int DP_, int NW_, bool TENSOR_>
@@ -295,6 +296,18 @@ struct RowKernel {
         for (int i = 0; i < D; i++) s = fma(__ldg(p.Lambda + tid + (size_t)i * D), __ldg(mu + i), s);
       }
       lmu[tid] = s;
+    }
+
+    // The row's standard normals (injected, or Philox + Box–Muller in double: a few hundred instructions each) are
+    // produced here by DP threads in parallel, under the shadow of the first gather, and parked in xs[] until the
+    // substitution needs them — not serially by warp 0 at the end of the row.
+    if (tid < DP) {
+      double z = 0.0;
+      if (tid < D) {
+        const int64_t grow0 = (int64_t)lrow * p.world + p.rank;
+        z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, p.entity, grow0, tid);
+      }
+      xs[tid] = z;
     }
 
     // ---- gather ring -----------------------------------------------------------------------------------------
@@ -547,15 +560,26 @@ struct RowKernel {
       const double* Pp = Tl + 64 * tri(pb) + fo;
       const double na0 = -Pp[64 * I], na1 = -Pp[64 * I + 32];
       double* trow = Tl + 64 * tri(I) + 2 * lane;
-      constexpr int kUnrollUR = BDF_UR_UNROLL;
-#pragma unroll kUnrollUR
-      for (int J = j0; J <= j1; J++) {
-        const double b0 = Pp[64 * J], b1 = Pp[64 * J + 32];
-        const double2 cv = *reinterpret_cast<const double2*>(trow + 64 * J);
-        double c2[2] = {cv.x, cv.y};
-        dmma884(c2, na0, b0);
-        dmma884(c2, na1, b1);
-        *reinterpret_cast<double2*>(trow + 64 * J) = make_double2(c2[0], c2[1]);
+      // four tiles at a time: all their operands are loaded before the first DMMA, so the shared-memory latency and the
+      // two dependent DMMAs of a tile overlap across the batch (the compiler cannot hoist loads over the tile stores)
+      for (int J = j0; J <= j1; J += 4) {
+        double b0[4], b1[4], c2[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int Ju = J + u <= j1 ? J + u : j1;
+          b0[u] = Pp[64 * Ju];
+          b1[u] = Pp[64 * Ju + 32];
+          const double2 cv = *reinterpret_cast<const double2*>(trow + 64 * Ju);
+          c2[u][0] = cv.x;
+          c2[u][1] = cv.y;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) dmma884(c2[u], na0, b0[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) dmma884(c2[u], na1, b1[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (J + u <= j1) *reinterpret_cast<double2*>(trow + 64 * (J + u)) = make_double2(c2[u][0], c2[u][1]);
       }
     };
     // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
@@ -585,9 +609,11 @@ struct RowKernel {
       }
     };
 
+    long long d_b = 0, d_c = 0, d_w1 = 0, d_w2 = 0, t_x = 0;
     if (warp == 0) factor_diag(NB - 1);
     __syncthreads();
     for (int pb = NB - 1; pb > 0; pb--) {
+      if (p.dbg) t_x = clock64();
       // (b) scale the panel tiles (pb, J < pb) in place
       {
         const double wa0 = WvT[pb * 64 + fo], wa1 = WvT[pb * 64 + 32 + fo];
@@ -600,7 +626,9 @@ struct RowKernel {
           *reinterpret_cast<double2*>(tp + 2 * lane) = make_double2(c2[0], c2[1]);
         }
       }
+      if (p.dbg) { const long long t = clock64(); d_b += t - t_x; t_x = t; }
       __syncthreads();
+      if (p.dbg) { const long long t = clock64(); d_w1 += t - t_x; t_x = t; }
       // (c) trailing update of block rows I < pb; rows are dealt to warps 1…NW-1 in a snake so the triangle balances
       if (NW == 1) {
         backsub_step(pb, true);
@@ -621,7 +649,13 @@ struct RowKernel {
           if (wo == warp) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
         }
       }
+      if (p.dbg) { const long long t = clock64(); d_c += t - t_x; t_x = t; }
       __syncthreads();
+      if (p.dbg) { const long long t = clock64(); d_w2 += t - t_x; t_x = t; }
+    }
+    if (p.dbg && lane == 0 && warp < 2) {
+      long long* o = p.dbg + (size_t)gridDim.x * 8 + ((size_t)item * 2 + warp) * 4;
+      o[0] = d_b; o[1] = d_w1; o[2] = d_c; o[3] = d_w2;
     }
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
     BDF_STAMP(5);
@@ -631,11 +665,7 @@ struct RowKernel {
       const int r8 = lane & 7;
       const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
       backsub_step(0, false);
-      for (int c = lane; c < DP; c += 32) {
-        double z = 0.0;
-        if (c < D) z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + c) : philox_normal(p.seed, p.sweep, p.entity, grow, c);
-        ys[c] += z;
-      }
+      for (int c = lane; c < DP; c += 32) ys[c] += xs[c];  // v = y + z (z parked in xs at kernel start)
       __syncwarp();
       // forward substitution R·x = v (R = Wᵀ, lower, block rows in the tiles): column-oriented — lane owns rows
       // lane, lane+32, … of v in registers; once x_J is known every lane subtracts R[i][8J..8J+7]·x_J from its rows.
