@@ -280,6 +280,14 @@ int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, in
   return BDF_OK;
 }
 int bdf_check_err_flag(bdf_t* h) { return check_err_flag(h); }
+int bdf_ensure_arena(bdf_t* h, size_t bytes) {
+  if (bytes <= h->arena_bytes) return BDF_OK;
+  if (h->arena) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->arena)); h->arena = nullptr; h->arena_bytes = 0; }
+  bytes = bytes + bytes / 4;
+  CU(cudaMalloc((void**)&h->arena, bytes));
+  h->arena_bytes = bytes;
+  return BDF_OK;
+}
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
 
 namespace {
@@ -372,7 +380,7 @@ int bdf_destroy(bdf_t* h) {
       cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk);
       cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
     }
-  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->work_counter);
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->work_counter); cudaFree(h->arena);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return BDF_OK;
@@ -738,13 +746,17 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
   if (ntest == 0) return BDF_OK;
   CU(cudaSetDevice(h->device));
   RelationS& r = h->rels[rel];
-  int64_t* d_ids = nullptr; int32_t* d_s = nullptr; double* d_out = nullptr; int* d_bad = nullptr;
-  CU(cudaMalloc((void**)&d_ids, sizeof(int64_t) * ntest * r.K));
-  CU(cudaMalloc((void**)&d_s, sizeof(int32_t) * ntest * r.K));
-  CU(cudaMalloc((void**)&d_out, sizeof(double) * ntest));
-  CU(cudaMalloc((void**)&d_bad, sizeof(int)));
+  // staging lives in a grow-only arena of the handle: no cudaMalloc/cudaFree (both synchronise the device) per call
+  const size_t b_ids = sizeof(int64_t) * ntest * r.K, b_s = sizeof(int32_t) * ntest * r.K, b_out = sizeof(double) * ntest;
+  const size_t off_s = (b_ids + 255) / 256 * 256, off_out = off_s + (b_s + 255) / 256 * 256, off_bad = off_out + (b_out + 255) / 256 * 256;
+  int rc_arena = bdf_ensure_arena(h, off_bad + 256);
+  if (rc_arena) return rc_arena;
+  int64_t* d_ids = reinterpret_cast<int64_t*>(h->arena);
+  int32_t* d_s = reinterpret_cast<int32_t*>(h->arena + off_s);
+  double* d_out = reinterpret_cast<double*>(h->arena + off_out);
+  int* d_bad = reinterpret_cast<int*>(h->arena + off_bad);
   CU(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
-  CU(cudaMemcpyAsync(d_ids, ids, sizeof(int64_t) * ntest * r.K, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_ids, ids, b_ids, cudaMemcpyHostToDevice, h->stream));
   const double* Us[3] = {nullptr, nullptr, nullptr};
   for (int m = 0; m < r.K; m++) {
     EntityS& e = h->ents[r.entity_of_mode[m]];
@@ -757,7 +769,6 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
   cudaError_t ce = cudaMemcpyAsync(yhat, d_out, sizeof(double) * ntest, cudaMemcpyDeviceToHost, h->stream);
   cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaError_t ce2 = cudaStreamSynchronize(h->stream);
-  cudaFree(d_ids); cudaFree(d_s); cudaFree(d_out); cudaFree(d_bad);
   if (ce != cudaSuccess || ce2 != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
   if (bad) FAIL(BDF_ERR_INVALID, "test id outside 1..count of its entity");
   return BDF_OK;

@@ -88,6 +88,9 @@ struct EntityS {
 #define CHECK_ENT(e) \
   if ((e) < 0 || (e) >= (int)h->ents.size()) FAIL(BDF_ERR_INVALID, "entity id out of range")
 
+struct bdf_handle;
+int bdf_ensure_arena(bdf_handle* h, size_t bytes);
+
 struct bdf_handle {
   int device = 0, D = 0, ld = 0, DP = 0, NW = 1, rank = 0, world = 1;
   cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -103,6 +106,8 @@ struct bdf_handle {
   int* work_counter = nullptr;  // work queue head of the persistent row kernel
   int num_sms = 148;
   double* lt = nullptr;  // Λ in tile order + Λ·μ, rebuilt per half-sweep
+  char* arena = nullptr;  // grow-only staging for host-facing calls (predict ids/slots/output, beta sampler temporaries)
+  size_t arena_bytes = 0;
   int64_t pst = 0;  // doubles per parked partial for this D
   std::string err;
 };

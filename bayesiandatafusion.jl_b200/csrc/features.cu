@@ -723,14 +723,18 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   if (tol != tol) tol = 2.220446049250313e-16 * (double)e.numF;
   CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
-  double *Cm = nullptr, *T = nullptr, *rhs = nullptr, *E1d = nullptr, *E2d = nullptr;
-  auto cleanup = [&]() { cudaFree(Cm); cudaFree(T); cudaFree(rhs); cudaFree(E1d); cudaFree(E2d); };
-  if ((rc = dalloc(h, &Cm, dd)) || (rc = dalloc(h, &T, (size_t)e.N * ld)) || (rc = dalloc(h, &rhs, (size_t)e.numF * ld))) { cleanup(); return rc; }
+  // temporaries from the handle's grow-only arena (no per-call cudaMalloc/cudaFree)
+  const size_t nT = (size_t)e.N * ld, nR = (size_t)e.numF * ld;
+  if ((rc = bdf_ensure_arena(h, sizeof(double) * (dd + 2 * nT + 2 * nR + 64)))) return rc;
+  double* Cm = reinterpret_cast<double*>(h->arena);
+  double* T = Cm + ((dd + 31) / 32) * 32;
+  double* rhs = T + nT;
+  double* E1d = E1 ? rhs + nR : nullptr;
+  double* E2d = E2 ? rhs + nR + nT : nullptr;
+  auto cleanup = [&]() {};
   color_matrix_kernel<<<1, 256, 0, h->stream>>>(e.Lambda, D, h->scratch, Cm, h->err_flag);
-  if (E1) { if ((rc = dalloc(h, &E1d, (size_t)e.N * ld))) { cleanup(); return rc; }
-            cudaMemcpy2DAsync(E1d, sizeof(double) * ld, E1, sizeof(double) * D, sizeof(double) * D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream); }
-  if (E2) { if ((rc = dalloc(h, &E2d, (size_t)e.numF * ld))) { cleanup(); return rc; }
-            cudaMemcpy2DAsync(E2d, sizeof(double) * ld, E2, sizeof(double) * D, sizeof(double) * D, (size_t)e.numF, cudaMemcpyHostToDevice, h->stream); }
+  if (E1) cudaMemcpy2DAsync(E1d, sizeof(double) * ld, E1, sizeof(double) * D, sizeof(double) * D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream);
+  if (E2) cudaMemcpy2DAsync(E2d, sizeof(double) * ld, E2, sizeof(double) * D, sizeof(double) * D, (size_t)e.numF, cudaMemcpyHostToDevice, h->stream);
   const size_t smem = sizeof(double) * (dd + 4 * (size_t)D);
   cudaFuncSetAttribute(colored_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const uint32_t s0 = 0x200u + 8u * (uint32_t)entity;
