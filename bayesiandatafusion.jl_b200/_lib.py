@@ -46,6 +46,7 @@ SIGNATURES = {
     "bdf_launch_count": (C.c_int64, [H]),
     "bdf_predict": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp]),
     "bdf_set_features_sbm": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, c_i32p, c_i32p]),
+    "bdf_set_features_csc": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, c_i64p, c_i64p, c_dp]),
     "bdf_debug_features_csr": (C.c_int, [H, C.c_int, C.c_int, c_i32p, c_i32p]),
     "bdf_spmm": (C.c_int, [H, C.c_int, C.c_int, c_dp, C.c_int, c_dp]),
     "bdf_ata_mul": (C.c_int, [H, C.c_int, c_dp, C.c_double, c_dp]),

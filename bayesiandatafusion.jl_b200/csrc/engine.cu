@@ -372,6 +372,7 @@ int bdf_destroy(bdf_t* h) {
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
     cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
     cudaFree(e.sp_items[0]); cudaFree(e.sp_items[1]); cudaFree(e.sp_long[0]); cudaFree(e.sp_long[1]); cudaFree(e.sp_part);
+    cudaFree(e.f_val_csr); cudaFree(e.f_val_csc);
   }
   for (auto& r : h->rels)
     for (int m = 0; m < r.K; m++) {

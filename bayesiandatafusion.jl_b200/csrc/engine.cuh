@@ -57,6 +57,8 @@ struct EntityS {
   int32_t* f_colind = nullptr;  // [fnnz]  0-based feature ids, stored order = stable sort of the COO list by row
   int64_t* f_colptr = nullptr;  // [numF+1] rows of Fᵀ
   int32_t* f_rowind = nullptr;  // [fnnz]  0-based row ids, stored order = stable sort of the COO list by column
+  double* f_val_csr = nullptr;  // [fnnz] stored values in CSR order (general sparse F) or nullptr (0/1 matrix)
+  double* f_val_csc = nullptr;  // [fnnz] the same in CSC order
   double* beta = nullptr;       // numF × ld
   double* uhat = nullptr;       // slots × ld, (F·beta)
   double* cgbuf = nullptr;      // CG work vectors

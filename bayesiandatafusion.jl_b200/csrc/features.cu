@@ -46,10 +46,12 @@ struct SpItem {
   int64_t beg, end;
 };
 
-template <int NC>
+// VAL: general sparse F with stored values (SparseMatrixCSC features, e.g. test/parallel_latent_basic.jl:4): y += a·x with a
+// separate multiply and add, like Julia's un-contracted `tmp += nzval[j]*x[...]`, in stored order.
+template <int NC, bool VAL>
 __global__ void __launch_bounds__(256) spbin_gather_kernel(const SpItem* __restrict__ items, int n_items, const int32_t* __restrict__ idx,
-                                                           const double* __restrict__ X, double* __restrict__ Y, double* __restrict__ part, int ld,
-                                                           double lam, const double* __restrict__ P) {
+                                                           const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                                                           double* __restrict__ part, int ld, double lam, const double* __restrict__ P) {
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -61,19 +63,24 @@ __global__ void __launch_bounds__(256) spbin_gather_kernel(const SpItem* __restr
     for (int64_t o = w.beg; o < w.end; o += 32) {
       const int n = (int)min((int64_t)32, w.end - o);
       const int mine = lane < n ? __ldg(idx + o + lane) : 0;
+      const double myval = (VAL && lane < n) ? __ldg(vals + o + lane) : 0.0;
       for (int j0 = 0; j0 < n; j0 += 8) {
         double v[8][NC];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int c = __shfl_sync(0xffffffffu, mine, (j0 + u) & 31);
+          const double a = VAL ? __shfl_sync(0xffffffffu, myval, (j0 + u) & 31) : 1.0;
           const double* src = X + (size_t)c * ld + lane;
 #pragma unroll
-          for (int k = 0; k < NC; k++) v[u][k] = (j0 + u < n && lane + 32 * k < ld) ? __ldg(src + 32 * k) : 0.0;
+          for (int k = 0; k < NC; k++) {
+            const double x = (j0 + u < n && lane + 32 * k < ld) ? __ldg(src + 32 * k) : 0.0;
+            v[u][k] = VAL ? __dmul_rn(a, x) : x;
+          }
         }
 #pragma unroll
         for (int u = 0; u < 8; u++)
 #pragma unroll
-          for (int k = 0; k < NC; k++) acc[k] += v[u][k];  // +0.0 for the padded slots leaves the sum bit-identical
+          for (int k = 0; k < NC; k++) acc[k] = __dadd_rn(acc[k], v[u][k]);  // +0.0 for the padded slots leaves the sum bit-identical
       }
     }
     if (w.slot < 0) {
@@ -325,6 +332,18 @@ __global__ void gather_other_kernel(const uint32_t* perm, int64_t n, const int32
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) out[o] = other[perm[o]] - 1;
 }
 
+__global__ void gather_fval_kernel(const uint32_t* perm, int64_t n, const double* v, double* out) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) out[o] = v[perm[o]];
+}
+__global__ void csc_expand_kernel(const int64_t* colptr, const int64_t* rowval, int64_t ncols, int64_t nnz, int32_t* rows, int32_t* cols, int* bad) {
+  // one thread per column: COO (row, col) pairs in CSC order (1-based in, 1-based out)
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = colptr[c] - 1, e = colptr[c + 1] - 1;
+    if (b < 0 || e < b || e > nnz) { *bad = 1; continue; }
+    for (int64_t o = b; o < e; o++) { rows[o] = (int32_t)rowval[o]; cols[o] = (int32_t)(c + 1); }
+  }
+}
+
 template <class T>
 int dalloc(bdf_t* h, T** p, size_t n) {
   *p = nullptr;
@@ -335,7 +354,7 @@ int dalloc(bdf_t* h, T** p, size_t n) {
 // one orientation of F: stable sort of the COO list by `key` (rows for CSR, cols for CSC) — the reference's
 // sortperm(rows) in SparseBinMatrixCSR (src/sparsebin_csr.jl:23) — then the pointer array by counting.
 int build_orientation(bdf_t* h, const int32_t* d_key, const int32_t* d_other, int64_t nnz, int64_t nkeys, int32_t other_max, int64_t** ptr_out,
-                      int32_t** ind_out) {
+                      int32_t** ind_out, const double* d_val = nullptr, double** val_out = nullptr) {
   uint32_t *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *idx2 = nullptr;
   int* d_bad = nullptr; unsigned long long* cnt = nullptr; void* tmp = nullptr;
   auto cleanup = [&]() { cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(idx2); cudaFree(d_bad); cudaFree(cnt); cudaFree(tmp); };
@@ -363,6 +382,10 @@ int build_orientation(bdf_t* h, const int32_t* d_key, const int32_t* d_other, in
   if ((rc = dalloc(h, ind_out, n1))) { cleanup(); return rc; }
   TRYC(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, *ptr_out, (int)(nkeys + 1), h->stream));
   gather_other_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(idx2, nnz, d_other, *ind_out);
+  if (d_val && val_out) {
+    if ((rc = dalloc(h, val_out, n1))) { cleanup(); return rc; }
+    gather_fval_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(idx2, nnz, d_val, *val_out);
+  }
   int bad = 0;
   TRYC(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream));
   TRYC(cudaStreamSynchronize(h->stream));
@@ -386,12 +409,17 @@ int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y,
   const int32_t* idx = transpose ? e.f_rowind : e.f_colind;
   const int nc = (h->ld + 31) / 32;
   double* part = reinterpret_cast<double*>(e.sp_part);
+  const double* vals = transpose ? e.f_val_csc : e.f_val_csr;
+#define SPL(NC_)                                                                                                                   \
+  if (vals) spbin_gather_kernel<NC_, true><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, vals, X, Y, part, h->ld, lam, P);         \
+  else spbin_gather_kernel<NC_, false><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, nullptr, X, Y, part, h->ld, lam, P);
   switch (nc) {
-    case 1: spbin_gather_kernel<1><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
-    case 2: spbin_gather_kernel<2><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
-    case 3: spbin_gather_kernel<3><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
-    default: spbin_gather_kernel<4><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, X, Y, part, h->ld, lam, P); break;
+    case 1: SPL(1) break;
+    case 2: SPL(2) break;
+    case 3: SPL(3) break;
+    default: SPL(4) break;
   }
+#undef SPL
   h->launches++;
   if (e.sp_nlong[o] > 0) {
     spbin_reduce_kernel<<<std::min(e.sp_nlong[o], 148 * 4), 128, 0, h->stream>>>(reinterpret_cast<const SpLong*>(e.sp_long[o]), e.sp_nlong[o], part, Y, h->ld, lam, P);
@@ -510,29 +538,14 @@ int download_colmajor(bdf_t* h, const double* dev_rm, int64_t rows, int ncol, do
 }  // namespace
 
 // =====================================================================================================================
-extern "C" {
-
-int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols) {
-  CHECK_H(); CHECK_ENT(entity);
-  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this round (world must be 1)");
+static int set_features_dev(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, int32_t* d_rows, int32_t* d_cols, const double* d_val) {
   EntityS& e = h->ents[entity];
-  if (m != e.N) FAIL(BDF_ERR_INVALID, "DimensionMismatch: number of feature rows must equal the entity count");  // src/RelationData.jl:263-268
-  if (n < 1 || n > 2000000000LL || nnz < 0 || nnz >= 2147483647LL) FAIL(BDF_ERR_INVALID, "bad feature matrix size");
-  if (nnz > 0 && (!rows || !cols)) FAIL(BDF_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
   cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
-  e.f_rowptr = e.f_colptr = nullptr; e.f_colind = e.f_rowind = nullptr; e.beta = e.uhat = e.cgbuf = e.btb = nullptr;
+  cudaFree(e.f_val_csr); cudaFree(e.f_val_csc);
+  e.f_rowptr = e.f_colptr = nullptr; e.f_colind = e.f_rowind = nullptr; e.beta = e.uhat = e.cgbuf = e.btb = nullptr; e.f_val_csr = e.f_val_csc = nullptr;
   e.numF = 0;
-  int32_t *d_rows = nullptr, *d_cols = nullptr;
-  int rc;
-  if ((rc = dalloc(h, &d_rows, (size_t)nnz)) || (rc = dalloc(h, &d_cols, (size_t)nnz))) { cudaFree(d_rows); return rc; }
-  if (nnz) {
-    CU(cudaMemcpyAsync(d_rows, rows, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(d_cols, cols, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
-  }
-  rc = build_orientation(h, d_rows, d_cols, nnz, m, (int32_t)n, &e.f_rowptr, &e.f_colind);
-  if (!rc) rc = build_orientation(h, d_cols, d_rows, nnz, n, (int32_t)m, &e.f_colptr, &e.f_rowind);
-  cudaFree(d_rows); cudaFree(d_cols);
+  int rc = build_orientation(h, d_rows, d_cols, nnz, m, (int32_t)n, &e.f_rowptr, &e.f_colind, d_val, &e.f_val_csr);
+  if (!rc) rc = build_orientation(h, d_cols, d_rows, nnz, n, (int32_t)m, &e.f_colptr, &e.f_rowind, d_val, &e.f_val_csc);
   if (rc) return rc;
   {
     int64_t slots = 0;
@@ -552,6 +565,62 @@ int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz
   CU(cudaStreamSynchronize(h->stream));
   return BDF_OK;
 }
+
+extern "C" int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this round (world must be 1)");
+  EntityS& e = h->ents[entity];
+  if (m != e.N) FAIL(BDF_ERR_INVALID, "DimensionMismatch: number of feature rows must equal the entity count");  // src/RelationData.jl:263-268
+  if (n < 1 || n > 2000000000LL || nnz < 0 || nnz >= 2147483647LL) FAIL(BDF_ERR_INVALID, "bad feature matrix size");
+  if (nnz > 0 && (!rows || !cols)) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  int32_t *d_rows = nullptr, *d_cols = nullptr;
+  int rc;
+  if ((rc = dalloc(h, &d_rows, (size_t)nnz)) || (rc = dalloc(h, &d_cols, (size_t)nnz))) { cudaFree(d_rows); return rc; }
+  if (nnz) {
+    CU(cudaMemcpyAsync(d_rows, rows, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_cols, cols, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = set_features_dev(h, entity, m, n, nnz, d_rows, d_cols, nullptr);
+  cudaFree(d_rows); cudaFree(d_cols);
+  return rc;
+}
+
+/* Entity(F = ::SparseMatrixCSC{Float64,Int64}) — the general sparse feature matrix of the reference's own tests
+ * (test/parallel_latent_basic.jl:4, test/parallel_mult.jl:4): Julia's CSC fields colptr (n+1), rowval (nnz), nzval (nnz),
+ * 1-based. Products accumulate in Julia's order (F*x: ascending column per row; F'x: stored order per column). */
+extern "C" int bdf_set_features_csc(bdf_t* h, int entity, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this round (world must be 1)");
+  EntityS& e = h->ents[entity];
+  if (m != e.N) FAIL(BDF_ERR_INVALID, "DimensionMismatch: number of feature rows must equal the entity count");
+  if (n < 1 || n > 2000000000LL || !colptr) FAIL(BDF_ERR_INVALID, "bad feature matrix size");
+  const int64_t nnz = colptr[n] - 1;
+  if (nnz < 0 || nnz >= 2147483647LL || (nnz > 0 && (!rowval || !nzval))) FAIL(BDF_ERR_INVALID, "bad colptr / null argument");
+  CU(cudaSetDevice(h->device));
+  int64_t *d_cp = nullptr, *d_rv = nullptr; double* d_nz = nullptr; int32_t *d_rows = nullptr, *d_cols = nullptr; int* d_bad = nullptr;
+  auto cleanup = [&]() { cudaFree(d_cp); cudaFree(d_rv); cudaFree(d_nz); cudaFree(d_rows); cudaFree(d_cols); cudaFree(d_bad); };
+  int rc;
+  if ((rc = dalloc(h, &d_cp, (size_t)n + 1)) || (rc = dalloc(h, &d_rv, (size_t)nnz)) || (rc = dalloc(h, &d_nz, (size_t)nnz)) ||
+      (rc = dalloc(h, &d_rows, (size_t)nnz)) || (rc = dalloc(h, &d_cols, (size_t)nnz)) || (rc = dalloc(h, &d_bad, 1))) { cleanup(); return rc; }
+  cudaMemsetAsync(d_bad, 0, 4, h->stream);
+  cudaMemcpyAsync(d_cp, colptr, 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, h->stream);
+  if (nnz) {
+    cudaMemcpyAsync(d_rv, rowval, 8 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_nz, nzval, 8 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream);
+  }
+  csc_expand_kernel<<<grid_for(n), 256, 0, h->stream>>>(d_cp, d_rv, n, nnz, d_rows, d_cols, d_bad);
+  int bad = 0;
+  cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t ce = cudaStreamSynchronize(h->stream);
+  if (ce != cudaSuccess) { cleanup(); FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce)); }
+  if (bad) { cleanup(); FAIL(BDF_ERR_INVALID, "colptr is not a valid CSC column pointer array"); }
+  rc = set_features_dev(h, entity, m, n, nnz, d_rows, d_cols, d_nz);
+  cleanup();
+  return rc;
+}
+
+extern "C" {
 
 /* debug/parity hook: the CSR the device built, in the reference's own representation (1-based Int32 row_ptr of length m+1
  * and col_ind, src/sparsebin_csr.jl:6-11) */

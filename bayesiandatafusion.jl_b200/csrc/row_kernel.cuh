@@ -153,6 +153,12 @@ __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
 #ifndef BDF_BUILD_PREFETCH
 #define BDF_BUILD_PREFETCH 0
 #endif
+#ifndef BDF_NBUF1
+#define BDF_NBUF1 3
+#endif
+#ifndef BDF_MINB1
+#define BDF_MINB1 16
+#endif
 #ifndef BDF_UR_UNROLL
 #define BDF_UR_UNROLL 4
 #endif
@@ -173,7 +179,7 @@ struct RowKernel {
   // gather ring of the row kernel
   static constexpr int GP = NW == 8 ? 1 : (NW == 4 ? 2 : 8);  // passes per stage
   static constexpr int KS = OPP * GP;                          // observations per stage (16)
-  static constexpr int NBUF = 3;
+  static constexpr int NBUF = NW == 1 ? BDF_NBUF1 : 3;
   static constexpr int STG = KS * S * (TENSOR ? 2 : 1) + KS;   // doubles per stage: tile(s) + residuals
   static constexpr int PSZ = 64 * C::NT;  // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
   static constexpr int REGSZ = PSZ > NBUF * STG ? PSZ : NBUF * STG;  // the tiles alias the (dead) stage ring
@@ -447,6 +453,7 @@ struct RowKernel {
     // ---- Λ* = Λ + αG, rhs = Λμ + α·Σv·r (augmented row), identity on the padding — same code for every warp -------
     // The pre-tiled Λ (L2 hits) is fetched for all of this warp's tiles before the barrier so the loads overlap it.
 #if BDF_BUILD_PREFETCH
+    // (variant kept for experiments)
     {
       constexpr int BT = (C::NT + NW - 1) / NW;
       double2 lt[BT];
@@ -726,7 +733,7 @@ struct RowKernel {
 #define BDF_MINB 3
 #endif
 template <class K>
-__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? 16 : (K::NW == 4 ? (K::TENSOR ? 4 : 6) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
+__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? BDF_MINB1 : (K::NW == 4 ? (K::TENSOR ? 4 : 6) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
   extern __shared__ __align__(16) double smem_dyn[];
   K::run(p, smem_dyn);
 }

@@ -179,9 +179,19 @@ class Engine:
         if hasattr(F, "rows") and hasattr(F, "cols"):
             rows, cols, (m, n) = F.rows, F.cols, F.shape
         else:
-            coo = F.tocsc().tocoo()
-            if not np.all(coo.data == 1):
-                raise ValueError("only sparse binary (0/1) feature matrices are on the device path")
+            csc = F.tocsc()
+            csc.sort_indices()
+            if not np.all(csc.data == 1):
+                # general sparse matrix (Julia SparseMatrixCSC fields, 1-based)
+                colptr = np.ascontiguousarray(csc.indptr, dtype=np.int64) + 1
+                rowval = np.ascontiguousarray(csc.indices, dtype=np.int64) + 1
+                nzval = np.ascontiguousarray(csc.data, dtype=np.float64)
+                m, n = F.shape
+                self._ck(self.lib.bdf_set_features_csc(self.h, entity, m, n, colptr.ctypes.data_as(_lib.c_i64p), rowval.ctypes.data_as(_lib.c_i64p), _dp(nzval)))
+                self.numF = getattr(self, "numF", {})
+                self.numF[entity] = int(n)
+                return
+            coo = csc.tocoo()
             rows, cols, (m, n) = coo.row + 1, coo.col + 1, F.shape
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         cols = np.ascontiguousarray(cols, dtype=np.int32)

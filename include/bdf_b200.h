@@ -119,6 +119,10 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
  * constructor, src/sparsebin_csr.jl:22-37: stable sort by row) and of Fᵀ on the device, allocates beta = zeros(n, D)
  * (src/RelationData.jl:76). m must equal the entity count (src/RelationData.jl:263-268). */
 int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols);
+/* Entity(F = ::SparseMatrixCSC{Float64,Int64}) — a general sparse feature matrix given by Julia's CSC fields (colptr n+1, rowval nnz,
+ * nzval nnz; 1-based), as in the reference's own tests (test/parallel_latent_basic.jl:4, test/parallel_mult.jl:4-18). Products
+ * accumulate in Julia's order with un-fused multiply-add. */
+int bdf_set_features_csc(bdf_t* h, int entity, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval);
 /* Parity hook: the device CSR in the reference's representation — row_ptr (m+1, or n+1 for the transpose) and col_ind
  * (nnz), Int32, 1-based (fields of SparseBinMatrixCSR, src/sparsebin_csr.jl:6-11). */
 int bdf_debug_features_csr(bdf_t* h, int entity, int transpose, int32_t* ptr_out, int32_t* ind_out);

@@ -83,6 +83,11 @@ set_features_sbm(h::Handle, entity, m, n, rows::Vector{Int32}, cols::Vector{Int3
   check(h, ccall((:bdf_set_features_sbm, LIB), Cint, (Ptr{Void}, Cint, Int64, Int64, Int64, Ptr{Int32}, Ptr{Int32}),
                  h.ptr, entity, m, n, length(rows), rows, cols))
 
+## Entity(F = ::SparseMatrixCSC{Float64,Int64}) — general sparse features by their CSC fields
+set_features_csc(h::Handle, entity, F::SparseMatrixCSC{Float64,Int64}) =
+  check(h, ccall((:bdf_set_features_csc, LIB), Cint, (Ptr{Void}, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}),
+                 h.ptr, entity, size(F, 1), size(F, 2), F.colptr, F.rowval, F.nzval))
+
 ## the feature-operator duck type (src/RelationData.jl:314-329): a type CudaSBM can forward *, At_mul_B, AtA_mul_B! here
 function spmm(h::Handle, entity, X::Matrix{Float64}, nout::Int; transpose::Bool = false)
   Y = zeros(nout, size(X, 2))

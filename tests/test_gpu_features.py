@@ -202,3 +202,45 @@ def test_long_rows_are_chunked_deterministically():
         short[6] = False
         assert np.array_equal(Y1[short, d], want[short])   # rows within one chunk stay bit-exact
     eng.close()
+
+
+@pytest.mark.parametrize("D", [5, 32])
+def test_general_sparse_features_match_julia_summation_order(D):
+    """Entity(F = sprand(...)) — the SparseMatrixCSC features of test/parallel_latent_basic.jl:4 and test/parallel_mult.jl:4-18.
+    scipy's CSC/CSR matvecs accumulate in the same order as Julia's (ascending column per row for F*x, stored order per
+    column for F'x) with un-fused multiply-add, so the device products must match them bit for bit."""
+    import scipy.sparse as sp
+
+    import bdf_b200
+
+    rng = np.random.default_rng(300 + D)
+    N, numF = 50, 20
+    X = sp.random(N, numF, 0.1, random_state=int(D), format="csc")   # sprand(50, 20, 0.1)
+    X.sort_indices()
+    eng = bdf_b200.Engine(D)
+    e1, e2 = eng.add_entity(N), eng.add_entity(10)
+    ids = np.stack([rng.integers(1, N + 1, 300), rng.integers(1, 11, 300)], axis=1)
+    vals = rng.standard_normal(300)
+    rel = eng.add_relation([e1, e2], ids, vals)
+    eng.set_features(e1, X)
+    B = rng.standard_normal((numF, D))
+    T = rng.standard_normal((N, D))
+    Y = eng.spmm(e1, B)
+    Yt = eng.spmm(e1, T, transpose=True)
+    Xcsr_t = sp.csr_matrix(X.T)
+    for d in range(D):
+        assert np.array_equal(Y[:, d], X @ B[:, d])            # Z2 = X * Y2, test/parallel_mult.jl:8
+        assert np.array_equal(Yt[:, d], Xcsr_t @ T[:, d])      # Z1 = X' * Y1, test/parallel_mult.jl:7
+    x = rng.standard_normal(numF)
+    Xd = X.toarray()
+    assert rel_err(eng.ata_mul(e1, x, 0.5), Xd.T @ (Xd @ x) + 0.5 * x) <= 1e-14
+    rhs = rng.standard_normal((numF, D))
+    got, iters = eng.cg_solve(e1, rhs, 0.75, tol=1e-12, maxiter=500)
+    assert rel_err(got, np.linalg.solve(Xd.T @ Xd + 0.75 * np.eye(numF), rhs)) <= 1e-9
+    # the reference's smoke test itself (test/parallel_latent_basic.jl:4-15): rank-2 data, sparse real features, D=5
+    A2, B2 = rng.standard_normal((N, 2)), rng.standard_normal((10, 2))
+    rd = bdf_b200.RelationData(sp.csc_matrix(A2 @ B2.T), class_cut=0.5, feat1=X)
+    bdf_b200.assignToTest(rd.relations[0], 50, rng)
+    res = bdf_b200.macau(rd, burnin=3, psamples=3, num_latent=5, verbose=False)
+    assert rd.entities[0].model.beta.shape == (numF, 5) and np.isfinite(res["RMSE"])
+    eng.close()

@@ -1,5 +1,5 @@
 #!/bin/bash
 # A/B of library variants: tools/ab.sh tag1 tag2 ...   (runs bench at quarter scale for each libbdf_<tag>.so)
 for t in "$@"; do
-  BDF_B200_LIB=$PWD/bayesiandatafusion.jl_b200/libbdf_$t.so python bench.py --steps 3 --warmup 2 --no-cpu --scale 0.25 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$t', round(d['ms_per_step'],2), 'ms/sweep  frac', round(d['roofline']['frac'],3), {k:round(v,2) for k,v in d['roofline']['ms_per_launch'].items()})"
+  BDF_B200_LIB=$PWD/bayesiandatafusion.jl_b200/libbdf_$t.so python bench.py --steps 3 --warmup 2 --no-cpu --scale 0.25 $BENCH_ARGS 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$t', round(d['ms_per_step'],2), 'ms/sweep  frac', round(d['roofline']['frac'],3), {k:round(v,2) for k,v in d['roofline']['ms_per_launch'].items()})"
 done
