@@ -28,6 +28,8 @@ SIGNATURES = {
     "bdf_set_factors": (C.c_int, [H, C.c_int, c_dp]),
     "bdf_get_factors": (C.c_int, [H, C.c_int, c_dp]),
     "bdf_factors_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), c_i64p, c_i64p]),
+    "bdf_ipc_export": (C.c_int, [H, C.c_int, C.c_char_p]),
+    "bdf_ipc_import": (C.c_int, [H, C.c_int, C.c_int, C.c_char_p]),
     "bdf_sample_mode": (C.c_int, [H, C.c_int, c_dp, C.c_int64, c_dp, c_dp]),
     "bdf_nw_stats": (C.c_int, [H, C.c_int, c_dp, c_dp, c_dp]),
     "bdf_stats_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), c_i64p]),

@@ -254,6 +254,7 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
   p.P0 = h->ents[mi.other_entity[0]].U;
   p.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr;
   p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper;
+  { int np = 0; for (int r = 0; r < 8; r++) if (e.peerU[r]) p.peer_out[np++] = e.peerU[r]; }
   p.Lambda = Lambda_dev; p.mu = mu_dev; p.mu_ld = mu_ld; p.Z = Z_dev;
   p.LT = h->lt; p.lmu = mu_ld ? nullptr : h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2;
   prep_lambda(h, Lambda_dev, mu_ld ? nullptr : mu_dev, h->D, h->DP, h->lt, h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2);
@@ -369,6 +370,7 @@ int bdf_destroy(bdf_t* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (auto& e : h->ents) {
+    for (int r = 0; r < 8; r++) if (e.peerU[r]) cudaIpcCloseMemHandle(e.peerU[r]);
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
     cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
     cudaFree(e.sp_items[0]); cudaFree(e.sp_items[1]); cudaFree(e.sp_long[0]); cudaFree(e.sp_long[1]); cudaFree(e.sp_part);
@@ -561,6 +563,29 @@ int bdf_factors_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* nper, int64_t
   if (dev_ptr) *dev_ptr = h->ents[entity].U;
   if (nper) *nper = h->ents[entity].Nper;
   if (ld) *ld = h->ld;
+  return BDF_OK;
+}
+
+int bdf_ipc_export(bdf_t* h, int entity, unsigned char* handle64) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!handle64) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  CU(cudaIpcGetMemHandle(&mh, h->ents[entity].U));
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &mh, 64);
+  return BDF_OK;
+}
+
+int bdf_ipc_import(bdf_t* h, int entity, int peer_rank, const unsigned char* handle64) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!handle64 || peer_rank < 0 || peer_rank >= h->world || peer_rank >= 8 || peer_rank == h->rank) FAIL(BDF_ERR_INVALID, "bad peer rank (fused all-gather supports up to 8 ranks)");
+  CU(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  void* ptr = nullptr;
+  CU(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->ents[entity].peerU[peer_rank] = (double*)ptr;
   return BDF_OK;
 }
 

@@ -42,6 +42,7 @@ struct EntityS {
   int64_t N = 0, Nper = 0;  // real rows; rows per rank (slots = world*Nper)
   int64_t nlocal = 0;       // real rows owned by this rank
   double* U = nullptr;      // world*Nper × ld, slot-major
+  double* peerU[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // IPC-mapped replicas on the other ranks
   double* mu = nullptr;     // D
   double* Lambda = nullptr; // D×D col-major
   double* mu_rows = nullptr;  // optional per-row mean, slot-major (ld pitch)

@@ -47,6 +47,7 @@ struct RowParams {
   const double* P1;
   int ld;        // row pitch (doubles) of every factor buffer
   double* Uout;  // factor buffer being sampled
+  double* peer_out[8];  // fused all-gather: the same buffer on every OTHER rank (IPC-mapped peer memory, NVLink stores), nullptr-terminated
   int64_t slot_base;  // slot of local row 0 (= rank * Nper)
   const double* Lambda;  // D×D column-major
   const double* LT;      // Λ in tile order (64 doubles per tile t = tri(I)+J, identity on the padding), see prep_lambda_kernel
@@ -722,6 +723,12 @@ struct RowKernel {
       __syncwarp();
       double* out = p.Uout + (size_t)slot * p.ld;
       for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[j] : 0.0;
+      // fused all-gather: the drawn row goes straight into every peer's replica over NVLink (no collective afterwards)
+#pragma unroll 1
+      for (int r = 0; r < 8 && p.peer_out[r]; r++) {
+        double* po = p.peer_out[r] + (size_t)slot * p.ld;
+        for (int j = lane; j < p.ld; j += 32) po[j] = j < D ? xs[j] : 0.0;
+      }
       __syncwarp();
       BDF_STAMP(6);
     }

@@ -413,6 +413,11 @@ struct RowKernelWS {
         }
         double* out = p.Uout + (size_t)slot * p.ld;
         for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[j] : 0.0;
+#pragma unroll 1
+        for (int r = 0; r < 8 && p.peer_out[r]; r++) {
+          double* po = p.peer_out[r] + (size_t)slot * p.ld;
+          for (int j = lane; j < p.ld; j += 32) po[j] = j < D ? xs[j] : 0.0;
+        }
       }
       named_bar(bid, NFI);  // the buffer (tiles, meta) is free again
       if (ft == 0) mbar_arrive(empty + g);

@@ -111,6 +111,14 @@ class Engine:
         self._ck(self.lib.bdf_factors_dev(self.h, entity, C.byref(p), C.byref(nper), C.byref(ld)))
         return p.value, nper.value, ld.value
 
+    def ipc_export(self, entity: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.bdf_ipc_export(self.h, entity, buf))
+        return buf.raw
+
+    def ipc_import(self, entity: int, peer_rank: int, handle: bytes):
+        self._ck(self.lib.bdf_ipc_import(self.h, entity, peer_rank, handle))
+
     def stats_dev(self, entity: int):
         p = C.c_void_p()
         n = C.c_int64()

@@ -69,7 +69,7 @@ class DistributedSweep:
     """Drives device-resident Gibbs sweeps over `world` GPUs: the loop body of src/macau.jl:96-134 with the collectives
     between the kernels. With world == 1 it degenerates to the same kernel sequence without communication."""
 
-    def __init__(self, engine, entities, group=None):
+    def __init__(self, engine, entities, group=None, fused_allgather=True):
         import torch
         import torch.distributed as dist
 
@@ -84,12 +84,24 @@ class DistributedSweep:
             ptr, nper, ld = engine.factors_dev(e)
             sptr, scount = engine.stats_dev(e)
             self.views[e] = (device_view(ptr, (engine.world * nper * ld,), dev), nper * ld, device_view(sptr, (scount,), dev))
+        # fused all-gather: exchange CUDA IPC handles once; afterwards the row kernel writes every drawn row into all peer
+        # replicas over NVLink and the per-half-sweep all-gather disappears
+        self.fused = bool(fused_allgather) and engine.world > 1 and engine.world <= 8
+        if self.fused:
+            mine = {e: engine.ipc_export(e) for e in self.entities}
+            everyone = [None] * engine.world
+            dist.all_gather_object(everyone, mine, group=group)
+            for r, handles in enumerate(everyone):
+                if r != engine.rank:
+                    for e in self.entities:
+                        engine.ipc_import(e, r, handles[e])
+            dist.barrier(group=group)
 
     def half_sweep(self, e):
         eng = self.eng
         eng.step_sample(e)
         U, blk, stats = self.views[e]
-        if self.dist is not None:
+        if self.dist is not None and not self.fused:
             mine = U[eng.rank * blk:(eng.rank + 1) * blk]
             self.dist.all_gather_into_tensor(U, mine, group=self.group)
         eng.step_nw_stats(e)

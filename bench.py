@@ -301,9 +301,9 @@ def run_ours(args):
             "config": {"workload": f"BPMF synthetic Netflix-scale {n1}x{n2}, {nnz_tr} training ratings (+{ntest} held out), D={D}",
                        "alpha": ALPHA, "skew": 2.5, "seed": SEED, "noise": "device Philox",
                        "l2": "inputs (ratings 1.2 GB/mode + factors) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"rows cyclic over {world} GPU(s); all-gather factors + all-reduce NW stats per half-sweep" if world > 1 else "single GPU"},
+                       "parallelism": f"rows cyclic over {world} GPU(s); drawn rows stored into every peer replica by the row kernel (NVLink P2P, fused all-gather) + NCCL all-reduce of NW stats per half-sweep" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "fp64_frac_of_peak_whole_sweep": (2 * alg_flops(nnz_tr, 0, D) + alg_flops(0, n1 + n2, D)) / (ms / args.steps / 1e3) / 1e12 / peak,
+            "fp64_frac_of_peak_whole_sweep": (2 * alg_flops(nnz_tr, 0, D) + alg_flops(0, n1 + n2, D)) / (ms / args.steps / 1e3) / 1e12 / peak / world,
         }
         print(json.dumps(line))
     eng.close()

@@ -64,6 +64,13 @@ int bdf_get_factors(bdf_t* h, int entity, double* U);
  * (world*Nper rows × ld doubles, row-major; rank r owns rows [r*Nper, (r+1)*Nper)). */
 int bdf_factors_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* nper, int64_t* ld);
 
+/* Fused all-gather (replaces the per-half-sweep shipping of `sample_m` to every worker, src/sampling.jl:155-168): each rank exports
+ * the CUDA IPC handle (64 bytes) of an entity's factor buffer, the host exchanges the handles, every rank imports its peers'. From
+ * then on the row-draw kernel stores each drawn row straight into every peer replica over NVLink, and no all-gather is needed;
+ * the all-reduce of the Normal-Wishart statistics that follows orders the peer stores before the next half-sweep reads them. */
+int bdf_ipc_export(bdf_t* h, int entity, unsigned char* handle64);
+int bdf_ipc_import(bdf_t* h, int entity, int peer_rank, const unsigned char* handle64);
+
 /* sample_latent_all2!(rel, dataRefs, procs, mode, mu_u, Lambda_u) — src/sampling.jl:149-172 (and the general
  * sample_user2_all! path, :251-289, when the entity sits in several relations): one half-sweep over `entity`,
  * overwriting its factors on the device. mu: D vector (mu_ld == 0) or D×N matrix (mu_ld == D) as in

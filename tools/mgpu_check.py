@@ -23,14 +23,14 @@ ids = np.stack([np.minimum((n1 * rng.random(nnz) ** 2.5).astype(np.int64), n1 - 
 vals = rng.standard_normal(nnz)
 
 
-def run(r, w):
+def run(r, w, fused=True):
     eng = bdf_b200.Engine(D, device=local, rank=r, world=w)
     eng.set_stream(stream.cuda_stream)
     eng.set_seed(7)
     e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
     rel = eng.add_relation([e1, e2], ids, vals)
     eng.set_relation_params(rel, 1.5, float(vals.mean()))
-    ds = DistributedSweep(eng, [e1, e2]) if w > 1 else None
+    ds = DistributedSweep(eng, [e1, e2], fused_allgather=fused) if w > 1 else None
     if w > 1:
         ds.sweep(3)
     else:
@@ -41,7 +41,9 @@ def run(r, w):
     return out
 
 
-multi = run(rank, world)
+multi = run(rank, world, fused=True)
+dist.barrier()
+multi_nccl = run(rank, world, fused=False)
 dist.barrier()
 if rank == 0:
     single = run(0, 1)
@@ -49,6 +51,7 @@ if rank == 0:
     errs += [float(np.max(np.abs(multi[k][1] - single[k][1])) / np.max(np.abs(single[k][1]))) for k in (2, 3)]
     print(f"world={world} D={D}: rel err of factors/hyper vs 1-GPU run:", errs)
     assert max(errs) < 1e-9, errs
-    print("MGPU OK")
+    assert all(np.array_equal(a, b) for a, b in zip(multi[:2], multi_nccl[:2])), "fused all-gather differs from the NCCL all-gather"
+    print("MGPU OK (fused peer-store all-gather == NCCL all-gather == 1 GPU)")
 dist.barrier()
 dist.destroy_process_group()
