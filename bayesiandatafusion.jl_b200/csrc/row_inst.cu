@@ -17,7 +17,10 @@ using namespace bdf;
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)
 static constexpr int kDP = BDF_DP;
-static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : 8);
+#ifndef BDF_NW_BIG
+#define BDF_NW_BIG 4
+#endif
+static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : BDF_NW_BIG);
 
 template <bool TENSOR>
 static int launch_rows_ws(bdf_t* h, RowParams p, int n_items) {

@@ -129,10 +129,16 @@ __host__ __device__ constexpr bool use_aug(int D) { return (D & 1) == 0 && (D & 
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H seed (≈ 2^-20 relative), no conversions
+#if BDF_HALLEY
+  // one cubically convergent step (2^-20 → 2^-60): e = 1 − x·y², y ← y + y·e·(1/2 + 3e/8); dependent depth 4 instead of 6
+  const double e = fma(-x, y * y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+#else
   const double h = 0.5 * x;
   y = y * fma(-h * y, y, 1.5);
   y = y * fma(-h * y, y, 1.5);
   return y;
+#endif
 }
 
 __host__ __device__ constexpr int tri(int i) { return i * (i + 1) / 2; }
@@ -159,6 +165,21 @@ __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
 #endif
 #ifndef BDF_MINB1
 #define BDF_MINB1 16
+#endif
+#ifndef BDF_VWARP
+#define BDF_VWARP 1
+#endif
+#ifndef BDF_HALLEY
+#define BDF_HALLEY 1
+#endif
+#ifndef BDF_FOLD
+#define BDF_FOLD 1
+#endif
+#ifndef BDF_TRAIL_PIPE
+#define BDF_TRAIL_PIPE 0
+#endif
+#ifndef BDF_BS_SWITCH
+#define BDF_BS_SWITCH 1000
 #endif
 #ifndef BDF_UR_UNROLL
 #define BDF_UR_UNROLL 4
@@ -293,30 +314,6 @@ struct RowKernel {
     for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
     double bsum = 0.0;  // Σ v_tid · r  (used when !aug)
 
-    // Λ·μ: precomputed when μ is shared; per-row μ (side features, src/macau.jl:102-107) is multiplied here
-    if (tid < DP) {
-      double s = 0.0;
-      if (p.lmu) {
-        s = __ldg(p.lmu + tid);
-      } else if (tid < D) {
-        const double* mu = p.mu + slot * p.mu_ld;
-        for (int i = 0; i < D; i++) s = fma(__ldg(p.Lambda + tid + (size_t)i * D), __ldg(mu + i), s);
-      }
-      lmu[tid] = s;
-    }
-
-    // The row's standard normals (injected, or Philox + Box–Muller in double: a few hundred instructions each) are
-    // produced here by DP threads in parallel, under the shadow of the first gather, and parked in xs[] until the
-    // substitution needs them — not serially by warp 0 at the end of the row.
-    if (tid < DP) {
-      double z = 0.0;
-      if (tid < D) {
-        const int64_t grow0 = (int64_t)lrow * p.world + p.rank;
-        z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, p.entity, grow0, tid);
-      }
-      xs[tid] = z;
-    }
-
     // ---- gather ring -----------------------------------------------------------------------------------------
     const int nst = (len + KS - 1) / KS;
     const int npc = (D + 1) >> 1;  // 16-byte pieces that carry latent columns; columns ≥ 2·npc are zeroed once
@@ -341,9 +338,14 @@ struct RowKernel {
     const uint32_t rowbytes = (uint32_t)npc * 16u;
     int c0n = 0, c1n = 0;
     double rvn = 0.0;
+    // each warp issues its share of a stage (KS/NW rows): UBLKCP is a per-thread (uniform-datapath) instruction, so 16 copies
+    // from one warp serialise for ~1000 cycles per stage; spread over the warps they go out in parallel
+    constexpr int KQ = KS / NW;
+    const bool gl = lane < KQ;
+    const int gk = warp * KQ + lane;  // this lane's observation within a stage (valid when gl)
     auto load_meta = [&](int s) {
-      if (tid < KS) {
-        int64_t o = obeg + (int64_t)s * KS + tid;
+      if (gl) {
+        int64_t o = obeg + (int64_t)s * KS + gk;
         if (o >= oend) o = oend - 1;
         c0n = __ldg(p.col0 + o);
         if (TENSOR) c1n = __ldg(p.col1 + o);
@@ -351,44 +353,90 @@ struct RowKernel {
       }
     };
     auto issue = [&](int s) {
-      if (tid < KS) {
+      if (gl) {
         const int b = s % NBUF;
         double* st = ring + b * STG;
         int nvalid = len - s * KS;
         if (nvalid > KS) nvalid = KS;
-        const bool ok = tid < nvalid;
+        const bool ok = gk < nvalid;
         if (tid == 0) mbar_arrive_expect_tx(fullb + b, (uint32_t)nvalid * rowbytes * (TENSOR ? 2u : 1u));
         if (ok) {
-          bulk_copy_g2s(st + tid * S, p.P0 + (size_t)c0n * p.ld, rowbytes, fullb + b);
-          if (TENSOR) bulk_copy_g2s(st + (KS + tid) * S, p.P1 + (size_t)c1n * p.ld, rowbytes, fullb + b);
-        } else if (tid < ((nvalid + 3) & ~3)) {
+          bulk_copy_g2s(st + gk * S, p.P0 + (size_t)c0n * p.ld, rowbytes, fullb + b);
+          if (TENSOR) bulk_copy_g2s(st + (KS + gk) * S, p.P1 + (size_t)c1n * p.ld, rowbytes, fullb + b);
+        } else if (gk < ((nvalid + 3) & ~3)) {
           // rows of the last, partly filled k-step: zero them (only the final stage of an item ever takes this path)
           for (int c = 0; c < 2 * npc; c += 2) {
-            *reinterpret_cast<double2*>(st + tid * S + c) = make_double2(0.0, 0.0);
-            if (TENSOR) *reinterpret_cast<double2*>(st + (KS + tid) * S + c) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2*>(st + gk * S + c) = make_double2(0.0, 0.0);
+            if (TENSOR) *reinterpret_cast<double2*>(st + (KS + gk) * S + c) = make_double2(0.0, 0.0);
           }
         }
         const double r = ok ? rvn - p.mean : 0.0;
-        st[(TENSOR ? 2 : 1) * KS * S + tid] = r;
-        if (aug) st[tid * S + D] = r;
+        st[(TENSOR ? 2 : 1) * KS * S + gk] = r;
+        if (aug) st[gk * S + D] = r;
       }
     };
-    BDF_STAMP(1);
     __syncthreads();  // ring zero-fill and barrier init visible before any stage is issued or consumed
-    if (nst > 0) { load_meta(0); issue(0); }
-    if (nst > 1) { load_meta(1); issue(1); }
+    const bool dbg_nogather = p.flags & 4, dbg_nocompute = p.flags & 2;  // timing experiments only (results invalid)
+    if (nst > 0 && !dbg_nogather) { load_meta(0); issue(0); }
+    if (nst > 1 && !dbg_nogather) { load_meta(1); issue(1); }
     if (nst > 2) load_meta(2);
+    // ---- everything below runs under the shadow of the first gathers ---------------------------------------------------
+#if BDF_FOLD
+    // Λ rides in the accumulators from the start (as Λ/α, on the row's first chunk), so that parking the tiles after the
+    // syrk yields Λ* = α·(Λ/α + G) in one pass; the loads are L2 hits hidden under the first gather.
+    if (split < 0 || p.item_chunk[item] == 0) {
+      const double ia = 1.0 / p.alpha;
+      warp_dispatch(warp, [&](auto w) {
+        constexpr int W = decltype(w)::value;
+        static_for<C::ntiles(W)>([&](auto t) {
+          constexpr int T = decltype(t)::value;
+          using ti = TI<C, W, T>;
+          const int i = 8 * ti::I + (lane >> 2), j = 8 * ti::J + 2 * (lane & 3);
+          const double2 l = __ldg(reinterpret_cast<const double2*>(p.LT + 64 * (tri(ti::I) + ti::J) + 2 * lane));
+          if (i < D) {
+            if (j < D) acc[T][0] = l.x * ia;
+            if (j + 1 < D) acc[T][1] = l.y * ia;
+          }
+        });
+      });
+    }
+#endif
+    // Λ·μ: precomputed when μ is shared; per-row μ (side features, src/macau.jl:102-107) is multiplied here
+    if (tid < DP) {
+      double s = 0.0;
+      if (p.lmu) {
+        s = __ldg(p.lmu + tid);
+      } else if (tid < D) {
+        const double* mu = p.mu + slot * p.mu_ld;
+        for (int i = 0; i < D; i++) s = fma(__ldg(p.Lambda + tid + (size_t)i * D), __ldg(mu + i), s);
+      }
+      lmu[tid] = s;
+    }
+
+    // The row's standard normals (injected, or Philox + Box–Muller in double: a few hundred instructions each) are
+    // produced here by DP threads in parallel, under the shadow of the first gather, and parked in xs[] until the
+    // substitution needs them — not serially by warp 0 at the end of the row.
+    if (tid < DP) {
+      double z = 0.0;
+      if (tid < D) {
+        const int64_t grow0 = (int64_t)lrow * p.world + p.rank;
+        z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, p.entity, grow0, tid);
+      }
+      xs[tid] = z;
+    }
+
+    BDF_STAMP(1);
     for (int s = 0; s < nst; s++) {
-      mbar_wait(fullb + (s % NBUF), (s / NBUF) & 1);  // the rows of stage s have landed
+      if (!dbg_nogather) mbar_wait(fullb + (s % NBUF), (s / NBUF) & 1);  // the rows of stage s have landed
       __syncthreads();                                // everyone is done with stage s-1: its buffer may be refilled
-      if (s + 2 < nst) issue(s + 2);
+      if (s + 2 < nst && !dbg_nogather) issue(s + 2);
       if (s + 3 < nst) load_meta(s + 3);
       const double* buf = ring + (s % NBUF) * STG;
       const double* rs = buf + (TENSOR ? 2 : 1) * KS * S;
       int rem = len - s * KS;
       if (rem > KS) rem = KS;
       const int nk4 = (rem + 3) >> 2;
-      warp_dispatch(warp, [&](auto w) { compute<decltype(w)::value, TENSOR>(acc, buf, nk4, lane); });
+      if (!dbg_nocompute) warp_dispatch(warp, [&](auto w) { compute<decltype(w)::value, TENSOR>(acc, buf, nk4, lane); });
       if (!aug && tid < DP) {
         for (int k = 0; k < nk4 * 4; k++) {
           double v = buf[k * S + tid];
@@ -438,8 +486,36 @@ struct RowKernel {
     BDF_STAMP(3);
     if (p.flags & 1) {
       if (tid == 0 && acc[0][0] == 1.2345) p.Uout[0] = acc[0][1];
+      if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + 4] = p.dbg[(size_t)item * 8 + 5] = p.dbg[(size_t)item * 8 + 6] = clock64();
       return;
     }
+#if BDF_FOLD
+    // ---- park Λ* = α·acc in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles), identity on the padding;
+    //      the augmented row (i == D) carries Σ v·r and becomes rhs = Λμ + α·Σv·r ---------------------------------------------
+    {
+      const double alpha = p.alpha;
+      warp_dispatch(warp, [&](auto w) {
+        constexpr int W = decltype(w)::value;
+        static_for<C::ntiles(W)>([&](auto t) {
+          constexpr int T = decltype(t)::value;
+          using ti = TI<C, W, T>;
+          double2 v = make_double2(alpha * acc[T][0], alpha * acc[T][1]);
+          if constexpr (ti::I == NB - 1) {  // only the last block row / column can touch the padding
+            const int i = 8 * ti::I + (lane >> 2), j = 8 * ti::J + 2 * (lane & 3);
+            if (aug && i == D) {
+              if (j < D) rhs[j] = fma(alpha, acc[T][0], lmu[j]);
+              if (j + 1 < D) rhs[j + 1] = fma(alpha, acc[T][1], lmu[j + 1]);
+            }
+            if (i >= D || j >= D) v.x = (i == j) ? 1.0 : 0.0;
+            if (i >= D || j + 1 >= D) v.y = (i == j + 1) ? 1.0 : 0.0;
+          }
+          *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + 2 * lane) = v;
+        });
+      });
+    }
+    if (!aug && tid < D) rhs[tid] = fma(p.alpha, bsum, lmu[tid]);
+    if (tid >= D && tid < DP) rhs[tid] = 0.0;
+#else
     // ---- park the Gram tiles in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles) -----------
     warp_dispatch(warp, [&](auto w) {
       constexpr int W = decltype(w)::value;
@@ -509,6 +585,7 @@ struct RowKernel {
       }
     }
 #endif
+#endif  // BDF_FOLD
     __syncthreads();
     BDF_STAMP(4);
 
@@ -516,6 +593,13 @@ struct RowKernel {
     // Per panel: (b) the panel tiles are scaled, R_pJ = W_pp⁻¹·A_pJ, by one DMMA pair each; (c) the tiles above the
     // panel get A_IJ −= R_pIᵀ·R_pJ, again DMMA, one block row per warp at a time; warp 0 takes the next diagonal tile
     // first and factors it while the other warps finish the trailing update (look-ahead).
+    // The serial roles (diagonal blocks, substitutions) rotate over the warps from item to item: warp w of every co-resident
+    // CTA sits on the same SM sub-partition, so a fixed "warp 0" would pile every row's dependent chain onto one scheduler.
+#if BDF_VWARP
+    const int vw = (warp - item) & (NW - 1);
+#else
+    const int vw = warp;
+#endif
     bool bad = false;
     const int fo = 8 * (lane & 3) + (lane >> 2);  // fragment offset in a row-major 8×8 tile: A[m][k]=B[k][m]=tile[k][m]
     auto factor_diag = [&](int pb) {
@@ -590,6 +674,73 @@ struct RowKernel {
           if (J + u <= j1) *reinterpret_cast<double2*>(trow + 64 * (J + u)) = make_double2(c2[u][0], c2[u][1]);
       }
     };
+    constexpr int BS_SWITCH = NW == 4 ? BDF_BS_SWITCH : 1000;  // panels at or above this: backsub_step rides on warp 0 (the trailing warps are the critical path there)
+#if BDF_TRAIL_PIPE
+    // The same trailing update as one flat tile list per warp (rows dealt to warps 1…NW-1 in a snake, tiles J = 0 … I, the
+    // tile (pb-1, pb-1) left to warp 0), software-pipelined: the operands of the next batch of four tiles are loaded before
+    // the DMMAs of the current batch issue, so the warp never sits on a shared-memory round trip with an idle pipe.
+    struct Batch {
+      double a0[4], a1[4], b0[4], b1[4], c[4][2];
+      int off[4];  // tile offset (doubles) of each slot, -1 = slot empty
+      bool any;
+    };
+    auto update_tiles = [&](int pb) {
+      constexpr int NWC = NW > 1 ? NW - 1 : 1;
+      const double* Pp = Tl + 64 * tri(pb) + fo;
+      int n = 0, I = 0, J = 0, j1 = -1;  // cursor: row counter n (I = pb-1-n), next tile J, last tile j1
+      auto seek_row = [&]() {            // advance n to this warp's next row; sets I, J, j1 (n == pb: exhausted)
+        for (; n < pb; n++) {
+          const int ph = n % (2 * NWC);
+          const int wo = 1 + (ph < NWC ? ph : 2 * NWC - 1 - ph);
+          if (wo == vw) {
+            I = pb - 1 - n;
+            J = 0;
+            j1 = n == 0 ? I - 1 : I;
+            if (j1 >= 0) return;
+          }
+        }
+      };
+      seek_row();
+      auto load = [&](Batch& B) {
+        B.any = n < pb;
+        int lastI = I, lastJ = J;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const bool ok = n < pb;
+          if (ok) { lastI = I; lastJ = J; }
+          B.off[u] = ok ? 64 * (tri(lastI) + lastJ) : -1;
+          B.a0[u] = -Pp[64 * lastI];
+          B.a1[u] = -Pp[64 * lastI + 32];
+          B.b0[u] = Pp[64 * lastJ];
+          B.b1[u] = Pp[64 * lastJ + 32];
+          const double2 cv = *reinterpret_cast<const double2*>(Tl + 64 * (tri(lastI) + lastJ) + 2 * lane);
+          B.c[u][0] = cv.x;
+          B.c[u][1] = cv.y;
+          if (ok) {
+            if (++J > j1) { n++; seek_row(); }
+          }
+        }
+      };
+      auto finish = [&](Batch& B) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) dmma884(B.c[u], B.a0[u], B.b0[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) dmma884(B.c[u], B.a1[u], B.b1[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (B.off[u] >= 0) *reinterpret_cast<double2*>(Tl + B.off[u] + 2 * lane) = make_double2(B.c[u][0], B.c[u][1]);
+      };
+      Batch A, B;
+      load(A);
+      while (A.any) {
+        load(B);
+        finish(A);
+        if (!B.any) break;
+        load(A);
+        finish(B);
+      }
+    };
+#endif
     // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
     // rhs[c] −= Σ_k R_J[k][c]·y_J[k] for c < 8J. One warp; rides along with the trailing update.
     auto backsub_step = [&](int J, bool update) {
@@ -618,14 +769,14 @@ struct RowKernel {
     };
 
     long long d_b = 0, d_c = 0, d_w1 = 0, d_w2 = 0, t_x = 0;
-    if (warp == 0) factor_diag(NB - 1);
+    if (vw == 0) factor_diag(NB - 1);
     __syncthreads();
     for (int pb = NB - 1; pb > 0; pb--) {
       if (p.dbg) t_x = clock64();
       // (b) scale the panel tiles (pb, J < pb) in place
       {
         const double wa0 = WvT[pb * 64 + fo], wa1 = WvT[pb * 64 + 32 + fo];
-        for (int J = warp; J < pb; J += NW) {
+        for (int J = vw; J < pb; J += NW) {
           double* tp = Tl + 64 * (tri(pb) + J);
           const double b0 = tp[fo], b1 = tp[32 + fo];
           double c2[2] = {0.0, 0.0};
@@ -643,33 +794,39 @@ struct RowKernel {
         for (int I = 0; I < pb; I++) update_row(pb, I, 0, I);
         __syncwarp();
         factor_diag(pb - 1);
-      } else if (warp == 0) {
+      } else if (vw == 0) {
         update_row(pb, pb - 1, pb - 1, pb - 1);
         __syncwarp();
         factor_diag(pb - 1);
+        if (pb >= BS_SWITCH) backsub_step(pb, true);  // large panels: the trailing warps are the critical path, the chain warp has slack
       } else {
-        if (warp == 1) backsub_step(pb, true);
+#if BDF_TRAIL_PIPE
+        if (vw == 1 && pb < BS_SWITCH) backsub_step(pb, true);
+        update_tiles(pb);
+#else
+        if (vw == 1 && pb < BS_SWITCH) backsub_step(pb, true);
         constexpr int NWC = NW > 1 ? NW - 1 : 1;
         for (int n = 0; n < pb; n++) {
           const int I = pb - 1 - n;
           const int ph = n % (2 * NWC);
           const int wo = 1 + (ph < NWC ? ph : 2 * NWC - 1 - ph);
-          if (wo == warp) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
+          if (wo == vw) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
         }
+#endif
       }
       if (p.dbg) { const long long t = clock64(); d_c += t - t_x; t_x = t; }
       __syncthreads();
       if (p.dbg) { const long long t = clock64(); d_w2 += t - t_x; t_x = t; }
     }
-    if (p.dbg && lane == 0 && warp < 2) {
-      long long* o = p.dbg + (size_t)gridDim.x * 8 + ((size_t)item * 2 + warp) * 4;
+    if (p.dbg && lane == 0 && vw < 2) {
+      long long* o = p.dbg + (size_t)gridDim.x * 8 + ((size_t)item * 2 + vw) * 4;
       o[0] = d_b; o[1] = d_w1; o[2] = d_c; o[3] = d_w2;
     }
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
     BDF_STAMP(5);
 
     // ---- warp 0: last block of y = W⁻¹·rhs, then x = W⁻ᵀ(y + z) by forward substitution over the block rows ---------
-    if (warp == 0) {
+    if (vw == 0) {
       const int r8 = lane & 7;
       const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
       backsub_step(0, false);
@@ -730,7 +887,7 @@ struct RowKernel {
         for (int j = lane; j < p.ld; j += 32) po[j] = j < D ? xs[j] : 0.0;
       }
       __syncwarp();
-      BDF_STAMP(6);
+      if (p.dbg && lane == 0) p.dbg[(size_t)item * 8 + 6] = clock64();
     }
   }
 #undef BDF_STAMP
@@ -739,8 +896,17 @@ struct RowKernel {
 #ifndef BDF_MINB
 #define BDF_MINB 3
 #endif
+#ifndef BDF_MINB4BIG
+#define BDF_MINB4BIG 4
+#endif
+// 4-warp CTAs for D > 64: as many rows in flight per SM as shared memory allows (≤ BDF_MINB4BIG), registers sized to match
 template <class K>
-__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? BDF_MINB1 : (K::NW == 4 ? (K::TENSOR ? 4 : 6) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
+constexpr int big4_min_blocks() {
+  const int fit = (int)(233472 / (K::SMEM_BYTES + 1024));
+  return fit < 1 ? 1 : (fit > BDF_MINB4BIG ? BDF_MINB4BIG : fit);
+}
+template <class K>
+__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? BDF_MINB1 : (K::NW == 4 ? (K::DP > 64 ? big4_min_blocks<K>() : (K::TENSOR ? 4 : 6)) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
   extern __shared__ __align__(16) double smem_dyn[];
   K::run(p, smem_dyn);
 }
