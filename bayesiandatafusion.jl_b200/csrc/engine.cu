@@ -180,26 +180,40 @@ int ensure_ws(bdf_t* h, size_t bytes) {
   return BDF_OK;
 }
 
-// Split heavy rows into chunks, order work items by cost (heaviest first) and upload the list.
-int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr, int64_t real_rows) {
+// Split heavy rows into chunks, order work items by cost (heaviest first) and upload the list. `rps` holds one host row_ptr per
+// relation the entity takes part in (src/sampling.jl:266-283 sums the relations' contributions to a row): a row whose
+// observations come as several items — chunks of a long row and/or one relation each — is a "split" row whose partials are
+// added in item order (relation order, then chunk order) by the last item to finish.
+int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector<int64_t>*>& rps, int64_t real_rows) {
   const int64_t CH = 8192;  // observations per chunk of a split row (multiple of every KS)
-  std::vector<int32_t> irow, ilen, isplit, ichunk, snch;
+  const bool multi = rps.size() > 1;
+  std::vector<int32_t> irow, ilen, isplit, ichunk, irel, snch;
   std::vector<int64_t> ibeg, swoff;
   int64_t slots = 0;
+  struct Piece { int64_t beg, len; int rel; };
+  std::vector<Piece> pieces;
   for (int64_t r = 0; r < real_rows; r++) {
-    const int64_t b = row_ptr[r], n = row_ptr[r + 1] - b;
-    if (n <= CH + CH / 2) {
-      irow.push_back((int32_t)r); ibeg.push_back(b); ilen.push_back((int32_t)n); isplit.push_back(-1); ichunk.push_back(0);
-    } else {
-      const int64_t nch = (n + CH - 1) / CH;
-      const int sid = (int)snch.size();
-      snch.push_back((int32_t)nch);
-      swoff.push_back(slots);
-      slots += nch;
-      for (int64_t c = 0; c < nch; c++) {
-        const int64_t cb = b + c * CH, ce = std::min(b + n, cb + CH);
-        irow.push_back((int32_t)r); ibeg.push_back(cb); ilen.push_back((int32_t)(ce - cb)); isplit.push_back(sid); ichunk.push_back((int32_t)c);
+    pieces.clear();
+    for (size_t s = 0; s < rps.size(); s++) {
+      const int64_t b = (*rps[s])[r], n = (*rps[s])[r + 1] - b;
+      if (n == 0) continue;
+      if (n <= CH + CH / 2) {
+        pieces.push_back({b, n, (int)s});
+      } else {
+        const int64_t nch = (n + CH - 1) / CH;
+        for (int64_t c = 0; c < nch; c++) pieces.push_back({b + c * CH, std::min(n - c * CH, CH), (int)s});
       }
+    }
+    if (pieces.empty()) pieces.push_back({(*rps[0])[r], 0, 0});  // no observations anywhere: the row is drawn from the prior
+    const int sid = pieces.size() > 1 ? (int)snch.size() : -1;
+    if (sid >= 0) {
+      snch.push_back((int32_t)pieces.size());
+      swoff.push_back(slots);
+      slots += (int64_t)pieces.size();
+    }
+    for (size_t c = 0; c < pieces.size(); c++) {
+      irow.push_back((int32_t)r); ibeg.push_back(pieces[c].beg); ilen.push_back((int32_t)pieces[c].len);
+      isplit.push_back(sid); ichunk.push_back((int32_t)c); irel.push_back(pieces[c].rel);
     }
   }
   const size_t ni = irow.size();
@@ -208,7 +222,7 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ilen[a] > ilen[b]; });
   auto permute32 = [&](std::vector<int32_t>& v) { std::vector<int32_t> t(ni); for (size_t i = 0; i < ni; i++) t[i] = v[order[i]]; v.swap(t); };
   auto permute64 = [&](std::vector<int64_t>& v) { std::vector<int64_t> t(ni); for (size_t i = 0; i < ni; i++) t[i] = v[order[i]]; v.swap(t); };
-  permute32(irow); permute32(ilen); permute32(isplit); permute32(ichunk); permute64(ibeg);
+  permute32(irow); permute32(ilen); permute32(isplit); permute32(ichunk); permute32(irel); permute64(ibeg);
   mi.n_items = (int)ni;
   mi.n_split = (int)snch.size();
   mi.ws_slots = slots;
@@ -218,6 +232,7 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr
   if ((rc = dev_alloc(h, &mi.item_len, ni))) return rc;
   if ((rc = dev_alloc(h, &mi.item_split, ni))) return rc;
   if ((rc = dev_alloc(h, &mi.item_chunk, ni))) return rc;
+  if (multi && (rc = dev_alloc(h, &mi.item_rel, ni))) return rc;
   if ((rc = dev_alloc(h, &mi.split_nchunks, snch.size()))) return rc;
   if ((rc = dev_alloc(h, &mi.split_wsoff, snch.size()))) return rc;
   if ((rc = dev_alloc(h, &mi.split_counter, snch.size()))) return rc;
@@ -227,6 +242,7 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr
     CU(cudaMemcpyAsync(mi.item_len, ilen.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(mi.item_split, isplit.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(mi.item_chunk, ichunk.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
+    if (multi) CU(cudaMemcpyAsync(mi.item_rel, irel.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
   }
   if (!snch.empty()) {
     CU(cudaMemcpyAsync(mi.split_nchunks, snch.data(), snch.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -237,32 +253,60 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<int64_t>& row_ptr
   return ensure_ws(h, std::max<size_t>(sizeof(double) * (size_t)slots * h->pst, sizeof(double) * 296 * (size_t)tri(h->D + 1)));
 }
 
+void free_work_list(ModeIndex& mi) {
+  cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk); cudaFree(mi.item_rel);
+  cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
+  mi.item_row = mi.item_len = mi.item_split = mi.item_chunk = mi.item_rel = mi.split_nchunks = nullptr;
+  mi.item_beg = mi.split_wsoff = nullptr;
+  mi.split_counter = nullptr;
+  mi.n_items = mi.n_split = 0;
+}
+
 void prep_lambda(bdf_t* h, const double* Lambda, const double* mu, int D, int DP, double* LT, double* lmu);
 
 int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev,
                   long long* dbg = nullptr) {
   EntityS& e = h->ents[entity];
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
-  if (e.uses.size() > 1) FAIL(BDF_ERR_INVALID, "entities in several relations are not supported yet (SURVEY §8f N4)");
-  RelationS& rel = h->rels[e.uses[0].first];
-  const int mode = e.uses[0].second;
-  ModeIndex& mi = rel.modes[mode];
+  if (e.uses.size() > BDF_MAX_USES) FAIL(BDF_ERR_INVALID, "an entity may take part in at most 6 relations");
+  // an entity in several relations (src/sampling.jl:251-289) runs off a merged work list, rebuilt when a relation was added
+  const ModeIndex* wl = &h->rels[e.uses[0].first].modes[e.uses[0].second];
+  if (e.uses.size() > 1) {
+    if (e.merged_uses != e.uses.size()) {
+      free_work_list(e.merged);
+      std::vector<const std::vector<int64_t>*> rps;
+      for (auto& u : e.uses) rps.push_back(&h->rels[u.first].modes[u.second].h_row_ptr);
+      int rc = build_work_list(h, e.merged, rps, e.nlocal);
+      if (rc) return rc;
+      e.merged_uses = e.uses.size();
+    }
+    wl = &e.merged;
+  }
   RowParams p{};
-  p.item_row = mi.item_row; p.item_beg = mi.item_beg; p.item_len = mi.item_len; p.item_split = mi.item_split; p.item_chunk = mi.item_chunk;
-  p.split_nchunks = mi.split_nchunks; p.split_wsoff = mi.split_wsoff; p.split_counter = mi.split_counter; p.ws = h->ws;
-  p.col0 = mi.col[0]; p.col1 = mi.col[1]; p.val = mi.val;
-  p.P0 = h->ents[mi.other_entity[0]].U;
-  p.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr;
+  p.item_row = wl->item_row; p.item_beg = wl->item_beg; p.item_len = wl->item_len; p.item_split = wl->item_split; p.item_chunk = wl->item_chunk;
+  p.item_rel = wl->item_rel;
+  p.split_nchunks = wl->split_nchunks; p.split_wsoff = wl->split_wsoff; p.split_counter = wl->split_counter; p.ws = h->ws;
+  bool tensor = false;
+  for (auto& u : e.uses) tensor = tensor || h->rels[u.first].K > 2;
+  for (size_t i = 0; i < e.uses.size(); i++) {
+    RelationS& rel = h->rels[e.uses[i].first];
+    ModeIndex& mi = rel.modes[e.uses[i].second];
+    RelTab& t = p.rt[i];
+    t.col0 = mi.col[0]; t.col1 = rel.K > 2 ? mi.col[1] : nullptr; t.val = mi.val;
+    t.P0 = h->ents[mi.other_entity[0]].U;
+    t.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : (tensor ? h->ones : nullptr);
+    t.alpha = rel.alpha; t.mean = rel.mean;
+  }
   p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper;
   { int np = 0; for (int r = 0; r < 8; r++) if (e.peerU[r]) p.peer_out[np++] = e.peerU[r]; }
   p.Lambda = Lambda_dev; p.mu = mu_dev; p.mu_ld = mu_ld; p.Z = Z_dev;
   p.LT = h->lt; p.lmu = mu_ld ? nullptr : h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2;
   prep_lambda(h, Lambda_dev, mu_ld ? nullptr : mu_dev, h->D, h->DP, h->lt, h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2);
   h->launches++;
-  p.alpha = rel.alpha; p.mean = rel.mean; p.D = h->D; p.rank = h->rank; p.world = h->world;
+  p.D = h->D; p.rank = h->rank; p.world = h->world;
   p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag; p.dbg = dbg;
   { const char* f = getenv("BDF_DEBUG_FLAGS"); p.flags = f ? atoi(f) : 0; }
-  return launch_rows(h, p, mi.n_items, rel.K > 2);
+  return launch_rows(h, p, wl->n_items, tensor);
 }
 
 void prep_lambda(bdf_t* h, const double* Lambda, const double* mu, int D, int DP, double* LT, double* lmu) {
@@ -354,7 +398,12 @@ int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
   if ((ce = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   h->stream = h->own_stream;
   if ((ce = cudaMalloc((void**)&h->err_flag, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
-  if ((ce = cudaMalloc((void**)&h->work_counter, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  {
+    if ((ce = cudaMalloc((void**)&h->ones, sizeof(double) * h->ld)) != cudaSuccess) return bail(ce, "cudaMalloc");
+    std::vector<double> one(h->ld, 0.0);
+    for (int j = 0; j < h->D; j++) one[j] = 1.0;
+    cudaMemcpy(h->ones, one.data(), sizeof(double) * h->ld, cudaMemcpyHostToDevice);
+  }
   h->num_sms = prop.multiProcessorCount;
   cudaMemset(h->err_flag, 0, sizeof(int));
   if ((ce = cudaMalloc((void**)&h->scratch, sizeof(double) * ((size_t)4 * num_latent * num_latent + 4 * num_latent))) != cudaSuccess) return bail(ce, "cudaMalloc");
@@ -375,15 +424,15 @@ int bdf_destroy(bdf_t* h) {
     cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
     cudaFree(e.sp_items[0]); cudaFree(e.sp_items[1]); cudaFree(e.sp_long[0]); cudaFree(e.sp_long[1]); cudaFree(e.sp_part);
     cudaFree(e.f_val_csr); cudaFree(e.f_val_csc);
+    free_work_list(e.merged);
   }
   for (auto& r : h->rels)
     for (int m = 0; m < r.K; m++) {
       ModeIndex& mi = r.modes[m];
       cudaFree(mi.row_ptr); cudaFree(mi.col[0]); cudaFree(mi.col[1]); cudaFree(mi.val);
-      cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk);
-      cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
+      free_work_list(mi);
     }
-  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->work_counter); cudaFree(h->arena);
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->ones); cudaFree(h->arena);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return BDF_OK;
@@ -515,7 +564,8 @@ int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, co
     std::vector<int64_t> rp((size_t)e.Nper + 1);
     CUT(cudaMemcpyAsync(rp.data(), mi.row_ptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost, h->stream));
     CUT(cudaStreamSynchronize(h->stream));
-    TRY(build_work_list(h, mi, rp, e.nlocal));
+    mi.h_row_ptr = rp;
+    TRY(build_work_list(h, mi, {&mi.h_row_ptr}, e.nlocal));
   }
   CUT(cudaStreamSynchronize(h->stream));
   cleanup();
@@ -735,7 +785,7 @@ int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, in
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
-  const int ni = h->rels[e.uses[0].first].modes[e.uses[0].second].n_items;
+  const int ni = e.uses.size() > 1 && e.merged_uses == e.uses.size() ? e.merged.n_items : h->rels[e.uses[0].first].modes[e.uses[0].second].n_items;
   long long* d = nullptr;
   CU(cudaMalloc((void**)&d, sizeof(long long) * 16 * (size_t)std::max(ni, 1)));
   CU(cudaMemsetAsync(d, 0, sizeof(long long) * 16 * (size_t)std::max(ni, 1), h->stream));

@@ -24,10 +24,12 @@ struct ModeIndex {            // one mode of one relation, restricted to the row
   int32_t* item_len = nullptr;
   int32_t* item_split = nullptr;
   int32_t* item_chunk = nullptr;
+  int32_t* item_rel = nullptr;  // merged list of an entity in several relations: index into EntityS::uses (else nullptr)
   int32_t* split_nchunks = nullptr;
   int64_t* split_wsoff = nullptr;
   int* split_counter = nullptr;
   int64_t ws_slots = 0;
+  std::vector<int64_t> h_row_ptr;  // host copy of row_ptr (merged work lists are built from it)
 };
 
 struct RelationS {
@@ -52,6 +54,8 @@ struct EntityS {
   std::vector<double> mu0, WI;
   double b0 = 2.0, nu0 = 0.0;
   std::vector<std::pair<int, int>> uses;  // (relation, mode) pairs this entity takes part in
+  ModeIndex merged;                       // work list over ALL uses (only its item_*/split_* fields), built lazily when uses.size() > 1
+  size_t merged_uses = 0;                 // number of uses the merged list was built for
   // side features (Macau): sparse binary F (N × numF) as CSR and CSC index lists, link matrix beta (numF × ld, row-major)
   int64_t numF = 0, fnnz = 0;
   int64_t* f_rowptr = nullptr;  // [N+1]   rows of F
@@ -106,7 +110,7 @@ struct bdf_handle {
   size_t ws_bytes = 0;
   double* scratch = nullptr;  // 4 D×D matrices for the Normal-Wishart draw
   int* err_flag = nullptr;
-  int* work_counter = nullptr;  // work queue head of the persistent row kernel
+  double* ones = nullptr;  // a row of ones (ld doubles, zero padding): the second partner of a 2-mode relation inside a 3-mode launch
   int num_sms = 148;
   double* lt = nullptr;  // Λ in tile order + Λ·μ, rebuilt per half-sweep
   char* arena = nullptr;  // grow-only staging for host-facing calls (predict ids/slots/output, beta sampler temporaries)

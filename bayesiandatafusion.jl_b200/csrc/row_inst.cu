@@ -5,7 +5,7 @@
 
 #include "../../include/bdf_b200.h"
 #include "engine.cuh"
-#include "row_kernel_ws.cuh"
+#include "row_kernel.cuh"
 #include "stats_kernel.cuh"
 
 #ifndef BDF_DP
@@ -23,30 +23,7 @@ static constexpr int kDP = BDF_DP;
 static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : BDF_NW_BIG);
 
 template <bool TENSOR>
-static int launch_rows_ws(bdf_t* h, RowParams p, int n_items) {
-  using KW = RowKernelWS<kDP, TENSOR>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(row_kernel_ws<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KW::SMEM_BYTES));
-    attr_done = true;
-  }
-  if (n_items > 0) {
-    CU(cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-    p.work_counter = h->work_counter;
-    p.n_items = n_items;
-    const int grid = n_items < h->num_sms ? n_items : h->num_sms;
-    row_kernel_ws<KW><<<grid, KW::NTHR, KW::SMEM_BYTES, h->stream>>>(p);
-    h->launches++;
-    CU(cudaGetLastError());
-  }
-  return BDF_OK;
-}
-
-template <bool TENSOR>
 static int launch_rows_t(bdf_t* h, const RowParams& p, int n_items) {
-  if constexpr (kDP > 64 && !TENSOR) {
-    if (getenv("BDF_WS") && !p.dbg) return launch_rows_ws<TENSOR>(h, p, n_items);  // experimental persistent variant, off by default
-  }
   using K = RowKernel<kDP, kNW, TENSOR>;
   static bool attr_done = false;
   if (!attr_done) {

@@ -26,7 +26,45 @@
 #include "philox.cuh"
 #include "tiles.cuh"
 
+// build-time knobs (tools/ab.sh builds variants with -D...)
+#ifndef BDF_K4_UNROLL
+#define BDF_K4_UNROLL 1
+#endif
+#ifndef BDF_FD_UNROLL
+#define BDF_FD_UNROLL 8
+#endif
+#ifndef BDF_NBUF1
+#define BDF_NBUF1 3
+#endif
+#ifndef BDF_MINB1
+#define BDF_MINB1 16
+#endif
+#ifndef BDF_VWARP
+#define BDF_VWARP 1
+#endif
+#ifndef BDF_HALLEY
+#define BDF_HALLEY 1
+#endif
+#ifndef BDF_BS_SWITCH
+#define BDF_BS_SWITCH 1000
+#endif
+#ifndef BDF_UR_UNROLL
+#define BDF_UR_UNROLL 4
+#endif
+
 namespace bdf {
+
+#define BDF_MAX_USES 6
+struct RelTab {
+  // CSR payload of the entity's mode in one relation; col* hold SLOT indices of the partner rows (col1 == nullptr in a launch
+  // of the 3-mode kernel: a 2-mode relation, the second partner is the all-ones row P1)
+  const int32_t* col0;
+  const int32_t* col1;
+  const double* val;
+  const double* P0;  // partner factor buffers (slot-major, ld doubles per row)
+  const double* P1;
+  double alpha, mean;
+};
 
 struct RowParams {
   // work list (cost-descending)
@@ -39,12 +77,10 @@ struct RowParams {
   const int64_t* split_wsoff;  // first partial slot of the split row
   int* split_counter;          // arrival counters (self-resetting)
   double* ws;                  // partial workspace
-  // observations of this mode (CSR payload); col* hold SLOT indices of the partner rows
-  const int32_t* col0;
-  const int32_t* col1;
-  const double* val;
-  const double* P0;  // partner factor buffers (slot-major, ld doubles per row)
-  const double* P1;
+  // observations of this mode, one table entry per relation the entity takes part in (src/sampling.jl:266-283 sums the
+  // relations' contributions); item_rel[item] picks the entry, nullptr = entry 0 for every item
+  RelTab rt[BDF_MAX_USES];
+  const int32_t* item_rel;
   int ld;        // row pitch (doubles) of every factor buffer
   double* Uout;  // factor buffer being sampled
   double* peer_out[8];  // fused all-gather: the same buffer on every OTHER rank (IPC-mapped peer memory, NVLink stores), nullptr-terminated
@@ -55,13 +91,11 @@ struct RowParams {
   const double* mu;      // D (mu_ld == 0) or slot-major matrix (mu_ld == ld)
   int64_t mu_ld;
   const double* Z;  // injected normals, slot-major (ld pitch), or nullptr → Philox
-  double alpha, mean;
   int D;
   int rank, world;
   uint64_t seed, sweep;
   int entity;
   int* err_flag;
-  int* work_counter;  // dynamic work queue of the persistent kernel (row_kernel_ws), zeroed before each launch
   int n_items;
   int flags;       // debug: bit 0 = return after the syrk (timing experiments only; results invalid)
   long long* dbg;  // optional per-item phase clocks [n_items][8] (bdf_debug_phase_clocks), else nullptr
@@ -151,39 +185,6 @@ __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
   J = t - tri(i);
 }
 
-#ifndef BDF_K4_UNROLL
-#define BDF_K4_UNROLL 1
-#endif
-#ifndef BDF_FD_UNROLL
-#define BDF_FD_UNROLL 8
-#endif
-#ifndef BDF_BUILD_PREFETCH
-#define BDF_BUILD_PREFETCH 0
-#endif
-#ifndef BDF_NBUF1
-#define BDF_NBUF1 3
-#endif
-#ifndef BDF_MINB1
-#define BDF_MINB1 16
-#endif
-#ifndef BDF_VWARP
-#define BDF_VWARP 1
-#endif
-#ifndef BDF_HALLEY
-#define BDF_HALLEY 1
-#endif
-#ifndef BDF_FOLD
-#define BDF_FOLD 1
-#endif
-#ifndef BDF_TRAIL_PIPE
-#define BDF_TRAIL_PIPE 0
-#endif
-#ifndef BDF_BS_SWITCH
-#define BDF_BS_SWITCH 1000
-#endif
-#ifndef BDF_UR_UNROLL
-#define BDF_UR_UNROLL 4
-#endif
 
 template <int DP_, int NW_, bool TENSOR_>
 struct RowKernel {
@@ -296,6 +297,10 @@ struct RowKernel {
     const int64_t oend = obeg + len;
     const int split = p.item_split[item];
     const int64_t slot = p.slot_base + lrow;
+    const RelTab& rt = p.rt[p.item_rel ? p.item_rel[item] : 0];
+    // a row fed by one work item scales its Gram matrix by α when parking it; the partials of a row split over several items
+    // (chunks of a long row, or one relation each) are parked already scaled by their own α and just add up
+    const double alpha_f = split < 0 ? rt.alpha : 1.0;
 
     double* ring = smem;                    // [NBUF][STG]: tile (KS×S), [second tile], residuals (KS)
     double* Tl = smem;                      // Λ* / factor tiles, alias the ring after the main loop
@@ -347,9 +352,9 @@ struct RowKernel {
       if (gl) {
         int64_t o = obeg + (int64_t)s * KS + gk;
         if (o >= oend) o = oend - 1;
-        c0n = __ldg(p.col0 + o);
-        if (TENSOR) c1n = __ldg(p.col1 + o);
-        rvn = __ldg(p.val + o);
+        c0n = __ldg(rt.col0 + o);
+        if (TENSOR) c1n = rt.col1 ? __ldg(rt.col1 + o) : 0;
+        rvn = __ldg(rt.val + o);
       }
     };
     auto issue = [&](int s) {
@@ -361,8 +366,8 @@ struct RowKernel {
         const bool ok = gk < nvalid;
         if (tid == 0) mbar_arrive_expect_tx(fullb + b, (uint32_t)nvalid * rowbytes * (TENSOR ? 2u : 1u));
         if (ok) {
-          bulk_copy_g2s(st + gk * S, p.P0 + (size_t)c0n * p.ld, rowbytes, fullb + b);
-          if (TENSOR) bulk_copy_g2s(st + (KS + gk) * S, p.P1 + (size_t)c1n * p.ld, rowbytes, fullb + b);
+          bulk_copy_g2s(st + gk * S, rt.P0 + (size_t)c0n * p.ld, rowbytes, fullb + b);
+          if (TENSOR) bulk_copy_g2s(st + (KS + gk) * S, rt.P1 + (size_t)c1n * p.ld, rowbytes, fullb + b);
         } else if (gk < ((nvalid + 3) & ~3)) {
           // rows of the last, partly filled k-step: zero them (only the final stage of an item ever takes this path)
           for (int c = 0; c < 2 * npc; c += 2) {
@@ -370,7 +375,7 @@ struct RowKernel {
             if (TENSOR) *reinterpret_cast<double2*>(st + (KS + gk) * S + c) = make_double2(0.0, 0.0);
           }
         }
-        const double r = ok ? rvn - p.mean : 0.0;
+        const double r = ok ? rvn - rt.mean : 0.0;
         st[(TENSOR ? 2 : 1) * KS * S + gk] = r;
         if (aug) st[gk * S + D] = r;
       }
@@ -381,11 +386,10 @@ struct RowKernel {
     if (nst > 1 && !dbg_nogather) { load_meta(1); issue(1); }
     if (nst > 2) load_meta(2);
     // ---- everything below runs under the shadow of the first gathers ---------------------------------------------------
-#if BDF_FOLD
     // Λ rides in the accumulators from the start (as Λ/α, on the row's first chunk), so that parking the tiles after the
     // syrk yields Λ* = α·(Λ/α + G) in one pass; the loads are L2 hits hidden under the first gather.
     if (split < 0 || p.item_chunk[item] == 0) {
-      const double ia = 1.0 / p.alpha;
+      const double ia = 1.0 / rt.alpha;
       warp_dispatch(warp, [&](auto w) {
         constexpr int W = decltype(w)::value;
         static_for<C::ntiles(W)>([&](auto t) {
@@ -400,7 +404,6 @@ struct RowKernel {
         });
       });
     }
-#endif
     // Λ·μ: precomputed when μ is shared; per-row μ (side features, src/macau.jl:102-107) is multiplied here
     if (tid < DP) {
       double s = 0.0;
@@ -454,8 +457,8 @@ struct RowKernel {
       double* part = p.ws + (size_t)(p.split_wsoff[split] + p.item_chunk[item]) * PST;
 #pragma unroll
       for (int t = 0; t < TPW; t++)
-        *reinterpret_cast<double2*>(part + ((size_t)(warp * TPW + t) * 32 + lane) * 2) = make_double2(acc[t][0], acc[t][1]);
-      if (tid < DP) part[NW * TPW * 64 + tid] = bsum;
+        *reinterpret_cast<double2*>(part + ((size_t)(warp * TPW + t) * 32 + lane) * 2) = make_double2(rt.alpha * acc[t][0], rt.alpha * acc[t][1]);
+      if (tid < DP) part[NW * TPW * 64 + tid] = rt.alpha * bsum;
       __threadfence();
       __syncthreads();
       __shared__ int s_last;
@@ -489,11 +492,10 @@ struct RowKernel {
       if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + 4] = p.dbg[(size_t)item * 8 + 5] = p.dbg[(size_t)item * 8 + 6] = clock64();
       return;
     }
-#if BDF_FOLD
     // ---- park Λ* = α·acc in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles), identity on the padding;
     //      the augmented row (i == D) carries Σ v·r and becomes rhs = Λμ + α·Σv·r ---------------------------------------------
     {
-      const double alpha = p.alpha;
+      const double alpha = alpha_f;
       warp_dispatch(warp, [&](auto w) {
         constexpr int W = decltype(w)::value;
         static_for<C::ntiles(W)>([&](auto t) {
@@ -513,79 +515,8 @@ struct RowKernel {
         });
       });
     }
-    if (!aug && tid < D) rhs[tid] = fma(p.alpha, bsum, lmu[tid]);
+    if (!aug && tid < D) rhs[tid] = fma(alpha_f, bsum, lmu[tid]);
     if (tid >= D && tid < DP) rhs[tid] = 0.0;
-#else
-    // ---- park the Gram tiles in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles) -----------
-    warp_dispatch(warp, [&](auto w) {
-      constexpr int W = decltype(w)::value;
-      static_for<C::ntiles(W)>([&](auto t) {
-        constexpr int T = decltype(t)::value;
-        using ti = TI<C, W, T>;
-        *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + 2 * lane) = make_double2(acc[T][0], acc[T][1]);
-      });
-    });
-    if (!aug && tid < D) rhs[tid] = fma(p.alpha, bsum, lmu[tid]);
-    if (tid >= D && tid < DP) rhs[tid] = 0.0;
-    // ---- Λ* = Λ + αG, rhs = Λμ + α·Σv·r (augmented row), identity on the padding — same code for every warp -------
-    // The pre-tiled Λ (L2 hits) is fetched for all of this warp's tiles before the barrier so the loads overlap it.
-#if BDF_BUILD_PREFETCH
-    // (variant kept for experiments)
-    {
-      constexpr int BT = (C::NT + NW - 1) / NW;
-      double2 lt[BT];
-#pragma unroll
-      for (int b = 0; b < BT; b++) {
-        const int t = warp + b * NW;
-        lt[b] = t < C::NT ? __ldg(reinterpret_cast<const double2*>(p.LT + 64 * t + 2 * lane)) : make_double2(0.0, 0.0);
-      }
-      __syncthreads();
-      const double alpha = p.alpha;
-      const int r = lane >> 2, q = lane & 3;
-#pragma unroll
-      for (int b = 0; b < BT; b++) {
-        const int t = warp + b * NW;
-        if (t < C::NT) {
-          int I, J;
-          tri_coords(t, I, J);
-          const int i = 8 * I + r, j = 8 * J + 2 * q;
-          const double2 g = *reinterpret_cast<const double2*>(Tl + 64 * t + 2 * lane);
-          double2 v = lt[b];
-          if (i < D) {
-            if (j < D) v.x = fma(alpha, g.x, v.x);
-            if (j + 1 < D) v.y = fma(alpha, g.y, v.y);
-          } else if (aug && i == D) {
-            if (j < D) rhs[j] = fma(alpha, g.x, lmu[j]);
-            if (j + 1 < D) rhs[j + 1] = fma(alpha, g.y, lmu[j + 1]);
-          }
-          *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = v;
-        }
-      }
-    }
-#else
-    __syncthreads();
-    {
-      const double alpha = p.alpha;
-      const int r = lane >> 2, q = lane & 3;
-#pragma unroll 2
-      for (int t = warp; t < C::NT; t += NW) {
-        int I, J;
-        tri_coords(t, I, J);
-        const int i = 8 * I + r, j = 8 * J + 2 * q;
-        const double2 g = *reinterpret_cast<const double2*>(Tl + 64 * t + 2 * lane);
-        double2 v = __ldg(reinterpret_cast<const double2*>(p.LT + 64 * t + 2 * lane));
-        if (i < D) {
-          if (j < D) v.x = fma(alpha, g.x, v.x);
-          if (j + 1 < D) v.y = fma(alpha, g.y, v.y);
-        } else if (aug && i == D) {
-          if (j < D) rhs[j] = fma(alpha, g.x, lmu[j]);
-          if (j + 1 < D) rhs[j + 1] = fma(alpha, g.y, lmu[j + 1]);
-        }
-        *reinterpret_cast<double2*>(Tl + 64 * t + 2 * lane) = v;
-      }
-    }
-#endif
-#endif  // BDF_FOLD
     __syncthreads();
     BDF_STAMP(4);
 
@@ -675,72 +606,6 @@ struct RowKernel {
       }
     };
     constexpr int BS_SWITCH = NW == 4 ? BDF_BS_SWITCH : 1000;  // panels at or above this: backsub_step rides on warp 0 (the trailing warps are the critical path there)
-#if BDF_TRAIL_PIPE
-    // The same trailing update as one flat tile list per warp (rows dealt to warps 1…NW-1 in a snake, tiles J = 0 … I, the
-    // tile (pb-1, pb-1) left to warp 0), software-pipelined: the operands of the next batch of four tiles are loaded before
-    // the DMMAs of the current batch issue, so the warp never sits on a shared-memory round trip with an idle pipe.
-    struct Batch {
-      double a0[4], a1[4], b0[4], b1[4], c[4][2];
-      int off[4];  // tile offset (doubles) of each slot, -1 = slot empty
-      bool any;
-    };
-    auto update_tiles = [&](int pb) {
-      constexpr int NWC = NW > 1 ? NW - 1 : 1;
-      const double* Pp = Tl + 64 * tri(pb) + fo;
-      int n = 0, I = 0, J = 0, j1 = -1;  // cursor: row counter n (I = pb-1-n), next tile J, last tile j1
-      auto seek_row = [&]() {            // advance n to this warp's next row; sets I, J, j1 (n == pb: exhausted)
-        for (; n < pb; n++) {
-          const int ph = n % (2 * NWC);
-          const int wo = 1 + (ph < NWC ? ph : 2 * NWC - 1 - ph);
-          if (wo == vw) {
-            I = pb - 1 - n;
-            J = 0;
-            j1 = n == 0 ? I - 1 : I;
-            if (j1 >= 0) return;
-          }
-        }
-      };
-      seek_row();
-      auto load = [&](Batch& B) {
-        B.any = n < pb;
-        int lastI = I, lastJ = J;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const bool ok = n < pb;
-          if (ok) { lastI = I; lastJ = J; }
-          B.off[u] = ok ? 64 * (tri(lastI) + lastJ) : -1;
-          B.a0[u] = -Pp[64 * lastI];
-          B.a1[u] = -Pp[64 * lastI + 32];
-          B.b0[u] = Pp[64 * lastJ];
-          B.b1[u] = Pp[64 * lastJ + 32];
-          const double2 cv = *reinterpret_cast<const double2*>(Tl + 64 * (tri(lastI) + lastJ) + 2 * lane);
-          B.c[u][0] = cv.x;
-          B.c[u][1] = cv.y;
-          if (ok) {
-            if (++J > j1) { n++; seek_row(); }
-          }
-        }
-      };
-      auto finish = [&](Batch& B) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) dmma884(B.c[u], B.a0[u], B.b0[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++) dmma884(B.c[u], B.a1[u], B.b1[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (B.off[u] >= 0) *reinterpret_cast<double2*>(Tl + B.off[u] + 2 * lane) = make_double2(B.c[u][0], B.c[u][1]);
-      };
-      Batch A, B;
-      load(A);
-      while (A.any) {
-        load(B);
-        finish(A);
-        if (!B.any) break;
-        load(A);
-        finish(B);
-      }
-    };
-#endif
     // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
     // rhs[c] −= Σ_k R_J[k][c]·y_J[k] for c < 8J. One warp; rides along with the trailing update.
     auto backsub_step = [&](int J, bool update) {
@@ -800,10 +665,6 @@ struct RowKernel {
         factor_diag(pb - 1);
         if (pb >= BS_SWITCH) backsub_step(pb, true);  // large panels: the trailing warps are the critical path, the chain warp has slack
       } else {
-#if BDF_TRAIL_PIPE
-        if (vw == 1 && pb < BS_SWITCH) backsub_step(pb, true);
-        update_tiles(pb);
-#else
         if (vw == 1 && pb < BS_SWITCH) backsub_step(pb, true);
         constexpr int NWC = NW > 1 ? NW - 1 : 1;
         for (int n = 0; n < pb; n++) {
@@ -812,7 +673,6 @@ struct RowKernel {
           const int wo = 1 + (ph < NWC ? ph : 2 * NWC - 1 - ph);
           if (wo == vw) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
         }
-#endif
       }
       if (p.dbg) { const long long t = clock64(); d_c += t - t_x; t_x = t; }
       __syncthreads();

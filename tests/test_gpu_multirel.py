@@ -1,0 +1,98 @@
+"""GPU parity for entities that sit in several relations (sample_user2_all! / sample_user2, src/sampling.jl:251-289):
+the row's precision and rhs are sums over the relations, each with its own alpha and mean. Oracle: orc.sample_row."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def oracle_rows(D, n_rows, uses, mu, Lambda, Z):
+    """uses: list of (ids, vals, mode, [partner factor matrices in mode order], alpha, mean)."""
+    out = np.zeros((n_rows, D))
+    for i in range(n_rows):
+        rels = []
+        for ids, vals, mode, Us, alpha, mean in uses:
+            sel = np.nonzero(ids[:, mode] == i + 1)[0]  # table order, as FastIDF keeps it
+            others = [m for m in range(ids.shape[1]) if m != mode]
+            rels.append({"U": Us, "ids": [ids[sel, m] for m in others], "vals": vals[sel], "offset": mean, "alpha": alpha})
+        out[i] = orc.sample_row(D, rels, mu, Lambda, Z[i])
+    return out
+
+
+@pytest.mark.parametrize("D", [5, 32, 100])
+def test_entity_in_two_matrix_relations(D):
+    import bdf_b200
+
+    rng = np.random.default_rng(900 + D)
+    nA, nB, nC = 40, 23, 17
+    idsAB = np.stack([rng.integers(1, nA + 1, 600), rng.integers(1, nB + 1, 600)], 1).astype(np.int64)
+    idsAC = np.stack([rng.integers(1, nA + 1, 300), rng.integers(1, nC + 1, 300)], 1).astype(np.int64)
+    idsAB[idsAB[:, 0] == 3, 0] = 4   # row 3 of A has no AB observations
+    idsAC[idsAC[:, 0] == 3, 0] = 5   # ... and none in AC either: prior draw
+    idsAC[idsAC[:, 0] == 7, 0] = 8   # row 7: only AB
+    vAB, vAC = rng.standard_normal(600), rng.standard_normal(300) + 1.0
+    UA, UB, UC = (rng.standard_normal((n, D)) * 0.3 for n in (nA, nB, nC))
+    G = rng.standard_normal((D, D)) * 0.3
+    Lambda, mu = G @ G.T + 2.0 * np.eye(D), rng.standard_normal(D) * 0.1
+    eng = bdf_b200.Engine(D)
+    eA, eB, eC = eng.add_entity(nA), eng.add_entity(nB), eng.add_entity(nC)
+    rAB = eng.add_relation([eA, eB], idsAB, vAB)
+    rAC = eng.add_relation([eA, eC], idsAC, vAC)
+    eng.set_relation_params(rAB, 2.0, float(vAB.mean()))
+    eng.set_relation_params(rAC, 0.7, float(vAC.mean()))
+    for e, u in ((eA, UA), (eB, UB), (eC, UC)):
+        eng.set_factors(e, u)
+    Z = rng.standard_normal((nA, D))
+    eng.sample_mode(eA, mu, Lambda, Z)
+    got = eng.get_factors(eA)
+    want = oracle_rows(D, nA, [(idsAB, vAB, 0, [UB], 2.0, float(vAB.mean())), (idsAC, vAC, 0, [UC], 0.7, float(vAC.mean()))], mu, Lambda, Z)
+    assert rel_err(got, want) <= TOL
+    # B sits in one relation only and must be untouched by the merged path
+    ZB = rng.standard_normal((nB, D))
+    eng.set_factors(eA, UA)
+    eng.sample_mode(eB, mu, Lambda, ZB)
+    wantB = oracle_rows(D, nB, [(idsAB, vAB, 1, [UA], 2.0, float(vAB.mean()))], mu, Lambda, ZB)
+    assert rel_err(eng.get_factors(eB), wantB) <= TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("D", [10, 30])
+def test_entity_in_a_matrix_and_a_tensor_relation_with_a_long_row(D):
+    import bdf_b200
+
+    rng = np.random.default_rng(950 + D)
+    nA, nB, nC, nE = 12, 300, 9, 11
+    nAB = 30000
+    idsAB = np.stack([rng.integers(1, nA + 1, nAB), rng.integers(1, nB + 1, nAB)], 1).astype(np.int64)
+    idsAB[:20000, 0] = 2                                    # a row long enough to be chunked inside its relation
+    idsT = np.stack([rng.integers(1, nA + 1, 900), rng.integers(1, nC + 1, 900), rng.integers(1, nE + 1, 900)], 1).astype(np.int64)
+    vAB, vT = rng.standard_normal(nAB), rng.standard_normal(900)
+    UA, UB, UC, UE = (rng.standard_normal((n, D)) * 0.3 for n in (nA, nB, nC, nE))
+    G = rng.standard_normal((D, D)) * 0.3
+    Lambda, mu = G @ G.T + 2.0 * np.eye(D), rng.standard_normal(D) * 0.1
+    eng = bdf_b200.Engine(D)
+    eA, eB, eC, eE = (eng.add_entity(n) for n in (nA, nB, nC, nE))
+    rAB = eng.add_relation([eA, eB], idsAB, vAB)
+    rT = eng.add_relation([eC, eA, eE], idsT[:, [1, 0, 2]], vT)   # A is the middle mode of the tensor
+    eng.set_relation_params(rAB, 1.5, 0.1)
+    eng.set_relation_params(rT, 3.0, -0.2)
+    for e, u in ((eA, UA), (eB, UB), (eC, UC), (eE, UE)):
+        eng.set_factors(e, u)
+    Z = rng.standard_normal((nA, D))
+    eng.sample_mode(eA, mu, Lambda, Z)
+    got = eng.get_factors(eA)
+    want = oracle_rows(D, nA, [(idsAB, vAB, 0, [UB], 1.5, 0.1), (idsT[:, [1, 0, 2]], vT, 1, [UC, UE], 3.0, -0.2)], mu, Lambda, Z)
+    assert rel_err(got, want) <= TOL
+    # deterministic: the split partials are added in item order
+    eng.set_factors(eA, UA)
+    eng.sample_mode(eA, mu, Lambda, Z)
+    assert np.array_equal(got, eng.get_factors(eA))
+    eng.close()
