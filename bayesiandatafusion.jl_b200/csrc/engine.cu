@@ -313,6 +313,62 @@ void prep_lambda(bdf_t* h, const double* Lambda, const double* mu, int D, int DP
   prep_lambda_kernel<<<8, 256, 0, h->stream>>>(Lambda, mu, D, DP, LT, lmu);
 }
 
+
+// Training residuals for sample_alpha (src/macau.jl:85-87): one warp per work item of the relation's first mode (rows, long rows in
+// chunks), err = Σ_k Π_m U_m[k] + mean − value per observation, squared and summed per item; the per-item sums are then added in
+// item order by one block, so the result does not depend on scheduling.
+__global__ void sse_items_kernel(const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_beg, const int32_t* __restrict__ item_len,
+                                 int n_items, const int32_t* __restrict__ col0, const int32_t* __restrict__ col1, const double* __restrict__ val,
+                                 const double* __restrict__ U, const double* __restrict__ P0, const double* __restrict__ P1, int64_t slot_base, int ld,
+                                 int D, double mean, double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int item = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (item >= n_items) return;
+  const double* u = U + (size_t)(slot_base + item_row[item]) * ld;
+  const int64_t b = item_beg[item];
+  const int n = item_len[item];
+  double acc = 0.0;
+  for (int o = 0; o < n; o++) {
+    const double* p0 = P0 + (size_t)__ldg(col0 + b + o) * ld;
+    const double* p1 = P1 ? P1 + (size_t)__ldg(col1 + b + o) * ld : nullptr;
+    double s = 0.0;
+    for (int k = lane; k < D; k += 32) {
+      double t = u[k] * __ldg(p0 + k);
+      if (p1) t *= __ldg(p1 + k);
+      s += t;
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+    const double err = s + mean - __ldg(val + b + o);
+    acc = fma(err, err, acc);
+  }
+  if (lane == 0) partial[item] = acc;
+}
+
+// out[0] = Σ partial (fixed order: thread-strided sums, then a tree over the block), out[1] = optional alpha draw
+__global__ void sse_reduce_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// sample_alpha (src/sampling.jl:129-134): SW = inv(inv(lambda0) + err'err); alpha = rand(Wishart(nu0 + n, SW))[1] = SW·chi2(nu0 + n)
+__global__ void alpha_draw_kernel(double sse, double n, double lambda0, double nu0, double chi2_inj, uint64_t seed, uint64_t sweep, uint32_t stream,
+                                  double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double SW = 1.0 / (1.0 / lambda0 + sse);
+    const double c2 = chi2_inj == chi2_inj ? chi2_inj : 2.0 * gamma_mt(0.5 * (nu0 + n), seed, sweep, stream, 0);
+    out[0] = SW * c2;
+  }
+}
+
 }  // namespace
 
 // statistics of an arbitrary row-major (rows × ld) buffer into a [count, colsum(D), Gram(D×D)] stats block (features.cu uses it for betaᵀbeta)
@@ -847,6 +903,47 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
   cudaError_t ce2 = cudaStreamSynchronize(h->stream);
   if (ce != cudaSuccess || ce2 != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
   if (bad) FAIL(BDF_ERR_INVALID, "test id outside 1..count of its entity");
+  return BDF_OK;
+}
+
+int bdf_train_sse(bdf_t* h, int rel, double* sse, int64_t* count) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  if (!sse) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  RelationS& r = h->rels[rel];
+  ModeIndex& mi = r.modes[0];
+  EntityS& e = h->ents[r.entity_of_mode[0]];
+  int rc = bdf_ensure_arena(h, sizeof(double) * ((size_t)std::max(mi.n_items, 1) + 2));
+  if (rc) return rc;
+  double* part = reinterpret_cast<double*>(h->arena);
+  double* out = part + std::max(mi.n_items, 1);
+  if (mi.n_items > 0) {
+    const int wpb = 8;
+    sse_items_kernel<<<(mi.n_items + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(
+        mi.item_row, mi.item_beg, mi.item_len, mi.n_items, mi.col[0], mi.col[1], mi.val, e.U, h->ents[mi.other_entity[0]].U,
+        r.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr, (int64_t)h->rank * e.Nper, h->ld, h->D, r.mean, part);
+    CU(cudaGetLastError());
+  }
+  sse_reduce_kernel<<<1, 256, 0, h->stream>>>(part, mi.n_items, out);
+  h->launches += 2;
+  CU(cudaMemcpyAsync(sse, out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (count) *count = mi.nnz;
+  return BDF_OK;
+}
+
+int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, double sse, double count, double chi2_variate, double* alpha_out) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  if (!alpha_out || !(alpha_lambda0 > 0.0) || !(sse >= 0.0)) FAIL(BDF_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(h->device));
+  double* out = h->scratch;
+  alpha_draw_kernel<<<1, 32, 0, h->stream>>>(sse, count, alpha_lambda0, alpha_nu0, chi2_variate, h->seed, h->sweep, 0x400u + (uint32_t)rel, out);
+  h->launches++;
+  CU(cudaMemcpyAsync(alpha_out, out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->rels[rel].alpha = *alpha_out;
   return BDF_OK;
 }
 

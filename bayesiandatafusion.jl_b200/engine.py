@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -296,6 +297,19 @@ class Engine:
         n = C.c_int64()
         self._ck(self.lib.bdf_debug_phase_clocks(self.h, entity, _dp(out), C.byref(n)))
         return dict(zip(["setup", "syrk", "split", "build", "factor", "solve", "total"], out)), n.value
+
+    def train_sse(self, rel: int):
+        """err'err of src/macau.jl:86 over this rank's share of the training table; returns (sse, count)."""
+        sse = C.c_double()
+        n = C.c_int64()
+        self._ck(self.lib.bdf_train_sse(self.h, rel, C.byref(sse), C.byref(n)))
+        return sse.value, n.value
+
+    def sample_alpha(self, rel: int, alpha_lambda0: float, alpha_nu0: float, sse: float, count: float, chi2: float = math.nan) -> float:
+        """sample_alpha (src/sampling.jl:129-134); `chi2` is the injected chi-square(alpha_nu0 + n) variate, NaN → Philox."""
+        out = C.c_double()
+        self._ck(self.lib.bdf_sample_alpha(self.h, rel, alpha_lambda0, alpha_nu0, sse, float(count), chi2, C.byref(out)))
+        return out.value
 
     def predict(self, rel: int, ids):
         ids = np.asfortranarray(ids, dtype=np.int64)

@@ -72,11 +72,12 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
     are drawn on the host and injected, otherwise every draw uses the device Philox stream keyed by `seed`."""
     if backend != "cuda":
         raise ValueError('backend must be "cuda": this package is the CUDA engine; the Julia path lives in the reference')
-    if len(data.relations) != 1:
-        raise NotImplementedError("entities in several relations are not on the device path yet (SURVEY §8f N4)")
-    rel = data.relations[0]
-    if rel.model.alpha_sample:
-        raise NotImplementedError("alpha sampling is not on the device path yet (SURVEY §8f N3)")
+    if not data.relations:
+        raise ValueError("RelationData holds no relation")
+    for r in data.relations:
+        if r.hasFeatures():
+            raise NotImplementedError("relation-level features are not on the device path yet (SURVEY §8f N3)")
+    rel = data.relations[0]  # predictions / RMSE are reported for the first relation, as in src/macau.jl:142-143
     if verbose:
         print("Model setup")
     if reset_model:
@@ -86,10 +87,15 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
 
     eng = engine or Engine(D, device=device)
     eng.set_seed(seed)
-    ents = [eng.add_entity(en.count) for en in rel.entities]
-    r_id = eng.add_relation(ents, rel.data.ids, rel.data.values)
-    eng.set_relation_params(r_id, rel.model.alpha, rel.model.mean_value)
-    for e, en in zip(ents, rel.entities):
+    ents = [eng.add_entity(en.count) for en in data.entities]
+    eid = {id(en): e for e, en in zip(ents, data.entities)}
+    r_ids = []
+    for r in data.relations:
+        rid = eng.add_relation([eid[id(en)] for en in r.entities], r.data.ids, r.data.values)
+        eng.set_relation_params(rid, r.model.alpha, r.model.mean_value)
+        r_ids.append(rid)
+    r_id = r_ids[0]
+    for e, en in zip(ents, data.entities):
         if np.any(en.model.sample):
             eng.set_factors(e, en.model.sample)
         if en.hasFeatures():
@@ -110,8 +116,14 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
 
     for i in range(1, burnin + psamples + 1):
         time0 = time.time()
-        # Sampling latent vectors — src/macau.jl:96-134
-        for e, en in zip(ents, rel.entities):
+        # sample relation model (alpha) — src/macau.jl:84-88
+        for rid, r in zip(r_ids, data.relations):
+            if r.model.alpha_sample:
+                sse, n = eng.train_sse(rid)
+                c2 = host_noise.chisquare(r.model.alpha_nu0 + n) if host_noise is not None else math.nan
+                r.model.alpha = eng.sample_alpha(rid, r.model.alpha_lambda0, r.model.alpha_nu0, sse, n, c2)
+        # Sampling latent vectors — src/macau.jl:96-134 (entities in several relations: sample_user2_all!, :109-118)
+        for e, en in zip(ents, data.entities):
             mj = en.model
             if en.hasFeatures():
                 eng.update_uhat(e, mj.mu)               # uhat = (F·beta)', mu_matrix = mu .+ uhat, on the device (:102-104)
@@ -133,7 +145,7 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             else:
                 mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu)
         # update_beta! — src/macau.jl:138-140, src/sampling.jl:361-370
-        for e, en in zip(ents, rel.entities):
+        for e, en in zip(ents, data.entities):
             if en.hasFeatures():
                 eng.sample_beta(e, en.model.mu, en.model.Lambda, en.lambda_beta, tol_arg)
                 if en.lambda_beta_sample:
@@ -146,7 +158,7 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         probe_rat = eng.predict(r_id, rel.test_ids) if ntest else np.zeros(0)
         if i > burnin:
             if output:
-                for e, en in zip(ents, rel.entities):
+                for e, en in zip(ents, data.entities):
                     ndigits = int(math.floor(math.log10(psamples))) + 1
                     nstr = str(i - burnin).rjust(ndigits, "0")
                     write_binary_matrix(f"{output}-{en.name}-{nstr}.binary", eng.get_factors(e).astype(np.float32))
@@ -175,17 +187,17 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             roc_avg = AUC_ROC(rel.test_label, -probe_rat_all)
         if verbose:
             print(f"{i:3d}: ROC={roc_avg:6.4f} RMSE={rmse_avg:6.4f} | " +
-                  " ".join(f"{en.name[:3]}[mu:{np.linalg.norm(en.model.mu):6.2f}]" for en in rel.entities) +
-                  f" | {rel.name[:4]}[a={rel.model.alpha:2.1f}] [{time1 - time0:1.1f}s]")
+                  " ".join(f"{en.name[:3]}[mu:{np.linalg.norm(en.model.mu):6.2f}]" for en in data.entities) + " | " +
+                  " ".join(f"{r.name[:4]}[a={r.model.alpha:2.1f}]" for r in data.relations) + f" [{time1 - time0:1.1f}s]")
 
     # the device holds the state during the run; hand the final sample back to the host model (model.sample)
-    for e, en in zip(ents, rel.entities):
+    for e, en in zip(ents, data.entities):
         en.model.sample = eng.get_factors(e)
         if en.hasFeatures():
             en.model.beta = eng.get_beta(e)
 
     result = {
-        "num_latent": num_latent, "burnin": burnin, "psamples": psamples, "lambda_beta": rel.entities[0].lambda_beta,
+        "num_latent": num_latent, "burnin": burnin, "psamples": psamples, "lambda_beta": data.entities[0].lambda_beta,
         "RMSE": rmse_avg, "accuracy": err_avg, "ROC": roc_avg, "latent_multi_threading": True,
     }
     if ntest > 0:

@@ -217,6 +217,22 @@ class RelationData:
             self.entities.append(en)
         self.relations.append(r)
 
+    def addRelation(self, r: Relation):
+        """addRelation! — src/RelationData.jl:387-409."""
+        if len(r.data.dims) != len(r.entities):
+            raise ValueError(f"Relation has {len(r.entities)} entities but its data implies {tuple(r.data.dims)}.")
+        self.relations.append(r)
+        for i, en in enumerate(r.entities):
+            if en.count == 0:
+                en.count = r.data.dims[i]
+            elif en.count != r.data.dims[i]:
+                raise ValueError(f"Entity {en.name} has {en.count} instances, relation {r.name} has data for {r.data.dims[i]}.")
+            if not any(e is en for e in self.entities):
+                self.entities.append(en)
+            if not any(x is r for x in en.relations):
+                en.relations.append(r)
+        return None
+
     def reset(self, num_latent: int, lambda_beta=math.nan, compute_ff_size=6500):
         """reset! — src/RelationData.jl:331-355."""
         for en in self.entities:

@@ -119,6 +119,13 @@ int64_t bdf_launch_count(const bdf_t* h);
  * + mean_value. ids: ntest×K column-major, 1-based. */
 int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yhat);
 
+/* sample_alpha — src/macau.jl:84-88, src/sampling.jl:129-134. bdf_train_sse: err'err with err = pred(r) - getValues(r.data) over the
+ * training observations whose first-mode row this rank owns (count = their number; all-reduce both across ranks).
+ * bdf_sample_alpha: alpha = rand(Wishart(alpha_nu0 + n, inv(inv(alpha_lambda0) + err'err)))[1] = SW·chi2(alpha_nu0 + n); chi2_variate is
+ * the injected chi-square draw behind the 1×1 Wishart (NaN → Philox). Stores the draw as the relation's alpha. */
+int bdf_train_sse(bdf_t* h, int rel, double* sse, int64_t* count);
+int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, double sse, double count, double chi2_variate, double* alpha_out);
+
 /* ---- Macau side features: the link-matrix (beta) path ------------------------------------------------------------- */
 
 /* Entity(F = SparseBinMatrix(m, n, rows, cols)) — src/parallel_matrix.jl:9-24: registers a sparse 0/1 feature matrix given

@@ -233,6 +233,15 @@ def bartlett_factor(rng: np.random.Generator, D: int, nu: float):
     return A
 
 
+def sample_alpha(alpha_lambda0: float, alpha_nu0: float, err, chi2: float) -> float:
+    """sample_alpha — src/sampling.jl:129-134: Λ = alpha_lambda0·eye(1); SW = inv(inv(Λ) + err'err);
+    rand(Wishart(alpha_nu0 + n, SW))[1]. A 1×1 Wishart(ν, S) draw is S·chi2(ν) (Bartlett with a single diagonal entry
+    [ext]); `chi2` is that injected variate."""
+    err = np.asarray(err, dtype=np.float64)
+    SW = 1.0 / (1.0 / alpha_lambda0 + float(err @ err))
+    return SW * chi2
+
+
 # ----------------------------------------------------------------------------------------------
 # sparse binary operators, CG, β
 # ----------------------------------------------------------------------------------------------

@@ -96,3 +96,68 @@ def test_entity_in_a_matrix_and_a_tensor_relation_with_a_long_row(D):
     eng.sample_mode(eA, mu, Lambda, Z)
     assert np.array_equal(got, eng.get_factors(eA))
     eng.close()
+
+
+def test_train_sse_and_alpha_draw_match_oracle():
+    """sample_alpha (src/macau.jl:84-88, src/sampling.jl:129-134) with the chi-square variate injected."""
+    import bdf_b200
+
+    rng = np.random.default_rng(77)
+    for dims, D in (([50, 30], 10), ([20, 9, 6], 30)):
+        nnz = 3000
+        ids = np.stack([rng.integers(1, d + 1, nnz) for d in dims], 1).astype(np.int64)
+        ids[:2500, 0] = 7  # one long row
+        vals = rng.standard_normal(nnz) + 0.5
+        U = [rng.standard_normal((d, D)) * 0.4 for d in dims]
+        eng = bdf_b200.Engine(D)
+        ents = [eng.add_entity(d) for d in dims]
+        rel = eng.add_relation(ents, ids, vals)
+        mean = float(vals.mean())
+        eng.set_relation_params(rel, 2.0, mean)
+        for e, u in zip(ents, U):
+            eng.set_factors(e, u)
+        err = orc.pred(ids, U, mean) - vals
+        sse, n = eng.train_sse(rel)
+        assert n == nnz
+        assert abs(sse - float(err @ err)) <= 1e-11 * float(err @ err)
+        chi2 = float(rng.chisquare(2.0 + nnz))
+        got = eng.sample_alpha(rel, 1.0, 2.0, sse, n, chi2)
+        want = orc.sample_alpha(1.0, 2.0, err, chi2)
+        assert abs(got - want) <= 1e-11 * want
+        # Philox draw: alpha concentrates around n / sse
+        draws = []
+        for _ in range(50):
+            draws.append(eng.sample_alpha(rel, 1.0, 2.0, sse, n))
+            eng.advance_sweep()
+        assert abs(np.mean(draws) / ((2.0 + nnz) / (1.0 + sse)) - 1.0) < 0.02 and np.std(draws) > 0
+        eng.close()
+
+
+def test_macau_with_two_relations_and_alpha_sampling():
+    """Driver level: an entity shared by two relations (docs/index.md:200-233 pattern) with alpha sampled."""
+    import bdf_b200
+    from bdf_b200.relation_data import Entity, IndexedDF, Relation, assignToTest
+
+    rng = np.random.default_rng(5)
+    nA, nB, nC, D0 = 120, 60, 40, 3
+    A, B, Cm = (rng.standard_normal((n, D0)) for n in (nA, nB, nC))
+
+    def table(X, Y, nnz, noise):
+        i = np.stack([rng.integers(1, X.shape[0] + 1, nnz), rng.integers(1, Y.shape[0] + 1, nnz)], 1).astype(np.int64)
+        v = np.einsum("ij,ij->i", X[i[:, 0] - 1], Y[i[:, 1] - 1]) + noise * rng.standard_normal(nnz)
+        return IndexedDF(i, v, [X.shape[0], Y.shape[0]])
+
+    a, b, c = Entity("a"), Entity("b"), Entity("c")
+    r1 = Relation(table(A, B, 4000, 0.3), "ab", [a, b], class_cut=0.0, alpha=1.0)
+    r2 = Relation(table(A, Cm, 3000, 0.3), "ac", [a, c], class_cut=0.0, alpha=1.0)
+    r1.model.alpha_sample = True
+    r2.model.alpha_sample = True
+    assignToTest(r1, 400, rng)
+    rd = bdf_b200.RelationData()
+    rd.addRelation(r1)
+    rd.addRelation(r2)
+    res = bdf_b200.macau(rd, num_latent=6, burnin=30, psamples=30, verbose=False, seed=3)
+    base = float(np.sqrt(np.mean((r1.test_values - r1.data.values.mean()) ** 2)))
+    assert np.isfinite(res["RMSE"]) and res["RMSE"] < 0.45 * base
+    # the sampled precisions settle near the planted noise level 1/0.3^2 ≈ 11
+    assert 6.0 < r1.model.alpha < 18.0 and 6.0 < r2.model.alpha < 18.0

@@ -93,11 +93,27 @@ def test_auc_clamp_and_binary_io():
 
 def test_macau_rejects_what_is_not_on_the_device_path():
     Y = sp.random(15, 10, 0.3, random_state=1, format="csc")
-    rd = bdf_b200.RelationData(Y, alpha_sample=True)
-    with pytest.raises(NotImplementedError):
-        bdf_b200.macau(rd, burnin=1, psamples=1, verbose=False)
     with pytest.raises(ValueError):
         bdf_b200.macau(bdf_b200.RelationData(Y), backend="julia")
+    with pytest.raises(ValueError):
+        bdf_b200.macau(bdf_b200.RelationData(), burnin=1, psamples=1, verbose=False)
+
+
+def test_add_relation_shares_entities():
+    """addRelation! — src/RelationData.jl:387-409: entities are shared by identity, counts must agree."""
+    from bdf_b200.relation_data import Entity, IndexedDF, Relation
+
+    a, b, c = Entity("a"), Entity("b"), Entity("c")
+    r1 = Relation(IndexedDF(np.array([[1, 1], [4, 3]]), np.array([1.0, 2.0]), [4, 3]), "ab", [a, b])
+    r2 = Relation(IndexedDF(np.array([[2, 5], [4, 1]]), np.array([0.5, 1.5]), [4, 5]), "ac", [a, c])
+    rd = bdf_b200.RelationData()
+    rd.addRelation(r1)
+    rd.addRelation(r2)
+    assert [e.name for e in rd.entities] == ["a", "b", "c"] and len(a.relations) == 2 and a.count == 4
+    rd.reset(3)
+    assert a.modes == [1, 1] and a.modes_other == [[2], [2]] and c.modes == [2]
+    with pytest.raises(ValueError):  # entity a has 4 instances, this table has ids up to 6
+        rd.addRelation(Relation(IndexedDF(np.array([[6, 1]]), np.array([1.0]), [6, 3]), "ad", [a, Entity("d")]))
 
 
 def test_shard_plan_is_the_reference_cyclic_split():
