@@ -30,6 +30,10 @@ SIGNATURES = {
     "bdf_factors_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), c_i64p, c_i64p]),
     "bdf_ipc_export": (C.c_int, [H, C.c_int, C.c_char_p]),
     "bdf_ipc_import": (C.c_int, [H, C.c_int, C.c_int, C.c_char_p]),
+    "bdf_set_features_dense": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, c_dp]),
+    "bdf_compute_ff": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_set_use_ff": (C.c_int, [H, C.c_int, C.c_int]),
+    "bdf_solve_full": (C.c_int, [H, C.c_int, c_dp, C.c_int, C.c_double, c_dp]),
     "bdf_train_sse": (C.c_int, [H, C.c_int, c_dp, c_i64p]),
     "bdf_sample_alpha": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_dp]),
     "bdf_sample_mode": (C.c_int, [H, C.c_int, c_dp, C.c_int64, c_dp, c_dp]),

@@ -70,7 +70,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
                 if ptxas_v:
                     print(log)
     objs = [os.path.join(OBJ, "engine.o"), os.path.join(OBJ, "features.o")] + [os.path.join(OBJ, f"row_inst_{dp}.o") for dp in DPS]
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
+           "-lcublas", "-lcusolver", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]  # dense features / FF direct solve (A9) are library calls
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed: {r.stdout}\n{r.stderr}")

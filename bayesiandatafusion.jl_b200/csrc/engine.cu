@@ -390,6 +390,7 @@ int bdf_ensure_arena(bdf_t* h, size_t bytes) {
   return BDF_OK;
 }
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
+void bdf_dense_teardown(bdf_t* h);
 
 namespace {
 
@@ -474,12 +475,13 @@ int bdf_destroy(bdf_t* h) {
   if (!h) return BDF_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  bdf_dense_teardown(h);
   for (auto& e : h->ents) {
     for (int r = 0; r < 8; r++) if (e.peerU[r]) cudaIpcCloseMemHandle(e.peerU[r]);
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
     cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
     cudaFree(e.sp_items[0]); cudaFree(e.sp_items[1]); cudaFree(e.sp_long[0]); cudaFree(e.sp_long[1]); cudaFree(e.sp_part);
-    cudaFree(e.f_val_csr); cudaFree(e.f_val_csc);
+    cudaFree(e.f_val_csr); cudaFree(e.f_val_csc); cudaFree(e.f_dense); cudaFree(e.FF);
     free_work_list(e.merged);
   }
   for (auto& r : h->rels)

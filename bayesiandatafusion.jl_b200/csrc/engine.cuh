@@ -64,6 +64,9 @@ struct EntityS {
   int32_t* f_rowind = nullptr;  // [fnnz]  0-based row ids, stored order = stable sort of the COO list by column
   double* f_val_csr = nullptr;  // [fnnz] stored values in CSR order (general sparse F) or nullptr (0/1 matrix)
   double* f_val_csc = nullptr;  // [fnnz] the same in CSC order
+  double* f_dense = nullptr;    // dense feature matrix (N × numF, column-major) when F was registered with bdf_set_features_dense
+  double* FF = nullptr;         // full(FᵀF), numF × numF column-major (src/RelationData.jl:337-339), when the direct solve is in use
+  bool use_ff = false;
   double* beta = nullptr;       // numF × ld
   double* uhat = nullptr;       // slots × ld, (F·beta)
   double* cgbuf = nullptr;      // CG work vectors
@@ -113,6 +116,8 @@ struct bdf_handle {
   double* ones = nullptr;  // a row of ones (ld doubles, zero padding): the second partner of a 2-mode relation inside a 3-mode launch
   int num_sms = 148;
   double* lt = nullptr;  // Λ in tile order + Λ·μ, rebuilt per half-sweep
+  void* cublas = nullptr;    // cublasHandle_t / cusolverDnHandle_t of the dense-feature and FF direct-solve paths (created on first use)
+  void* cusolver = nullptr;
   char* arena = nullptr;  // grow-only staging for host-facing calls (predict ids/slots/output, beta sampler temporaries)
   size_t arena_bytes = 0;
   int64_t pst = 0;  // doubles per parked partial for this D

@@ -9,6 +9,8 @@
 // A 0/1 matrix needs no multiplies: both products are gathers of D-vectors summed in stored order (the reference's
 // order), one warp per output row, indices read 128 bits at a time, the D columns spread over the lanes.
 #include <cub/cub.cuh>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -395,12 +397,73 @@ int build_orientation(bdf_t* h, const int32_t* d_key, const int32_t* d_other, in
   return BDF_OK;
 }
 
+// ---- dense feature matrices and the FF direct solve (A9: solve_full, src/sampling.jl:314-320; FF = full(FᵀF), src/RelationData.jl:337-339)
+// Plain library calls: cuBLAS dgemm for F·X / Fᵀ·X / FᵀF with a dense F, cuSOLVER potrf/potrs for (FF + λI)·β = rhs.
+int dense_handles(bdf_t* h) {
+  if (!h->cublas) {
+    cublasHandle_t cb = nullptr;
+    if (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cublasCreate failed");
+    h->cublas = cb;
+  }
+  if (!h->cusolver) {
+    cusolverDnHandle_t cs = nullptr;
+    if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnCreate failed");
+    h->cusolver = cs;
+  }
+  cublasSetStream((cublasHandle_t)h->cublas, h->stream);
+  cusolverDnSetStream((cusolverDnHandle_t)h->cusolver, h->stream);
+  return BDF_OK;
+}
+
+__global__ void identity_block_kernel(double* __restrict__ X, int64_t rows, int ld, int64_t c0, int ncol) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * ld; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / ld;
+    const int c = (int)(e % ld);
+    X[e] = (c < ncol && r == c0 + c) ? 1.0 : 0.0;
+  }
+}
+// FF[:, c0 + c] = Y[:, c] for c < ncol (Y row-major rows × ld, FF column-major rows × rows)
+__global__ void scatter_ff_kernel(const double* __restrict__ Y, int64_t rows, int ld, int64_t c0, int ncol, double* __restrict__ FF) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * ncol; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % rows;
+    const int c = (int)(e / rows);
+    FF[r + (size_t)(c0 + c) * rows] = Y[(size_t)r * ld + c];
+  }
+}
+__global__ void add_diag_kernel(double* __restrict__ A, int64_t n, double lam) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) A[i + (size_t)i * n] += lam;
+}
+
+// Y = F·X (transpose == false, X numF × ld → Y N × ld) or Y = Fᵀ·X (+ lam·P) for a dense column-major F; all operands row-major with
+// pitch ld, i.e. column-major ld × rows, so both products are one dgemm on the transposed problem.
+int dense_mm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam, const double* P) {
+  int rc = dense_handles(h);
+  if (rc) return rc;
+  cublasHandle_t cb = (cublasHandle_t)h->cublas;
+  const double one = 1.0, zero = 0.0;
+  const int ld = h->ld;
+  cublasStatus_t st;
+  if (!transpose) {
+    // Yᵀ (ld × N) = Xᵀ (ld × numF) · Fᵀ (numF × N)
+    st = cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, ld, (int)e.N, (int)e.numF, &one, X, ld, e.f_dense, (int)e.N, &zero, Y, ld);
+  } else {
+    if (P && lam != 0.0) CU(cudaMemcpyAsync(Y, P, sizeof(double) * (size_t)e.numF * ld, cudaMemcpyDeviceToDevice, h->stream));
+    const double beta = (P && lam != 0.0) ? lam : 0.0;
+    // Yᵀ (ld × numF) = Xᵀ (ld × N) · F (N × numF)
+    st = cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, ld, (int)e.numF, (int)e.N, &one, X, ld, e.f_dense, (int)e.N, &beta, Y, ld);
+  }
+  h->launches++;
+  if (st != CUBLAS_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cublasDgemm failed");
+  return BDF_OK;
+}
+
 int need_features(bdf_t* h, int entity) {
-  if (h->ents[entity].numF <= 0) FAIL(BDF_ERR_STATE, "entity has no feature matrix (bdf_set_features_sbm)");
+  if (h->ents[entity].numF <= 0) FAIL(BDF_ERR_STATE, "entity has no feature matrix (bdf_set_features_sbm / _csc / _dense)");
   return BDF_OK;
 }
 
 int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr) {
+  if (e.f_dense) return dense_mm(h, e, transpose, X, Y, lam, P);
   const int o = transpose ? 1 : 0;
   const SpItem* items = reinterpret_cast<const SpItem*>(e.sp_items[o]);
   const int ni = e.sp_nitems[o];
@@ -538,25 +601,23 @@ int download_colmajor(bdf_t* h, const double* dev_rm, int64_t rows, int ncol, do
 }  // namespace
 
 // =====================================================================================================================
-static int set_features_dev(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, int32_t* d_rows, int32_t* d_cols, const double* d_val) {
-  EntityS& e = h->ents[entity];
+static void free_feature_state(EntityS& e) {
   cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
-  cudaFree(e.f_val_csr); cudaFree(e.f_val_csc);
+  cudaFree(e.f_val_csr); cudaFree(e.f_val_csc); cudaFree(e.f_dense); cudaFree(e.FF);
   e.f_rowptr = e.f_colptr = nullptr; e.f_colind = e.f_rowind = nullptr; e.beta = e.uhat = e.cgbuf = e.btb = nullptr; e.f_val_csr = e.f_val_csc = nullptr;
-  e.numF = 0;
-  int rc = build_orientation(h, d_rows, d_cols, nnz, m, (int32_t)n, &e.f_rowptr, &e.f_colind, d_val, &e.f_val_csr);
-  if (!rc) rc = build_orientation(h, d_cols, d_rows, nnz, n, (int32_t)m, &e.f_colptr, &e.f_rowind, d_val, &e.f_val_csc);
-  if (rc) return rc;
-  {
-    int64_t slots = 0;
-    for (int o = 0; o < 2; o++) { cudaFree(e.sp_items[o]); cudaFree(e.sp_long[o]); e.sp_items[o] = e.sp_long[o] = nullptr; }
-    cudaFree(e.sp_part); e.sp_part = nullptr;
-    if ((rc = build_sp_items(h, e, 0, e.f_rowptr, m, &slots)) || (rc = build_sp_items(h, e, 1, e.f_colptr, n, &slots))) return rc;
-    CU(cudaMalloc(&e.sp_part, std::max<size_t>((size_t)slots * h->ld, 1) * sizeof(double)));
-  }
+  e.f_dense = e.FF = nullptr;
+  e.use_ff = false;
+  for (int o = 0; o < 2; o++) { cudaFree(e.sp_items[o]); cudaFree(e.sp_long[o]); e.sp_items[o] = e.sp_long[o] = nullptr; e.sp_nitems[o] = e.sp_nlong[o] = 0; }
+  cudaFree(e.sp_part); e.sp_part = nullptr;
+  e.numF = 0; e.fnnz = 0;
+}
+
+// beta = zeros(numF, num_latent) (src/RelationData.jl:76), uhat, the betaᵀbeta statistics block, the per-row mean buffer
+static int alloc_feature_state(bdf_t* h, EntityS& e, int64_t n, int64_t nnz) {
+  int rc;
   const size_t bn = (size_t)n * h->ld, un = (size_t)e.Nper * h->world * h->ld;
   if ((rc = dalloc(h, &e.beta, bn)) || (rc = dalloc(h, &e.uhat, un)) || (rc = dalloc(h, &e.btb, (size_t)1 + h->D + (size_t)h->D * h->D))) return rc;
-  CU(cudaMemsetAsync(e.beta, 0, bn * 8, h->stream));   // beta = zeros(numF, num_latent), src/RelationData.jl:76
+  CU(cudaMemsetAsync(e.beta, 0, bn * 8, h->stream));
   CU(cudaMemsetAsync(e.uhat, 0, un * 8, h->stream));
   if (!e.mu_rows) { if ((rc = dalloc(h, &e.mu_rows, un))) return rc; CU(cudaMemsetAsync(e.mu_rows, 0, un * 8, h->stream)); }
   e.numF = n; e.fnnz = nnz;
@@ -564,6 +625,143 @@ static int set_features_dev(bdf_t* h, int entity, int64_t m, int64_t n, int64_t 
   if (h->ws_bytes < need) FAIL(BDF_ERR_STATE, "workspace too small");
   CU(cudaStreamSynchronize(h->stream));
   return BDF_OK;
+}
+
+static int set_features_dev(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, int32_t* d_rows, int32_t* d_cols, const double* d_val) {
+  EntityS& e = h->ents[entity];
+  free_feature_state(e);
+  int rc = build_orientation(h, d_rows, d_cols, nnz, m, (int32_t)n, &e.f_rowptr, &e.f_colind, d_val, &e.f_val_csr);
+  if (!rc) rc = build_orientation(h, d_cols, d_rows, nnz, n, (int32_t)m, &e.f_colptr, &e.f_rowind, d_val, &e.f_val_csc);
+  if (rc) return rc;
+  {
+    int64_t slots = 0;
+    if ((rc = build_sp_items(h, e, 0, e.f_rowptr, m, &slots)) || (rc = build_sp_items(h, e, 1, e.f_colptr, n, &slots))) return rc;
+    CU(cudaMalloc(&e.sp_part, std::max<size_t>((size_t)slots * h->ld, 1) * sizeof(double)));
+  }
+  return alloc_feature_state(h, e, n, nnz);
+}
+
+void bdf_dense_teardown(bdf_t* h) {
+  if (h->cublas) cublasDestroy((cublasHandle_t)h->cublas);
+  if (h->cusolver) cusolverDnDestroy((cusolverDnHandle_t)h->cusolver);
+  h->cublas = h->cusolver = nullptr;
+}
+
+// FF = full(At_mul_B(F, F)) (src/RelationData.jl:337-339). Sparse F: num_latent columns of the identity at a time through the two
+// gather products (exact integer counts for a 0/1 matrix); dense F: one dgemm.
+static int compute_ff_dev(bdf_t* h, EntityS& e) {
+  int rc;
+  const int64_t n = e.numF;
+  if (!e.FF && (rc = dalloc(h, &e.FF, (size_t)n * n))) return rc;
+  if (e.f_dense) {
+    if ((rc = dense_handles(h))) return rc;
+    const double one = 1.0, zero = 0.0;
+    if (cublasDgemm((cublasHandle_t)h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)n, (int)n, (int)e.N, &one, e.f_dense, (int)e.N, e.f_dense, (int)e.N, &zero, e.FF, (int)n) !=
+        CUBLAS_STATUS_SUCCESS)
+      FAIL(BDF_ERR_CUDA, "cublasDgemm failed");
+    h->launches++;
+  } else {
+    double *X = nullptr, *T = nullptr, *Y = nullptr;
+    if ((rc = dalloc(h, &X, (size_t)n * h->ld)) || (rc = dalloc(h, &T, (size_t)e.N * h->ld)) || (rc = dalloc(h, &Y, (size_t)n * h->ld))) { cudaFree(X); cudaFree(T); return rc; }
+    for (int64_t c0 = 0; c0 < n; c0 += h->D) {
+      const int nc = (int)std::min<int64_t>(h->D, n - c0);
+      identity_block_kernel<<<grid_for(n * h->ld), 256, 0, h->stream>>>(X, n, h->ld, c0, nc);
+      spmm(h, e, false, X, T);
+      spmm(h, e, true, T, Y);
+      scatter_ff_kernel<<<grid_for(n * nc), 256, 0, h->stream>>>(Y, n, h->ld, c0, nc, e.FF);
+      h->launches += 2;
+    }
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    cudaFree(X); cudaFree(T); cudaFree(Y);
+    if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  e.use_ff = true;
+  return BDF_OK;
+}
+
+// solve_full(FF, rhs, lambda) — src/sampling.jl:314-320: (FF + λI) \ rhs for num_latent right-hand sides; B and X row-major numF × ld.
+// The regularised matrix is symmetric positive definite, so the factorisation is a Cholesky (cuSOLVER potrf/potrs).
+static int solve_full_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda) {
+  int rc = dense_handles(h);
+  if (rc) return rc;
+  if (!e.FF) FAIL(BDF_ERR_STATE, "FF has not been computed (bdf_compute_ff)");
+  cusolverDnHandle_t cs = (cusolverDnHandle_t)h->cusolver;
+  const int n = (int)e.numF, D = h->D;
+  int lwork = 0;
+  if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, n, e.FF, n, &lwork) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+  double *A = nullptr, *Bc = nullptr, *work = nullptr;
+  int* info = nullptr;
+  auto cleanup = [&]() { cudaFree(A); cudaFree(Bc); cudaFree(work); cudaFree(info); };
+  if ((rc = dalloc(h, &A, (size_t)n * n)) || (rc = dalloc(h, &Bc, (size_t)n * D)) || (rc = dalloc(h, &work, (size_t)std::max(lwork, 1))) || (rc = dalloc(h, &info, 1))) { cleanup(); return rc; }
+  cudaMemcpyAsync(A, e.FF, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, h->stream);
+  add_diag_kernel<<<grid_for(n), 256, 0, h->stream>>>(A, n, lambda);
+  to_colmajor_kernel<<<grid_for((int64_t)n * D), 256, 0, h->stream>>>(B, n, D, h->ld, Bc);
+  int hinfo[2] = {0, 0};
+  cusolverStatus_t s1 = cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, n, A, n, work, lwork, info);
+  cudaMemcpyAsync(&hinfo[0], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cusolverStatus_t s2 = cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, n, D, A, n, Bc, n, info);
+  cudaMemcpyAsync(&hinfo[1], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  to_rowmajor_kernel<<<grid_for((int64_t)n * h->ld), 256, 0, h->stream>>>(Bc, n, D, h->ld, X);
+  h->launches += 5;
+  cudaError_t ce = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  if (s1 != CUSOLVER_STATUS_SUCCESS || s2 != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cuSOLVER potrf/potrs failed");
+  if (hinfo[0] != 0 || hinfo[1] != 0) FAIL(BDF_ERR_NUMERIC, "solve_full: FF + lambda*I is not positive definite");
+  return BDF_OK;
+}
+
+extern "C" int bdf_set_features_dense(bdf_t* h, int entity, int64_t m, int64_t n, const double* F) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!F || m < 1 || n < 1) FAIL(BDF_ERR_INVALID, "null or empty feature matrix");
+  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this version");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if (m != e.N) FAIL(BDF_ERR_INVALID, "Number of rows in the feature matrix must equal the entity count");
+  if (m >= 2147483647LL || n >= 2147483647LL) FAIL(BDF_ERR_INVALID, "feature matrix too large");
+  free_feature_state(e);
+  int rc;
+  if ((rc = dalloc(h, &e.f_dense, (size_t)m * n))) return rc;
+  CU(cudaMemcpyAsync(e.f_dense, F, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice, h->stream));
+  return alloc_feature_state(h, e, n, m * n);
+}
+
+extern "C" int bdf_compute_ff(bdf_t* h, int entity, double* FF_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if ((rc = compute_ff_dev(h, e))) return rc;
+  if (FF_out) CU(cudaMemcpyAsync(FF_out, e.FF, sizeof(double) * (size_t)e.numF * e.numF, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+extern "C" int bdf_set_use_ff(bdf_t* h, int entity, int use_ff) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  EntityS& e = h->ents[entity];
+  if (use_ff && !e.FF) FAIL(BDF_ERR_STATE, "FF has not been computed (bdf_compute_ff)");
+  e.use_ff = use_ff != 0;
+  return BDF_OK;
+}
+
+extern "C" int bdf_solve_full(bdf_t* h, int entity, const double* rhs, int ncol, double lambda, double* x) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!rhs || !x || ncol != h->D) FAIL(BDF_ERR_INVALID, "DimensionMismatch: rhs must have num_latent columns");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  double *db = nullptr, *dx = nullptr;
+  if ((rc = dalloc(h, &db, (size_t)e.numF * h->ld)) || (rc = dalloc(h, &dx, (size_t)e.numF * h->ld))) { cudaFree(db); return rc; }
+  rc = upload_rowmajor(h, rhs, e.numF, ncol, db);
+  if (!rc) rc = solve_full_dev(h, e, db, dx, lambda);
+  if (!rc) rc = download_colmajor(h, dx, e.numF, ncol, x);
+  cudaFree(db); cudaFree(dx);
+  return rc;
 }
 
 extern "C" int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols) {
@@ -630,6 +828,7 @@ int bdf_debug_features_csr(bdf_t* h, int entity, int transpose, int32_t* ptr_out
   if (rc) return rc;
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
+  if (e.f_dense) FAIL(BDF_ERR_STATE, "the feature matrix is dense: no CSR representation");
   const int64_t nk = transpose ? e.numF : e.N;
   std::vector<int64_t> p((size_t)nk + 1);
   std::vector<int32_t> ind((size_t)std::max<int64_t>(e.fnnz, 1));
@@ -814,7 +1013,12 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   h->launches += 3;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { cleanup(); FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce)); }
-  rc = cg_solve_dev(h, e, rhs, e.beta, lambda_beta, tol, e.numF, iters_out);
+  if (e.use_ff) {  // use_ff: solve_full(entity.FF, Ft_y, lambda_beta), src/sampling.jl:303-304
+    rc = solve_full_dev(h, e, rhs, e.beta, lambda_beta);
+    if (iters_out) for (int d = 0; d < D; d++) iters_out[d] = 0;
+  } else {
+    rc = cg_solve_dev(h, e, rhs, e.beta, lambda_beta, tol, e.numF, iters_out);
+  }
   if (!rc && beta_out) rc = download_colmajor(h, e.beta, e.numF, D, beta_out);
   if (!rc && rhs_out) rc = download_colmajor(h, rhs, e.numF, D, rhs_out);
   if (!rc) rc = bdf_check_err_flag(h); else cudaStreamSynchronize(h->stream);

@@ -185,6 +185,14 @@ class Engine:
     # -- Macau side features ------------------------------------------------------------------------------
     def set_features(self, entity: int, F):
         """F: a SparseBinMatrix-like object with .rows/.cols (1-based Int32) and .shape, or a scipy.sparse 0/1 matrix."""
+        if isinstance(F, np.ndarray):
+            # dense feature matrix (Julia Matrix{Float64}): column-major on the device, products by cuBLAS
+            Fd = np.asfortranarray(F, dtype=np.float64)
+            m, n = Fd.shape
+            self._ck(self.lib.bdf_set_features_dense(self.h, entity, m, n, _dp(Fd)))
+            self.numF = getattr(self, "numF", {})
+            self.numF[entity] = int(n)
+            return
         if hasattr(F, "rows") and hasattr(F, "cols"):
             rows, cols, (m, n) = F.rows, F.cols, F.shape
         else:
@@ -209,6 +217,23 @@ class Engine:
         self._ck(self.lib.bdf_set_features_sbm(self.h, entity, m, n, len(rows), rows.ctypes.data_as(_lib.c_i32p), cols.ctypes.data_as(_lib.c_i32p)))
         self.numF = getattr(self, "numF", {})
         self.numF[entity] = int(n)
+
+    def compute_ff(self, entity: int, want: bool = False):
+        """en.FF = full(At_mul_B(en.F, en.F)), en.use_FF = true (src/RelationData.jl:337-339); returns FF when `want`."""
+        n = self.numF[entity]
+        out = np.zeros((n, n), order="F") if want else None
+        self._ck(self.lib.bdf_compute_ff(self.h, entity, _dp(out) if want else None))
+        return out
+
+    def set_use_ff(self, entity: int, use_ff: bool):
+        self._ck(self.lib.bdf_set_use_ff(self.h, entity, int(bool(use_ff))))
+
+    def solve_full(self, entity: int, rhs, lam: float):
+        """solve_full(FF, rhs, lambda) — src/sampling.jl:314-320. rhs: (numF, num_latent)."""
+        rhs = np.asfortranarray(rhs, dtype=np.float64)
+        x = np.zeros_like(rhs, order="F")
+        self._ck(self.lib.bdf_solve_full(self.h, entity, _dp(rhs), rhs.shape[1], float(lam), _dp(x)))
+        return x
 
     def debug_features_csr(self, entity: int, transpose: bool, nnz: int):
         nk = self.numF[entity] if transpose else self.counts[entity]

@@ -100,6 +100,8 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             eng.set_factors(e, en.model.sample)
         if en.hasFeatures():
             eng.set_features(e, en.F)
+            if en.use_FF:
+                eng.compute_ff(e)  # en.FF = full(At_mul_B(en.F, en.F)) — reset!, src/RelationData.jl:337-339
 
     if verbose:
         print("Sampling")

@@ -137,6 +137,17 @@ int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz
  * nzval nnz; 1-based), as in the reference's own tests (test/parallel_latent_basic.jl:4, test/parallel_mult.jl:4-18). Products
  * accumulate in Julia's order with un-fused multiply-add. */
 int bdf_set_features_csc(bdf_t* h, int entity, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval);
+/* Entity(F = ::Matrix{Float64}) — a dense feature matrix (m × n column-major, m = entity count). The feature-operator duck type
+ * (src/RelationData.jl:314-329) then runs on cuBLAS dgemm (a plain library GEMM; its summation order is the library's). */
+int bdf_set_features_dense(bdf_t* h, int entity, int64_t m, int64_t n, const double* F);
+/* en.FF = full(At_mul_B(en.F, en.F)); en.use_FF = true — reset!, src/RelationData.jl:337-339 (numF <= compute_ff_size). Afterwards
+ * bdf_sample_beta solves with solve_full instead of CG (src/sampling.jl:303-304). FF_out (n × n column-major) may be NULL. */
+int bdf_compute_ff(bdf_t* h, int entity, double* FF_out);
+/* en.use_FF — switch between the direct solve and CG (the FF matrix stays resident). */
+int bdf_set_use_ff(bdf_t* h, int entity, int use_ff);
+/* solve_full(FF, rhs, lambda) — src/sampling.jl:314-320: (FF + lambda·I) \ rhs, rhs and x n × ncol column-major, ncol == num_latent.
+ * The regularised matrix is symmetric positive definite; the device factorisation is a Cholesky (cuSOLVER potrf/potrs). */
+int bdf_solve_full(bdf_t* h, int entity, const double* rhs, int ncol, double lambda, double* x);
 /* Parity hook: the device CSR in the reference's representation — row_ptr (m+1, or n+1 for the transpose) and col_ind
  * (nnz), Int32, 1-based (fields of SparseBinMatrixCSR, src/sparsebin_csr.jl:6-11). */
 int bdf_debug_features_csr(bdf_t* h, int entity, int transpose, int32_t* ptr_out, int32_t* ind_out);
