@@ -185,7 +185,11 @@ int ensure_ws(bdf_t* h, size_t bytes) {
 // observations come as several items — chunks of a long row and/or one relation each — is a "split" row whose partials are
 // added in item order (relation order, then chunk order) by the last item to finish.
 int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector<int64_t>*>& rps, int64_t real_rows) {
-  const int64_t CH = 8192;  // observations per chunk of a split row (multiple of every KS)
+  // observations per chunk of a split row (a multiple of every KS): 8192, less when this rank's share of the table is small (more
+  // GPUs), so that the heavy rows still break into enough items to fill the 148 SMs several times over
+  int64_t total = 0;
+  for (auto* rp : rps) total += (*rp)[real_rows] - (*rp)[0];
+  const int64_t CH = std::min<int64_t>(8192, std::max<int64_t>(1024, (total / 4096 + 15) / 16 * 16));
   const bool multi = rps.size() > 1;
   std::vector<int32_t> irow, ilen, isplit, ichunk, irel, snch;
   std::vector<int64_t> ibeg, swoff;
@@ -375,7 +379,7 @@ __global__ void alpha_draw_kernel(double sse, double n, double lambda0, double n
 int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, int64_t nrows, double* stats) {
   const int nblk = launch_stats_partials(h, X, sub, slot0, nrows);
   if (nblk < 0) return nblk;
-  stats_reduce_kernel<<<8, 256, 0, h->stream>>>(h->ws, nblk, h->D, (double)nrows, stats);
+  stats_reduce_kernel<<<(tri(h->D + 1) + 127) / 128, 128, 0, h->stream>>>(h->ws, nblk, h->D, (double)nrows, stats);
   h->launches++;
   CU(cudaGetLastError());
   return BDF_OK;
@@ -398,7 +402,7 @@ int stats_entity(bdf_t* h, int entity) {
   EntityS& e = h->ents[entity];
   const int nblk = launch_stats_partials(h, e.U, nullptr, (int64_t)h->rank * e.Nper, e.nlocal);
   if (nblk < 0) return nblk;
-  stats_reduce_kernel<<<8, 256, 0, h->stream>>>(h->ws, nblk, h->D, (double)e.nlocal, e.stats);
+  stats_reduce_kernel<<<(tri(h->D + 1) + 127) / 128, 128, 0, h->stream>>>(h->ws, nblk, h->D, (double)e.nlocal, e.stats);
   h->launches++;
   CU(cudaGetLastError());
   return BDF_OK;
@@ -417,7 +421,12 @@ int draw_entity(bdf_t* h, int entity, const double* mu0_dev, double b0, const do
   p.D = h->D; p.stats = e.stats; p.mu0 = mu0_dev; p.Tinv = Tinv_dev; p.b0 = b0; p.nu = nu; p.A_inj = A_dev; p.z_inj = z_dev;
   p.seed = h->seed; p.sweep = h->sweep; p.stream = 0x100u + 8u * (uint32_t)entity; p.scratch = h->scratch;
   p.mu_out = e.mu; p.Lam_out = e.Lambda; p.err_flag = h->err_flag;
-  nw_draw_kernel<<<1, 256, 0, h->stream>>>(p);
+  p.debug = getenv("BDF_DEBUG_NW") != nullptr;
+  const size_t dd8 = sizeof(double) * (size_t)h->D * h->D;
+  p.nsm = 2 * dd8 <= 227 * 1024 ? 2 : (dd8 <= 227 * 1024 ? 1 : 0);
+  static bool attr_done = false;
+  if (!attr_done) { CU(cudaFuncSetAttribute(nw_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  nw_draw_kernel<<<1, 256, p.nsm * dd8, h->stream>>>(p);
   h->launches++;
   CU(cudaGetLastError());
   return BDF_OK;

@@ -4,9 +4,12 @@
 
 namespace bdf {
 
-// In-place lower Cholesky of a column-major n×n matrix (single CTA). Returns false on a non-positive pivot.
+// In-place lower Cholesky of a column-major n×n matrix (single CTA, blockDim.x a multiple of 16). Returns false on a non-positive
+// pivot. Right-looking; the trailing update walks 16×(blockDim/16) patches of the lower triangle with a 2-D thread mapping (no
+// integer division in the loop — the kernel that calls this sits on the critical path of every half-sweep).
 __device__ inline bool cta_chol_lower(double* A, int n) {
   bool ok = true;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, nty = blockDim.x >> 4;
   for (int j = 0; j < n; j++) {
     __syncthreads();
     const double d = A[j + (size_t)j * n];
@@ -16,10 +19,12 @@ __device__ inline bool cta_chol_lower(double* A, int n) {
     __syncthreads();
     for (int i = j + threadIdx.x; i < n; i += blockDim.x) A[i + (size_t)j * n] = (i == j) ? sd : A[i + (size_t)j * n] * is;
     __syncthreads();
-    // trailing update, columns k > j
-    for (int e = threadIdx.x; e < (n - j - 1) * (n - j - 1); e += blockDim.x) {
-      const int k = j + 1 + e / (n - j - 1), i = j + 1 + e % (n - j - 1);
-      if (i >= k) A[i + (size_t)k * n] -= A[i + (size_t)j * n] * A[k + (size_t)j * n];
+    // trailing update, columns k > j, rows i >= k
+    const double* cj = A + (size_t)j * n;
+    for (int k = j + 1 + ty; k < n; k += nty) {
+      const double akj = cj[k];
+      double* ck = A + (size_t)k * n;
+      for (int i = k + tx; i < n; i += 16) ck[i] = fma(-cj[i], akj, ck[i]);
     }
   }
   __syncthreads();

@@ -4,6 +4,7 @@
 // The statistics are a streaming DMMA syrk over the rank's factor rows (same tile machinery as the row draw);
 // the draw is a single-CTA kernel on D×D matrices.
 #pragma once
+#include <cstdio>
 #include "nw_device.cuh"
 #include "row_kernel.cuh"
 
@@ -38,7 +39,8 @@ __global__ void stats_reduce_kernel(const double* __restrict__ ws, int nblk, int
     const int j = e - tri(i);
     if (j >= D) continue;  // (D, D) = Σ1·1 is not part of the statistics
     double s = 0.0;
-    for (int b = 0; b < nblk; b++) s += ws[(size_t)b * ne + e];
+#pragma unroll 8
+    for (int b = 0; b < nblk; b++) s += ws[(size_t)b * ne + e];  // block order: deterministic
     if (i < D) {
       stats[1 + D + i + (size_t)j * D] = s;
       stats[1 + D + j + (size_t)i * D] = s;
@@ -61,6 +63,8 @@ struct NWDrawParams {
   uint64_t seed, sweep;
   uint32_t stream;
   double* scratch;  // 4·D·D doubles
+  int debug;        // print phase clocks (BDF_DEBUG_NW)
+  int nsm;          // how many D×D work matrices live in dynamic shared memory (2, 1 or 0); the rest use `scratch`
   double* mu_out;   // D
   double* Lam_out;  // D×D
   int* err_flag;
@@ -69,10 +73,17 @@ struct NWDrawParams {
 __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
   const int D = p.D, tid = threadIdx.x, nt = blockDim.x;
   const size_t dd = (size_t)D * D;
-  double* Sm = p.scratch;       // S reversed → L
-  double* Y = p.scratch + dd;   // J·A → Y = L⁻ᵀ(J·A)
-  double* Lm = p.scratch + 2 * dd;  // Lambda reversed → L2
+  // The two factorisations are dependent chains of D column steps; on-chip operands (≈30-cycle loads instead of an L2 round trip
+  // per step) are what makes this single-CTA kernel short — it sits on the critical path of every half-sweep.
+  extern __shared__ __align__(16) double nw_smem[];
+  double* Sm = p.nsm >= 1 ? nw_smem : p.scratch;            // S reversed → L
+  double* Y = p.nsm >= 2 ? nw_smem + dd : p.scratch + dd;   // J·A → Y = L⁻ᵀ(J·A)
+  double* Lm = Sm;                  // Lambda reversed → L2; Sm is dead once Y has been formed
   double* v = p.scratch + 3 * dd;   // vectors: mu_N [0,D), w [D,2D)
+  long long tk[10];
+  int nk = 0;
+#define NW_STAMP() do { __syncthreads(); if (p.debug && nk < 10) tk[nk++] = clock64(); } while (0)
+  NW_STAMP();
   const double N = p.stats[0];
   const double* NU = p.stats + 1;
   const double* NS = p.stats + 1 + D;
@@ -94,23 +105,34 @@ __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
     if (p.A_inj) {
       aij = i >= j ? p.A_inj[e] : 0.0;
     } else if (i == j) {
-      aij = sqrt(2.0 * gamma_mt(0.5 * (nuN - i), p.seed, p.sweep, p.stream + 1, (uint64_t)i));
+      continue;  // the chi-square diagonal is drawn below, one thread per entry, so that no warp runs both samplers per element
     } else if (i > j) {
       aij = philox_normal(p.seed, p.sweep, p.stream + 2, (uint64_t)i, j);
     }
     Y[(D - 1 - i) + (size_t)j * D] = aij;
   }
+  if (!p.A_inj)
+    for (int i = tid; i < D; i += nt) Y[(D - 1 - i) + (size_t)i * D] = sqrt(2.0 * gamma_mt(0.5 * (nuN - i), p.seed, p.sweep, p.stream + 1, (uint64_t)i));
+  NW_STAMP();
   bool ok = cta_chol_lower(Sm, D);  // J·S·J = L·Lᵀ  ⇒  chol_lower(inv(S)) = J·L⁻ᵀ·J
-  // Y ← L⁻ᵀ·Y : thread per column, back substitution
-  for (int c = tid; c < D; c += nt) {
-    double* y = Y + (size_t)c * D;
+  NW_STAMP();
+  // Y ← L⁻ᵀ·Y, right-looking: row i of Y is final once divided by L[i][i]; it is then eliminated from all rows k < i at once
+  // (i·D independent updates per step over the whole CTA instead of one dependent chain per column)
+  {
+    const int tx = tid & 15, ty = tid >> 4, nty = nt >> 4;
     for (int i = D - 1; i >= 0; i--) {
-      double s = y[i];
-      for (int k = i + 1; k < D; k++) s -= Sm[k + (size_t)i * D] * y[k];
-      y[i] = s / Sm[i + (size_t)i * D];
+      const double inv = 1.0 / Sm[i + (size_t)i * D];
+      for (int c = tid; c < D; c += nt) Y[i + (size_t)c * D] *= inv;
+      __syncthreads();
+      for (int c = ty; c < D; c += nty) {
+        double* yc = Y + (size_t)c * D;
+        const double yic = yc[i];
+        for (int k = tx; k < i; k += 16) yc[k] = fma(-Sm[i + (size_t)k * D], yic, yc[k]);
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
+  NW_STAMP();
   // Z = J·Y ; Lambda = Z·Zᵀ ; store Lambda and its index-reversed copy
   for (size_t e = tid; e < dd; e += nt) {
     const int i = (int)(e % D), j = (int)(e / D);
@@ -122,7 +144,9 @@ __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
     Lm[(D - 1 - i) + (size_t)(D - 1 - j) * D] = s;
     Lm[(D - 1 - j) + (size_t)(D - 1 - i) * D] = s;
   }
+  NW_STAMP();
   ok = cta_chol_lower(Lm, D) && ok;  // J·Lambda·J = L2·L2ᵀ ⇒ chol_lower(inv(Lambda)) = J·L2⁻ᵀ·J
+  NW_STAMP();
   // w = L2⁻ᵀ (J z): column-oriented back substitution
   double* w = v + D;
   for (int i = tid; i < D; i += nt) {
@@ -140,6 +164,11 @@ __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
   const double sc = 1.0 / sqrt(betaN);
   for (int i = tid; i < D; i += nt) p.mu_out[i] = v[i] + sc * w[D - 1 - i];
   if (!ok && tid == 0) atomicOr(p.err_flag, 2);
+  NW_STAMP();
+  if (p.debug && tid == 0)
+    printf("nw_draw D=%d cycles: build+noise %lld, chol1 %lld, backsub %lld, ZZt %lld, chol2 %lld, mu %lld, total %lld\n", D, tk[1] - tk[0], tk[2] - tk[1],
+           tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[6] - tk[0]);
+#undef NW_STAMP
 }
 
 // standard normals of the row-noise stream, D×N column-major (debug / parity hook)

@@ -49,7 +49,7 @@
 #define BDF_BS_SWITCH 1000
 #endif
 #ifndef BDF_UR_UNROLL
-#define BDF_UR_UNROLL 4
+#define BDF_UR_UNROLL 2
 #endif
 
 namespace bdf {
@@ -583,12 +583,13 @@ struct RowKernel {
       const double* Pp = Tl + 64 * tri(pb) + fo;
       const double na0 = -Pp[64 * I], na1 = -Pp[64 * I + 32];
       double* trow = Tl + 64 * tri(I) + 2 * lane;
-      // four tiles at a time: all their operands are loaded before the first DMMA, so the shared-memory latency and the
+      // UB tiles at a time: all their operands are loaded before the first DMMA, so the shared-memory latency and the
       // two dependent DMMAs of a tile overlap across the batch (the compiler cannot hoist loads over the tile stores)
-      for (int J = j0; J <= j1; J += 4) {
-        double b0[4], b1[4], c2[4][2];
+      constexpr int UB = BDF_UR_UNROLL;
+      for (int J = j0; J <= j1; J += UB) {
+        double b0[UB], b1[UB], c2[UB][2];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < UB; u++) {
           const int Ju = J + u <= j1 ? J + u : j1;
           b0[u] = Pp[64 * Ju];
           b1[u] = Pp[64 * Ju + 32];
@@ -597,15 +598,15 @@ struct RowKernel {
           c2[u][1] = cv.y;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) dmma884(c2[u], na0, b0[u]);
+        for (int u = 0; u < UB; u++) dmma884(c2[u], na0, b0[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) dmma884(c2[u], na1, b1[u]);
+        for (int u = 0; u < UB; u++) dmma884(c2[u], na1, b1[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < UB; u++)
           if (J + u <= j1) *reinterpret_cast<double2*>(trow + 64 * (J + u)) = make_double2(c2[u][0], c2[u][1]);
       }
     };
-    constexpr int BS_SWITCH = NW == 4 ? BDF_BS_SWITCH : 1000;  // panels at or above this: backsub_step rides on warp 0 (the trailing warps are the critical path there)
+    constexpr int BS_SWITCH = NW == 4 ? BDF_BS_SWITCH : 1000;  // panels at or above this: backsub_step rides on warp 0 (off by default)
     // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
     // rhs[c] −= Σ_k R_J[k][c]·y_J[k] for c < 8J. One warp; rides along with the trailing update.
     auto backsub_step = [&](int J, bool update) {
@@ -685,8 +686,10 @@ struct RowKernel {
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
     BDF_STAMP(5);
 
-    // ---- warp 0: last block of y = W⁻¹·rhs, then x = W⁻ᵀ(y + z) by forward substitution over the block rows ---------
+    // ---- one warp: last block of y = W⁻¹·rhs, then x = W⁻ᵀ(y + z) by forward substitution over the block rows (a CTA-wide
+    //      version with one barrier per block was measured slower under load: the idle warps' issue slots go to co-resident rows)
     if (vw == 0) {
+      {
       const int r8 = lane & 7;
       const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
       backsub_step(0, false);
@@ -736,6 +739,7 @@ struct RowKernel {
           }
           __syncwarp();
         }
+      }
       }
       __syncwarp();
       double* out = p.Uout + (size_t)slot * p.ld;
