@@ -415,7 +415,7 @@ int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t m
 namespace {
 
 int draw_entity(bdf_t* h, int entity, const double* mu0_dev, double b0, const double* Tinv_dev, double nu, const double* A_dev,
-                const double* z_dev) {
+                const double* z_dev, cudaStream_t side = nullptr) {
   EntityS& e = h->ents[entity];
   NWDrawParams p{};
   p.D = h->D; p.stats = e.stats; p.mu0 = mu0_dev; p.Tinv = Tinv_dev; p.b0 = b0; p.nu = nu; p.A_inj = A_dev; p.z_inj = z_dev;
@@ -424,9 +424,19 @@ int draw_entity(bdf_t* h, int entity, const double* mu0_dev, double b0, const do
   p.debug = getenv("BDF_DEBUG_NW") != nullptr;
   const size_t dd8 = sizeof(double) * (size_t)h->D * h->D;
   p.nsm = 2 * dd8 <= 227 * 1024 ? 2 : (dd8 <= 227 * 1024 ? 1 : 0);
+  // on a side stream the draw runs next to the following half-sweep's row kernel: the no-shared-memory, <= 64-register variant fits
+  // into the slot one retiring row CTA leaves behind (the row kernel owns all shared memory and registers of an SM otherwise)
+  if (side) p.nsm = 0;
+  cudaStream_t st = side ? side : h->stream;
   static bool attr_done = false;
-  if (!attr_done) { CU(cudaFuncSetAttribute(nw_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  nw_draw_kernel<<<1, 256, p.nsm * dd8, h->stream>>>(p);
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(nw_draw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(nw_draw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  if (p.nsm == 2) nw_draw_kernel<2><<<1, 256, 2 * dd8, st>>>(p);
+  else if (p.nsm == 1) nw_draw_kernel<1><<<1, 256, dd8, st>>>(p);
+  else nw_draw_kernel<0><<<1, 256, 0, st>>>(p);
   h->launches++;
   CU(cudaGetLastError());
   return BDF_OK;
@@ -792,6 +802,14 @@ int bdf_step_nw_draw(bdf_t* h, int entity) {
   CHECK_H(); CHECK_ENT(entity);
   EntityS& e = h->ents[entity];
   return draw_entity(h, entity, e.hyper, e.b0, e.hyper + h->D, e.nu0, nullptr, nullptr);
+}
+
+int bdf_step_nw_draw_on(bdf_t* h, int entity, void* cuda_stream) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!cuda_stream) FAIL(BDF_ERR_INVALID, "null stream");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  return draw_entity(h, entity, e.hyper, e.b0, e.hyper + h->D, e.nu0, nullptr, nullptr, (cudaStream_t)cuda_stream);
 }
 
 int bdf_sweep(bdf_t* h, int nsweeps) {

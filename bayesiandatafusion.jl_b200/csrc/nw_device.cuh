@@ -24,7 +24,20 @@ __device__ inline bool cta_chol_lower(double* A, int n) {
     for (int k = j + 1 + ty; k < n; k += nty) {
       const double akj = cj[k];
       double* ck = A + (size_t)k * n;
-      for (int i = k + tx; i < n; i += 16) ck[i] = fma(-cj[i], akj, ck[i]);
+      for (int i0 = k + tx; i0 < n; i0 += 64) {  // four independent elements per pass: loads first, then the stores
+        double a[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + 16 * u;
+          a[u] = i < n ? cj[i] : 0.0;
+          c[u] = i < n ? ck[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + 16 * u;
+          if (i < n) ck[i] = fma(-a[u], akj, c[u]);
+        }
+      }
     }
   }
   __syncthreads();

@@ -70,14 +70,15 @@ struct NWDrawParams {
   int* err_flag;
 };
 
-__global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
+template <int NSM>  // D×D work matrices in dynamic shared memory: 2, 1 or 0 (compile-time, so that their accesses are LDS/STS, not generic)
+__global__ void __launch_bounds__(256, NSM == 0 ? 4 : 1) nw_draw_kernel(const NWDrawParams p) {
   const int D = p.D, tid = threadIdx.x, nt = blockDim.x;
   const size_t dd = (size_t)D * D;
   // The two factorisations are dependent chains of D column steps; on-chip operands (≈30-cycle loads instead of an L2 round trip
   // per step) are what makes this single-CTA kernel short — it sits on the critical path of every half-sweep.
   extern __shared__ __align__(16) double nw_smem[];
-  double* Sm = p.nsm >= 1 ? nw_smem : p.scratch;            // S reversed → L
-  double* Y = p.nsm >= 2 ? nw_smem + dd : p.scratch + dd;   // J·A → Y = L⁻ᵀ(J·A)
+  double* Sm = NSM >= 1 ? nw_smem : p.scratch;            // S reversed → L
+  double* Y = NSM >= 2 ? nw_smem + dd : p.scratch + dd;   // J·A → Y = L⁻ᵀ(J·A)
   double* Lm = Sm;                  // Lambda reversed → L2; Sm is dead once Y has been formed
   double* v = p.scratch + 3 * dd;   // vectors: mu_N [0,D), w [D,2D)
   long long tk[10];
@@ -127,7 +128,20 @@ __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
       for (int c = ty; c < D; c += nty) {
         double* yc = Y + (size_t)c * D;
         const double yic = yc[i];
-        for (int k = tx; k < i; k += 16) yc[k] = fma(-Sm[i + (size_t)k * D], yic, yc[k]);
+        for (int k0 = tx; k0 < i; k0 += 64) {  // four independent elements per pass
+          double l[4], y[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int k = k0 + 16 * u;
+            l[u] = k < i ? Sm[i + (size_t)k * D] : 0.0;
+            y[u] = k < i ? yc[k] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int k = k0 + 16 * u;
+            if (k < i) yc[k] = fma(-l[u], yic, y[u]);
+          }
+        }
       }
       __syncthreads();
     }
@@ -137,8 +151,18 @@ __global__ void __launch_bounds__(256) nw_draw_kernel(const NWDrawParams p) {
   for (size_t e = tid; e < dd; e += nt) {
     const int i = (int)(e % D), j = (int)(e / D);
     if (i < j) continue;
-    double s = 0.0;
-    for (int k = 0; k < D; k++) s = fma(Y[(D - 1 - i) + (size_t)k * D], Y[(D - 1 - j) + (size_t)k * D], s);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four partial sums: the dot product is not one dependent chain
+    const double* yi = Y + (D - 1 - i);
+    const double* yj = Y + (D - 1 - j);
+    int k = 0;
+    for (; k + 4 <= D; k += 4) {
+      s0 = fma(yi[(size_t)k * D], yj[(size_t)k * D], s0);
+      s1 = fma(yi[(size_t)(k + 1) * D], yj[(size_t)(k + 1) * D], s1);
+      s2 = fma(yi[(size_t)(k + 2) * D], yj[(size_t)(k + 2) * D], s2);
+      s3 = fma(yi[(size_t)(k + 3) * D], yj[(size_t)(k + 3) * D], s3);
+    }
+    for (; k < D; k++) s0 = fma(yi[(size_t)k * D], yj[(size_t)k * D], s0);
+    const double s = (s0 + s1) + (s2 + s3);
     p.Lam_out[i + (size_t)j * D] = s;
     p.Lam_out[j + (size_t)i * D] = s;
     Lm[(D - 1 - i) + (size_t)(D - 1 - j) * D] = s;

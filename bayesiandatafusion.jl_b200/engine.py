@@ -162,6 +162,10 @@ class Engine:
     def step_nw_draw(self, entity: int):
         self._ck(self.lib.bdf_step_nw_draw(self.h, entity))
 
+
+    def step_nw_draw_on(self, entity: int, cuda_stream: int):
+        self._ck(self.lib.bdf_step_nw_draw_on(self.h, entity, C.c_void_p(cuda_stream)))
+
     def sweep(self, n: int = 1):
         self._ck(self.lib.bdf_sweep(self.h, n))
 

@@ -69,7 +69,7 @@ class DistributedSweep:
     """Drives device-resident Gibbs sweeps over `world` GPUs: the loop body of src/macau.jl:96-134 with the collectives
     between the kernels. With world == 1 it degenerates to the same kernel sequence without communication."""
 
-    def __init__(self, engine, entities, group=None, fused_allgather=True):
+    def __init__(self, engine, entities, group=None, fused_allgather=True, overlap_draw=True):
         import torch
         import torch.distributed as dist
 
@@ -97,8 +97,19 @@ class DistributedSweep:
                         engine.ipc_import(e, r, handles[e])
             dist.barrier(group=group)
 
+        # The Normal-Wishart draw of an entity is first needed by that entity's NEXT half-sweep, so it runs on a high-priority side
+        # stream beside the following entity's row kernel (same kernels, same Philox streams: results are unchanged)
+        self.overlap = bool(overlap_draw)
+        self.side = torch.cuda.Stream(priority=-1) if self.overlap else None
+        self.draw_done = {}
+
     def half_sweep(self, e):
+        import torch
+
         eng = self.eng
+        main = torch.cuda.current_stream()
+        if e in self.draw_done:
+            main.wait_event(self.draw_done.pop(e))  # this entity's (mu, Lambda) from its previous draw
         eng.step_sample(e)
         U, blk, stats = self.views[e]
         if self.dist is not None and not self.fused:
@@ -107,10 +118,29 @@ class DistributedSweep:
         eng.step_nw_stats(e)
         if self.dist is not None:
             self.dist.all_reduce(stats, group=self.group)
-        eng.step_nw_draw(e)
+        if not self.overlap:
+            eng.step_nw_draw(e)
+            return
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.side.wait_event(ready)
+        eng.step_nw_draw_on(e, self.side.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(self.side)
+        self.draw_done[e] = done
+
+    def join(self):
+        """Order every outstanding draw before whatever the caller enqueues next on the current stream."""
+        import torch
+
+        main = torch.cuda.current_stream()
+        for e in list(self.draw_done):
+            main.wait_event(self.draw_done.pop(e))
 
     def sweep(self, n: int = 1):
         for _ in range(n):
             for e in self.entities:
                 self.half_sweep(e)
             self.eng.advance_sweep()
+        if self.overlap:
+            self.join()

@@ -97,6 +97,10 @@ int bdf_nw_sample(bdf_t* h, int entity, const double* mu0, double b0, const doub
 int bdf_step_sample(bdf_t* h, int entity);
 int bdf_step_nw_stats(bdf_t* h, int entity);
 int bdf_step_nw_draw(bdf_t* h, int entity);
+/* The same draw enqueued on another cudaStream_t (the caller orders it after the statistics with events): the new (mu, Lambda) of an
+ * entity are first needed by ITS next half-sweep, so the draw can run beside the next entity's row kernel. Uses the small-footprint
+ * variant of the kernel (global scratch, <= 64 registers) that fits next to resident row-kernel CTAs. */
+int bdf_step_nw_draw_on(bdf_t* h, int entity, void* cuda_stream);
 /* Whole sweeps on one GPU (world == 1): for each entity {sample, stats, draw}. */
 int bdf_sweep(bdf_t* h, int nsweeps);
 /* Advance the Philox sweep counter by one (drivers that sequence the bdf_step_* / host-pointer entries themselves call
