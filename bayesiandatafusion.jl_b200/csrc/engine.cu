@@ -76,15 +76,15 @@ int64_t pst_of(int DP) {
 // slot of 0-based global row i: rows are dealt cyclically to ranks (src/sampling.jl:154), each rank's rows contiguous
 __host__ __device__ inline int64_t slot_of(int64_t i, int world, int64_t nper) { return (i % world) * nper + i / world; }
 
-__global__ void make_keys_kernel(const int64_t* ids, int64_t nnz, int64_t N, int world, int64_t nper, uint32_t* keys, uint32_t* idx,
-                                 int* bad) {
+__global__ void make_keys_kernel(const int64_t* ids, int64_t nnz, int64_t N, int world, int64_t nper, const int32_t* __restrict__ tab,
+                                 uint32_t* keys, uint32_t* idx, int* bad) {
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nnz; o += (int64_t)gridDim.x * blockDim.x) {
     const int64_t id = ids[o];
     if (id < 1 || id > N) {
       *bad = 1;
       keys[o] = 0;
     } else {
-      keys[o] = (uint32_t)slot_of(id - 1, world, nper);
+      keys[o] = tab ? (uint32_t)tab[id - 1] : (uint32_t)slot_of(id - 1, world, nper);
     }
     idx[o] = (uint32_t)o;
   }
@@ -107,20 +107,33 @@ __global__ void lower_bound_kernel(const uint32_t* keys, int64_t nnz, uint32_t t
 }
 
 __global__ void gather_obs_kernel(const uint32_t* perm, int64_t base, int64_t n, const int64_t* ids_other, int world, int64_t nper_other,
-                                  int32_t* col) {
-  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
-    col[o] = (int32_t)slot_of(ids_other[perm[base + o]] - 1, world, nper_other);
+                                  const int32_t* __restrict__ tab, int32_t* col) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = ids_other[perm[base + o]] - 1;
+    col[o] = tab ? tab[i] : (int32_t)slot_of(i, world, nper_other);
+  }
 }
 
 __global__ void gather_val_kernel(const uint32_t* perm, int64_t base, int64_t n, const double* vals, double* out) {
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) out[o] = vals[perm[base + o]];
 }
 
-__global__ void ids_to_slots_kernel(const int64_t* ids, int64_t n, int64_t N, int world, int64_t nper, int32_t* out, int* bad) {
+__global__ void ids_to_slots_kernel(const int64_t* ids, int64_t n, int64_t N, int world, int64_t nper, const int32_t* __restrict__ tab, int32_t* out,
+                                    int* bad) {
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
     const int64_t id = ids[o];
-    if (id < 1 || id > N) { *bad = 1; out[o] = 0; } else out[o] = (int32_t)slot_of(id - 1, world, nper);
+    if (id < 1 || id > N) { *bad = 1; out[o] = 0; } else out[o] = tab ? tab[id - 1] : (int32_t)slot_of(id - 1, world, nper);
   }
+}
+
+// rows of a D×N column-major host-order staging matrix → slot-major ld-pitched device buffer (and back) through an explicit row → slot map
+__global__ void scatter_rows_kernel(const double* __restrict__ stage, const int32_t* __restrict__ slot_of_row, int64_t N, int D, int ld, double* __restrict__ dev) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * D; e += (int64_t)gridDim.x * blockDim.x)
+    dev[(size_t)slot_of_row[e / D] * ld + e % D] = stage[e];
+}
+__global__ void gather_rows_kernel(const double* __restrict__ dev, const int32_t* __restrict__ slot_of_row, int64_t N, int D, int ld, double* __restrict__ stage) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * D; e += (int64_t)gridDim.x * blockDim.x)
+    stage[e] = dev[(size_t)slot_of_row[e / D] * ld + e % D];
 }
 
 __global__ void set_identity_kernel(double* A, int D, double v) {
@@ -137,6 +150,15 @@ inline int grid_for(int64_t n, int block = 256) {
 // host↔device copies between Julia's D×N column-major matrix and the slot-major, ld-pitched device buffer
 int copy_rows_h2d(bdf_t* h, const EntityS& e, const double* host, double* dev) {
   const int D = h->D, W = h->world;
+  if (e.slot_of_row) {
+    int rc = bdf_ensure_arena(h, sizeof(double) * (size_t)e.N * D);
+    if (rc) return rc;
+    double* stage = reinterpret_cast<double*>(h->arena);
+    CU(cudaMemcpyAsync(stage, host, sizeof(double) * (size_t)e.N * D, cudaMemcpyHostToDevice, h->stream));
+    scatter_rows_kernel<<<grid_for(e.N * D), 256, 0, h->stream>>>(stage, e.slot_of_row, e.N, D, h->ld, dev);
+    CU(cudaGetLastError());
+    return BDF_OK;
+  }
   for (int r = 0; r < W; r++) {
     const int64_t cnt = (e.N - r + W - 1) / W;  // rows r, r+W, ...
     if (cnt <= 0) continue;
@@ -147,6 +169,15 @@ int copy_rows_h2d(bdf_t* h, const EntityS& e, const double* host, double* dev) {
 }
 int copy_rows_d2h(bdf_t* h, const EntityS& e, const double* dev, double* host) {
   const int D = h->D, W = h->world;
+  if (e.slot_of_row) {
+    int rc = bdf_ensure_arena(h, sizeof(double) * (size_t)e.N * D);
+    if (rc) return rc;
+    double* stage = reinterpret_cast<double*>(h->arena);
+    gather_rows_kernel<<<grid_for(e.N * D), 256, 0, h->stream>>>(dev, e.slot_of_row, e.N, D, h->ld, stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, stage, sizeof(double) * (size_t)e.N * D, cudaMemcpyDeviceToHost, h->stream));
+    return BDF_OK;
+  }
   for (int r = 0; r < W; r++) {
     const int64_t cnt = (e.N - r + W - 1) / W;
     if (cnt <= 0) continue;
@@ -301,7 +332,7 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
     t.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : (tensor ? h->ones : nullptr);
     t.alpha = rel.alpha; t.mean = rel.mean;
   }
-  p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper;
+  p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper; p.row_of_slot = e.row_of_slot;
   { int np = 0; for (int r = 0; r < 8; r++) if (e.peerU[r]) p.peer_out[np++] = e.peerU[r]; }
   p.Lambda = Lambda_dev; p.mu = mu_dev; p.mu_ld = mu_ld; p.Z = Z_dev;
   p.LT = h->lt; p.lmu = mu_ld ? nullptr : h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2;
@@ -497,6 +528,7 @@ int bdf_destroy(bdf_t* h) {
   bdf_dense_teardown(h);
   for (auto& e : h->ents) {
     for (int r = 0; r < 8; r++) if (e.peerU[r]) cudaIpcCloseMemHandle(e.peerU[r]);
+    cudaFree(e.slot_of_row); cudaFree(e.row_of_slot);
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
     cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
     cudaFree(e.sp_items[0]); cudaFree(e.sp_items[1]); cudaFree(e.sp_long[0]); cudaFree(e.sp_long[1]); cudaFree(e.sp_part);
@@ -527,15 +559,11 @@ int64_t bdf_sweep_counter(const bdf_t* h) { return h ? (int64_t)h->sweep : -1; }
 int64_t bdf_launch_count(const bdf_t* h) { return h ? h->launches : -1; }
 int bdf_synchronize(bdf_t* h) { CHECK_H(); CU(cudaSetDevice(h->device)); CU(cudaStreamSynchronize(h->stream)); return BDF_OK; }
 
-int bdf_add_entity(bdf_t* h, int64_t count) {
-  CHECK_H();
-  if (count < 1 || count > 2000000000LL) FAIL(BDF_ERR_INVALID, "entity count must be in 1..2e9");
-  CU(cudaSetDevice(h->device));
+static int add_entity_impl(bdf_t* h, int64_t count, int64_t nper, int64_t nlocal, const std::vector<int32_t>* slot_of_row) {
   EntityS e;
   e.N = count;
-  e.Nper = (count + h->world - 1) / h->world;
-  e.nlocal = (count - h->rank + h->world - 1) / h->world;
-  if (e.nlocal < 0) e.nlocal = 0;
+  e.Nper = nper;
+  e.nlocal = nlocal;
   const int D = h->D;
   const size_t un = (size_t)e.Nper * h->world * h->ld;
   int rc;
@@ -544,6 +572,14 @@ int bdf_add_entity(bdf_t* h, int64_t count) {
   if ((rc = dev_alloc(h, &e.Lambda, (size_t)D * D))) return rc;
   if ((rc = dev_alloc(h, &e.stats, (size_t)1 + D + (size_t)D * D))) return rc;
   if ((rc = dev_alloc(h, &e.hyper, (size_t)D + (size_t)D * D))) return rc;
+  if (slot_of_row) {
+    std::vector<int32_t> inv((size_t)e.Nper * h->world, -1);
+    for (int64_t i = 0; i < count; i++) inv[(*slot_of_row)[i]] = (int32_t)i;
+    if ((rc = dev_alloc(h, &e.slot_of_row, (size_t)count))) return rc;
+    if ((rc = dev_alloc(h, &e.row_of_slot, inv.size()))) return rc;
+    CU(cudaMemcpy(e.slot_of_row, slot_of_row->data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e.row_of_slot, inv.data(), sizeof(int32_t) * inv.size(), cudaMemcpyHostToDevice));
+  }
   // initModel! — src/RelationData.jl:66-90
   CU(cudaMemsetAsync(e.U, 0, un * sizeof(double), h->stream));
   CU(cudaMemsetAsync(e.mu, 0, D * sizeof(double), h->stream));
@@ -558,6 +594,37 @@ int bdf_add_entity(bdf_t* h, int64_t count) {
   e.nu0 = D;
   h->ents.push_back(e);
   return (int)h->ents.size() - 1;
+}
+
+int bdf_add_entity(bdf_t* h, int64_t count) {
+  CHECK_H();
+  if (count < 1 || count > 2000000000LL) FAIL(BDF_ERR_INVALID, "entity count must be in 1..2e9");
+  CU(cudaSetDevice(h->device));
+  int64_t nlocal = (count - h->rank + h->world - 1) / h->world;
+  if (nlocal < 0) nlocal = 0;
+  return add_entity_impl(h, count, (count + h->world - 1) / h->world, nlocal, nullptr);
+}
+
+int bdf_add_entity_partitioned(bdf_t* h, int64_t count, const int32_t* rank_of_row) {
+  CHECK_H();
+  if (count < 1 || count > 2000000000LL) FAIL(BDF_ERR_INVALID, "entity count must be in 1..2e9");
+  if (!rank_of_row) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  std::vector<int64_t> cnt(h->world, 0);
+  for (int64_t i = 0; i < count; i++) {
+    if (rank_of_row[i] < 0 || rank_of_row[i] >= h->world) FAIL(BDF_ERR_INVALID, "rank_of_row entries must lie in 0..world-1");
+    cnt[rank_of_row[i]]++;
+  }
+  int64_t nper = 1;
+  for (int r = 0; r < h->world; r++) nper = std::max(nper, cnt[r]);
+  if (nper * h->world >= 2147483647LL) FAIL(BDF_ERR_INVALID, "too many slots");
+  std::vector<int32_t> slot((size_t)count);
+  std::vector<int64_t> next(h->world, 0);
+  for (int64_t i = 0; i < count; i++) {  // rows keep their relative order inside a shard
+    const int r = rank_of_row[i];
+    slot[i] = (int32_t)(r * nper + next[r]++);
+  }
+  return add_entity_impl(h, count, nper, cnt[h->rank], &slot);
 }
 
 int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, const int64_t* ids, const double* vals) {
@@ -607,7 +674,7 @@ int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, co
     const int64_t slot0 = (int64_t)h->rank * e.Nper;
     int bits = 1;
     while ((1LL << bits) < e.Nper * h->world) bits++;
-    make_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(d_ids + (size_t)m * nnz, nnz, e.N, h->world, e.Nper, keys, idx, d_bad);
+    make_keys_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(d_ids + (size_t)m * nnz, nnz, e.N, h->world, e.Nper, e.slot_of_row, keys, idx, d_bad);
     CUT(cudaGetLastError());
     if (nnz) CUT(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys, keys2, idx, idx2, (int)nnz, 0, bits, h->stream));  // stable: table order kept
     // local segment of the sorted table
@@ -631,7 +698,7 @@ int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, co
       EntityS& eo = h->ents[entity_of_mode[m2]];
       mi.other_entity[no] = entity_of_mode[m2];
       TRY(dev_alloc(h, &mi.col[no], (size_t)std::max<int64_t>(mi.nnz, 1)));
-      gather_obs_kernel<<<grid_for(mi.nnz), 256, 0, h->stream>>>(idx2, lb[0], mi.nnz, d_ids + (size_t)m2 * nnz, h->world, eo.Nper, mi.col[no]);
+      gather_obs_kernel<<<grid_for(mi.nnz), 256, 0, h->stream>>>(idx2, lb[0], mi.nnz, d_ids + (size_t)m2 * nnz, h->world, eo.Nper, eo.slot_of_row, mi.col[no]);
       CUT(cudaGetLastError());
       no++;
     }
@@ -922,7 +989,7 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
   for (int m = 0; m < r.K; m++) {
     EntityS& e = h->ents[r.entity_of_mode[m]];
     Us[m] = e.U;
-    ids_to_slots_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(d_ids + (size_t)m * ntest, ntest, e.N, h->world, e.Nper, d_s + (size_t)m * ntest, d_bad);
+    ids_to_slots_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(d_ids + (size_t)m * ntest, ntest, e.N, h->world, e.Nper, e.slot_of_row, d_s + (size_t)m * ntest, d_bad);
   }
   predict_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(r.K, Us[0], Us[1], Us[2], d_s, d_s + ntest, d_s + 2 * ntest, h->ld, h->D, ntest, r.mean, d_out);
   h->launches += 1 + r.K;

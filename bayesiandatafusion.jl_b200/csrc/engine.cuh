@@ -44,6 +44,9 @@ struct EntityS {
   int64_t N = 0, Nper = 0;  // real rows; rows per rank (slots = world*Nper)
   int64_t nlocal = 0;       // real rows owned by this rank
   double* U = nullptr;      // world*Nper × ld, slot-major
+  // explicit row → slot map of an entity created with bdf_add_entity_partitioned (nnz-balanced shards); nullptr = the cyclic map
+  int32_t* slot_of_row = nullptr;  // [N]
+  int32_t* row_of_slot = nullptr;  // [world*Nper], -1 on padding slots
   double* peerU[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // IPC-mapped replicas on the other ranks
   double* mu = nullptr;     // D
   double* Lambda = nullptr; // D×D col-major

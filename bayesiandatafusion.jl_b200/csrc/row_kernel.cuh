@@ -85,6 +85,7 @@ struct RowParams {
   double* Uout;  // factor buffer being sampled
   double* peer_out[8];  // fused all-gather: the same buffer on every OTHER rank (IPC-mapped peer memory, NVLink stores), nullptr-terminated
   int64_t slot_base;  // slot of local row 0 (= rank * Nper)
+  const int32_t* row_of_slot;  // global 0-based row of each slot (nnz-balanced shards) or nullptr = cyclic: row = local·world + rank
   const double* Lambda;  // D×D column-major
   const double* LT;      // Λ in tile order (64 doubles per tile t = tri(I)+J, identity on the padding), see prep_lambda_kernel
   const double* lmu;     // Λ·μ (DP doubles) when μ is shared by all rows, else nullptr
@@ -422,7 +423,7 @@ struct RowKernel {
     if (tid < DP) {
       double z = 0.0;
       if (tid < D) {
-        const int64_t grow0 = (int64_t)lrow * p.world + p.rank;
+        const int64_t grow0 = p.row_of_slot ? (int64_t)p.row_of_slot[slot] : (int64_t)lrow * p.world + p.rank;
         z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, p.entity, grow0, tid);
       }
       xs[tid] = z;

@@ -79,6 +79,15 @@ class Engine:
         self.counts.append(int(count))
         return e
 
+    def add_entity_partitioned(self, count: int, rank_of_row) -> int:
+        """Entity with an explicit shard map (rank of every row, identical on all ranks) instead of the cyclic deal."""
+        r = np.ascontiguousarray(rank_of_row, dtype=np.int32)
+        if r.shape != (count,):
+            raise ValueError("rank_of_row must have one entry per row")
+        e = self._ck(self.lib.bdf_add_entity_partitioned(self.h, C.c_int64(count), r.ctypes.data_as(_lib.c_i32p)))
+        self.counts.append(int(count))
+        return e
+
     def add_relation(self, entities, ids, vals) -> int:
         ids = np.asfortranarray(ids, dtype=np.int64)
         vals = _f64(vals)

@@ -65,6 +65,27 @@ def device_view(ptr: int, shape, device):
     return torch.as_tensor(_DevArray(ptr, shape), device=device)
 
 
+def balanced_partition(degrees, world: int, row_cost: float = 0.0):
+    """Work-balanced shard map: rank_of_row for `world` ranks by greedy longest-processing-time assignment of the rows, heaviest
+    first, each to the currently lightest rank. The weight of a row is its number of observations plus `row_cost` (the fixed
+    factorisation + draw cost of a row in observation-equivalents). With a heavy-tailed degree distribution the cyclic deal
+    `i:Nprocs:N` (src/sampling.jl:154) always hands the heaviest row of every group of `world` to the same rank."""
+    import heapq
+
+    deg = np.asarray(degrees, dtype=np.float64) + float(row_cost)
+    n = deg.shape[0]
+    rank = np.zeros(n, dtype=np.int32)
+    if world == 1:
+        return rank
+    order = np.argsort(-deg, kind="stable")
+    heap = [(0.0, r) for r in range(world)]
+    for i in order.tolist():
+        load, r = heap[0]
+        rank[i] = r
+        heapq.heapreplace(heap, (load + deg[i], r))
+    return rank
+
+
 class DistributedSweep:
     """Drives device-resident Gibbs sweeps over `world` GPUs: the loop body of src/macau.jl:96-134 with the collectives
     between the kernels. With world == 1 it degenerates to the same kernel sequence without communication."""

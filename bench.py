@@ -190,7 +190,15 @@ def run_ours(args):
     eng = bdf_b200.Engine(D, device=local, rank=rank, world=world)
     eng.set_stream(stream.cuda_stream)
     eng.set_seed(SEED)
-    e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
+    if world > 1 and args.partition == "balanced":
+        # work-balanced shard maps (the same on every rank): with heavy-tailed degrees the cyclic deal of src/sampling.jl:154 hands
+        # the heaviest row of every group of `world` to rank 0; row_cost = the fixed per-row work in observation-equivalents
+        from bdf_b200.shard import balanced_partition
+
+        e1 = eng.add_entity_partitioned(n1, balanced_partition(np.bincount(tr_ids[:, 0] - 1, minlength=n1), world, 2.0 * D))
+        e2 = eng.add_entity_partitioned(n2, balanced_partition(np.bincount(tr_ids[:, 1] - 1, minlength=n2), world, 2.0 * D))
+    else:
+        e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
     rel = eng.add_relation([e1, e2], tr_ids, tr_vals)
     eng.set_relation_params(rel, ALPHA, mean)
     ds = DistributedSweep(eng, [e1, e2])
@@ -301,7 +309,7 @@ def run_ours(args):
             "config": {"workload": f"BPMF synthetic Netflix-scale {n1}x{n2}, {nnz_tr} training ratings (+{ntest} held out), D={D}",
                        "alpha": ALPHA, "skew": 2.5, "seed": SEED, "noise": "device Philox",
                        "l2": "inputs (ratings 1.2 GB/mode + factors) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"rows cyclic over {world} GPU(s); drawn rows stored into every peer replica by the row kernel (NVLink P2P, fused all-gather) + NCCL all-reduce of NW stats per half-sweep" if world > 1 else "single GPU"},
+                       "parallelism": f"rows sharded over {world} GPU(s) ({args.partition} shard map); drawn rows stored into every peer replica by the row kernel (NVLink P2P, fused all-gather) + NCCL all-reduce of NW stats per half-sweep" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "fp64_frac_of_peak_whole_sweep": (2 * alg_flops(nnz_tr, 0, D) + alg_flops(0, n1 + n2, D)) / (ms / args.steps / 1e3) / 1e12 / peak / world,
         }
@@ -321,6 +329,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 480k-user / 100M-rating workload (1.0 = the judged config)")
     ap.add_argument("--cpu-scale", type=float, default=0.01, help="bounded sample for the CPU arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--partition", default="balanced", choices=["balanced", "cyclic"], help="row → GPU shard map for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -49,6 +49,11 @@ int bdf_set_seed(bdf_t* h, uint64_t seed);
 /* Entity(name) + initModel! — src/RelationData.jl:42-90: sample=0, mu=0, Lambda=5I, mu0=0, b0=2, WI=I, nu0=D.
  * Returns the entity id (>= 0) or a negative error. */
 int bdf_add_entity(bdf_t* h, int64_t count);
+/* The same with an explicit shard map: rank_of_row[i] in 0..world-1 (identical on every rank) replaces the cyclic deal, e.g. an
+ * nnz-balanced assignment when a few rows carry a large share of the observations (the reference balances its workers' blocks by
+ * measured work in the same spirit, balanced_parallelsbm, src/parallel_matrix.jl:167). Rows keep their relative order inside a shard; results do not
+ * depend on the map (noise is keyed by global row id). Must be used for all entities before they enter a relation. */
+int bdf_add_entity_partitioned(bdf_t* h, int64_t count, const int32_t* rank_of_row);
 
 /* FastIDF(rel.data) + @spawnat (src/macau.jl:51-52, src/IndexedDF.jl:46-70): registers the observation table
  * of a K-mode relation and builds one device CSR per mode (stable in table order, duplicates kept).

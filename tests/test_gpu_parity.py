@@ -228,3 +228,63 @@ def test_device_resident_sweeps_recover_planted_model():
     assert np.all(np.isfinite(mu)) and np.all(np.linalg.eigvalsh(Lam) > 0)
     assert eng.launches > 0
     eng.close()
+
+
+@pytest.mark.parametrize("partition", ["cyclic", "balanced"])
+def test_three_emulated_ranks_with_shard_maps(partition):
+    """Rows sharded over world=3 handles (all on this GPU): cyclic `i:Nprocs:N` (src/sampling.jl:154) and an explicit
+    work-balanced shard map. Every rank samples only its rows; together they reproduce the oracle's half-sweep, for injected
+    noise and for Philox noise (keyed by global row id, so the map must not matter)."""
+    import bdf_b200
+    from bdf_b200.shard import balanced_partition
+
+    rng = np.random.default_rng(321)
+    dims, D, W, nnz = [61, 29], 32, 3, 2500
+    ids, vals, U, mu, Lambda = make_problem(rng, dims, nnz, D, heavy=(0, 5, 900))
+    mean = float(vals.mean())
+    maps = [balanced_partition(np.bincount(ids[:, m] - 1, minlength=d), W, 20.0) for m, d in enumerate(dims)]
+    if partition == "balanced":
+        assert len(set(maps[0].tolist())) == W and not np.array_equal(maps[0], np.arange(dims[0]) % W)
+    engs = []
+    for r in range(W):
+        eng = bdf_b200.Engine(D, rank=r, world=W)
+        if partition == "balanced":
+            ents = [eng.add_entity_partitioned(d, mp) for d, mp in zip(dims, maps)]
+        else:
+            ents = [eng.add_entity(d) for d in dims]
+        rel = eng.add_relation(ents, ids, vals)
+        eng.set_relation_params(rel, 2.0, mean)
+        for e, u in zip(ents, U):
+            eng.set_factors(e, u)
+        engs.append((eng, ents, rel))
+    owner = maps if partition == "balanced" else [np.arange(d) % W for d in dims]
+    idf = orc.FastIDF(ids, vals, dims)
+    # predictions go through the same id → slot map
+    tids = np.stack([rng.integers(1, d + 1, 50) for d in dims], 1)
+    assert rel_err(engs[1][0].predict(engs[1][2], tids), orc.pred(tids, U, mean)) <= 1e-12
+    for mode in (0, 1):
+        Z = rng.standard_normal((dims[mode], D))
+        got = U[mode].copy()
+        for r, (eng, ents, rel) in enumerate(engs):
+            eng.set_factors(ents[mode], U[mode])
+            eng.sample_mode(ents[mode], mu, Lambda, Z)
+            mine = owner[mode] == r
+            got[mine] = eng.get_factors(ents[mode])[mine]
+        Uo = [u.copy() for u in U]
+        orc.sample_latent_all(idf, mode, Uo, 2.0, mean, mu, Lambda, Z)
+        assert rel_err(got, Uo[mode]) <= TOL
+        # Philox: the noise of a row does not depend on which rank / slot holds it
+        eng0, ents0, _ = engs[0]
+        Zp = eng0.debug_row_noise(ents0[mode], 0)
+        got = U[mode].copy()
+        for r, (eng, ents, rel) in enumerate(engs):
+            eng.set_factors(ents[mode], U[mode])
+            eng.sample_mode(ents[mode], mu, Lambda, None)
+            mine = owner[mode] == r
+            got[mine] = eng.get_factors(ents[mode])[mine]
+            eng.set_factors(ents[mode], U[mode])
+        Uo = [u.copy() for u in U]
+        orc.sample_latent_all(idf, mode, Uo, 2.0, mean, mu, Lambda, Zp)
+        assert rel_err(got, Uo[mode]) <= TOL
+    for eng, _, _ in engs:
+        eng.close()

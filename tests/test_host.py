@@ -131,3 +131,19 @@ def test_shard_plan_is_the_reference_cyclic_split():
             assert np.array_equal(np.sort(slots[rows[r]]), np.arange(r * plan.nper, r * plan.nper + len(rows[r])))
         U = np.random.default_rng(0).standard_normal((count, 3))
         assert np.array_equal(plan.from_slots(plan.to_slots(U)), U)
+
+
+def test_balanced_partition_levels_heavy_tailed_work():
+    from bdf_b200.shard import balanced_partition
+
+    rng = np.random.default_rng(0)
+    n, nnz = 2000, 400_000
+    deg = np.bincount(np.minimum((n * rng.random(nnz) ** 2.5).astype(np.int64), n - 1), minlength=n)
+    for world in (1, 2, 8):
+        r = balanced_partition(deg, world, row_cost=20.0)
+        assert r.shape == (n,) and r.min() >= 0 and r.max() < world
+        load = np.bincount(r, weights=deg + 20.0, minlength=world)
+        assert load.max() / load.mean() < 1.01
+        cyc = np.bincount(np.arange(n) % world, weights=deg + 20.0, minlength=world)
+        if world == 8:
+            assert cyc.max() / cyc.mean() > 1.05  # the cyclic deal is what it fixes

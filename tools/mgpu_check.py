@@ -23,11 +23,17 @@ ids = np.stack([np.minimum((n1 * rng.random(nnz) ** 2.5).astype(np.int64), n1 - 
 vals = rng.standard_normal(nnz)
 
 
-def run(r, w, fused=True):
+def run(r, w, fused=True, balanced=False):
     eng = bdf_b200.Engine(D, device=local, rank=r, world=w)
     eng.set_stream(stream.cuda_stream)
     eng.set_seed(7)
-    e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
+    if balanced and w > 1:
+        from bdf_b200.shard import balanced_partition
+
+        e1 = eng.add_entity_partitioned(n1, balanced_partition(np.bincount(ids[:, 0] - 1, minlength=n1), w, 2.0 * D))
+        e2 = eng.add_entity_partitioned(n2, balanced_partition(np.bincount(ids[:, 1] - 1, minlength=n2), w, 2.0 * D))
+    else:
+        e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
     rel = eng.add_relation([e1, e2], ids, vals)
     eng.set_relation_params(rel, 1.5, float(vals.mean()))
     ds = DistributedSweep(eng, [e1, e2], fused_allgather=fused) if w > 1 else None
@@ -45,12 +51,17 @@ multi = run(rank, world, fused=True)
 dist.barrier()
 multi_nccl = run(rank, world, fused=False)
 dist.barrier()
+multi_bal = run(rank, world, fused=True, balanced=True)
+dist.barrier()
 if rank == 0:
     single = run(0, 1)
     errs = [float(np.max(np.abs(a - b)) / np.max(np.abs(b))) for a, b in zip(multi[:2], single[:2])]
     errs += [float(np.max(np.abs(multi[k][1] - single[k][1])) / np.max(np.abs(single[k][1]))) for k in (2, 3)]
     print(f"world={world} D={D}: rel err of factors/hyper vs 1-GPU run:", errs)
     assert max(errs) < 1e-9, errs
+    errs_b = [float(np.max(np.abs(multi_bal[k] - single[k])) / np.max(np.abs(single[k]))) for k in (0, 1)]
+    print(f"   work-balanced shard map vs 1-GPU run:", errs_b)
+    assert max(errs_b) < 1e-9, errs_b
     assert all(np.array_equal(a, b) for a, b in zip(multi[:2], multi_nccl[:2])), "fused all-gather differs from the NCCL all-gather"
     print("MGPU OK (fused peer-store all-gather == NCCL all-gather == 1 GPU)")
 dist.barrier()
