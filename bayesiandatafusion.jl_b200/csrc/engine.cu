@@ -222,9 +222,9 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector
   for (auto* rp : rps) total += (*rp)[real_rows] - (*rp)[0];
   const int64_t CH = std::min<int64_t>(8192, std::max<int64_t>(1024, (total / 4096 + 15) / 16 * 16));
   const bool multi = rps.size() > 1;
-  std::vector<int32_t> irow, ilen, isplit, ichunk, irel, snch;
-  std::vector<int64_t> ibeg, swoff;
-  int64_t slots = 0;
+  std::vector<int32_t> irow, ilen, isplit, ichunk, irel, snch, sgsize;
+  std::vector<int64_t> ibeg, swoff, sgcoff;
+  int64_t slots = 0, groups = 0;
   struct Piece { int64_t beg, len; int rel; };
   std::vector<Piece> pieces;
   for (int64_t r = 0; r < real_rows; r++) {
@@ -242,9 +242,15 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector
     if (pieces.empty()) pieces.push_back({(*rps[0])[r], 0, 0});  // no observations anywhere: the row is drawn from the prior
     const int sid = pieces.size() > 1 ? (int)snch.size() : -1;
     if (sid >= 0) {
-      snch.push_back((int32_t)pieces.size());
+      const int64_t nch = (int64_t)pieces.size();
+      // partials are added up in two levels once a row has many of them: groups of ~sqrt(nch) consecutive chunks
+      const int64_t G = nch <= 32 ? nch : (int64_t)std::ceil(std::sqrt((double)nch));
+      snch.push_back((int32_t)nch);
       swoff.push_back(slots);
-      slots += (int64_t)pieces.size();
+      sgsize.push_back((int32_t)G);
+      sgcoff.push_back(groups);
+      slots += nch;
+      groups += (nch + G - 1) / G;
     }
     for (size_t c = 0; c < pieces.size(); c++) {
       irow.push_back((int32_t)r); ibeg.push_back(pieces[c].beg); ilen.push_back((int32_t)pieces[c].len);
@@ -260,7 +266,8 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector
   permute32(irow); permute32(ilen); permute32(isplit); permute32(ichunk); permute32(irel); permute64(ibeg);
   mi.n_items = (int)ni;
   mi.n_split = (int)snch.size();
-  mi.ws_slots = slots;
+  mi.chunk_slots = slots;
+  mi.ws_slots = slots + groups;
   int rc;
   if ((rc = dev_alloc(h, &mi.item_row, ni))) return rc;
   if ((rc = dev_alloc(h, &mi.item_beg, ni))) return rc;
@@ -271,6 +278,9 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector
   if ((rc = dev_alloc(h, &mi.split_nchunks, snch.size()))) return rc;
   if ((rc = dev_alloc(h, &mi.split_wsoff, snch.size()))) return rc;
   if ((rc = dev_alloc(h, &mi.split_counter, snch.size()))) return rc;
+  if ((rc = dev_alloc(h, &mi.split_gsize, snch.size()))) return rc;
+  if ((rc = dev_alloc(h, &mi.split_gcoff, snch.size()))) return rc;
+  if ((rc = dev_alloc(h, &mi.group_counter, (size_t)groups))) return rc;
   if (ni) {
     CU(cudaMemcpyAsync(mi.item_row, irow.data(), ni * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(mi.item_beg, ibeg.data(), ni * 8, cudaMemcpyHostToDevice, h->stream));
@@ -282,15 +292,19 @@ int build_work_list(bdf_t* h, ModeIndex& mi, const std::vector<const std::vector
   if (!snch.empty()) {
     CU(cudaMemcpyAsync(mi.split_nchunks, snch.data(), snch.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(mi.split_wsoff, swoff.data(), swoff.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.split_gsize, sgsize.data(), sgsize.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mi.split_gcoff, sgcoff.data(), sgcoff.size() * 8, cudaMemcpyHostToDevice, h->stream));
   }
+  CU(cudaMemsetAsync(mi.group_counter, 0, std::max<size_t>(1, (size_t)groups) * sizeof(int), h->stream));
   CU(cudaMemsetAsync(mi.split_counter, 0, std::max<size_t>(1, snch.size()) * sizeof(int), h->stream));
   CU(cudaStreamSynchronize(h->stream));  // host vectors die here
-  return ensure_ws(h, std::max<size_t>(sizeof(double) * (size_t)slots * h->pst, sizeof(double) * 296 * (size_t)tri(h->D + 1)));
+  return ensure_ws(h, std::max<size_t>(sizeof(double) * (size_t)(slots + groups) * h->pst, sizeof(double) * 296 * (size_t)tri(h->D + 1)));
 }
 
 void free_work_list(ModeIndex& mi) {
   cudaFree(mi.item_row); cudaFree(mi.item_beg); cudaFree(mi.item_len); cudaFree(mi.item_split); cudaFree(mi.item_chunk); cudaFree(mi.item_rel);
-  cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter);
+  cudaFree(mi.split_nchunks); cudaFree(mi.split_wsoff); cudaFree(mi.split_counter); cudaFree(mi.split_gsize); cudaFree(mi.split_gcoff); cudaFree(mi.group_counter);
+  mi.split_gsize = nullptr; mi.split_gcoff = nullptr; mi.group_counter = nullptr;
   mi.item_row = mi.item_len = mi.item_split = mi.item_chunk = mi.item_rel = mi.split_nchunks = nullptr;
   mi.item_beg = mi.split_wsoff = nullptr;
   mi.split_counter = nullptr;
@@ -321,6 +335,7 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
   p.item_row = wl->item_row; p.item_beg = wl->item_beg; p.item_len = wl->item_len; p.item_split = wl->item_split; p.item_chunk = wl->item_chunk;
   p.item_rel = wl->item_rel;
   p.split_nchunks = wl->split_nchunks; p.split_wsoff = wl->split_wsoff; p.split_counter = wl->split_counter; p.ws = h->ws;
+  p.split_gsize = wl->split_gsize; p.split_gcoff = wl->split_gcoff; p.group_counter = wl->group_counter; p.gslot_base = wl->chunk_slots;
   bool tensor = false;
   for (auto& u : e.uses) tensor = tensor || h->rels[u.first].K > 2;
   for (size_t i = 0; i < e.uses.size(); i++) {

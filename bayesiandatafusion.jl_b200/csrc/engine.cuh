@@ -28,6 +28,10 @@ struct ModeIndex {            // one mode of one relation, restricted to the row
   int32_t* split_nchunks = nullptr;
   int64_t* split_wsoff = nullptr;
   int* split_counter = nullptr;
+  int32_t* split_gsize = nullptr;   // two-level reduction of the partials: chunks per group, first group index, group counters
+  int64_t* split_gcoff = nullptr;
+  int* group_counter = nullptr;
+  int64_t chunk_slots = 0;          // workspace slots taken by chunk partials; the group partials follow
   int64_t ws_slots = 0;
   std::vector<int64_t> h_row_ptr;  // host copy of row_ptr (merged work lists are built from it)
 };

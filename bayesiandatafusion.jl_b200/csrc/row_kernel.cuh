@@ -75,7 +75,11 @@ struct RowParams {
   const int32_t* item_chunk;  // chunk number within the split row
   const int32_t* split_nchunks;
   const int64_t* split_wsoff;  // first partial slot of the split row
-  int* split_counter;          // arrival counters (self-resetting)
+  const int32_t* split_gsize;  // chunks per reduction group of the split row
+  const int64_t* split_gcoff;  // first group counter / group-partial slot of the split row
+  int64_t gslot_base;          // workspace slot of group partial 0 (the group partials follow all chunk partials)
+  int* group_counter;          // arrival counters of the groups (self-resetting)
+  int* split_counter;          // arrival counters of the rows' groups (self-resetting)
   double* ws;                  // partial workspace
   // observations of this mode, one table entry per relation the entity takes part in (src/sampling.jl:266-283 sums the
   // relations' contributions); item_rel[item] picks the entry, nullptr = entry 0 for every item
@@ -452,38 +456,59 @@ struct RowKernel {
     __syncthreads();  // the ring is dead from here on
 
     BDF_STAMP(2);
-    // ---- split rows: park the partial, last arriver reduces in chunk order -------------------------------
+    // ---- split rows: park the partial; the last item of a GROUP of consecutive chunks adds the group's partials in chunk order, and
+    //      (rows with many chunks) parks the group sum, the last group then adds the group sums in group order. Two levels keep the
+    //      serial part short — a row with 2M observations has hundreds of 46 KB partials — and the order fixed (deterministic). ------
     if (split >= 0) {
       const int nch = p.split_nchunks[split];
-      double* part = p.ws + (size_t)(p.split_wsoff[split] + p.item_chunk[item]) * PST;
-#pragma unroll
-      for (int t = 0; t < TPW; t++)
-        *reinterpret_cast<double2*>(part + ((size_t)(warp * TPW + t) * 32 + lane) * 2) = make_double2(rt.alpha * acc[t][0], rt.alpha * acc[t][1]);
-      if (tid < DP) part[NW * TPW * 64 + tid] = rt.alpha * bsum;
-      __threadfence();
-      __syncthreads();
+      const int G = p.split_gsize[split];  // chunks per group
+      const int ng = (nch + G - 1) / G;
+      const int c = p.item_chunk[item], g = c / G;
+      const int gsz = (g == ng - 1) ? nch - g * G : G;
+      const int64_t gc = p.split_gcoff[split] + g;  // this group's counter / partial slot
       __shared__ int s_last;
-      if (tid == 0) {
-        const int old = atomicAdd(p.split_counter + split, 1);
-        s_last = (old == nch - 1);
-        if (s_last) p.split_counter[split] = 0;
-      }
-      __syncthreads();
-      if (!s_last) return;
-      __threadfence();
+      auto park = [&](double* part, double sc) {
 #pragma unroll
-      for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
-      bsum = 0.0;
-      const double* base = p.ws + (size_t)p.split_wsoff[split] * PST;
-      for (int c = 0; c < nch; c++) {
-        const double* pc = base + (size_t)c * PST;
-#pragma unroll
-        for (int t = 0; t < TPW; t++) {
-          const double2 v = __ldcg(reinterpret_cast<const double2*>(pc + ((size_t)(warp * TPW + t) * 32 + lane) * 2));
-          acc[t][0] += v.x;
-          acc[t][1] += v.y;
+        for (int t = 0; t < TPW; t++)
+          *reinterpret_cast<double2*>(part + ((size_t)(warp * TPW + t) * 32 + lane) * 2) = make_double2(sc * acc[t][0], sc * acc[t][1]);
+        if (tid < DP) part[NW * TPW * 64 + tid] = sc * bsum;
+        __threadfence();
+        __syncthreads();
+      };
+      auto arrive = [&](int* counter, int expect) {  // true for the last arriver (which also resets the counter)
+        if (tid == 0) {
+          const int old = atomicAdd(counter, 1);
+          s_last = (old == expect - 1);
+          if (s_last) *counter = 0;
         }
-        if (tid < DP) bsum += __ldcg(pc + NW * TPW * 64 + tid);
+        __syncthreads();
+        const bool last = s_last;
+        __syncthreads();
+        if (last) __threadfence();
+        return last;
+      };
+      auto add_up = [&](const double* base, int n) {
+#pragma unroll
+        for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
+        bsum = 0.0;
+        for (int k = 0; k < n; k++) {
+          const double* pc = base + (size_t)k * PST;
+#pragma unroll
+          for (int t = 0; t < TPW; t++) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(pc + ((size_t)(warp * TPW + t) * 32 + lane) * 2));
+            acc[t][0] += v.x;
+            acc[t][1] += v.y;
+          }
+          if (tid < DP) bsum += __ldcg(pc + NW * TPW * 64 + tid);
+        }
+      };
+      park(p.ws + (size_t)(p.split_wsoff[split] + c) * PST, rt.alpha);
+      if (!arrive(p.group_counter + gc, gsz)) return;
+      add_up(p.ws + (size_t)(p.split_wsoff[split] + (int64_t)g * G) * PST, gsz);
+      if (ng > 1) {
+        park(p.ws + (size_t)(p.gslot_base + gc) * PST, 1.0);
+        if (!arrive(p.split_counter + split, ng)) return;
+        add_up(p.ws + (size_t)(p.gslot_base + p.split_gcoff[split]) * PST, ng);
       }
     }
 
