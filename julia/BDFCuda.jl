@@ -118,4 +118,32 @@ function predict(h::Handle, rel, ids::Matrix{Int64})
   return yhat
 end
 
+## Entity(F = ::Matrix{Float64}) — a dense feature matrix
+set_features_dense(h::Handle, entity, F::Matrix{Float64}) =
+  check(h, ccall((:bdf_set_features_dense, LIB), Cint, (Ptr{Void}, Cint, Int64, Int64, Ptr{Cdouble}), h.ptr, entity, size(F, 1), size(F, 2), F))
+
+## reset!: en.FF = full(At_mul_B(en.F, en.F)); en.use_FF = true — src/RelationData.jl:337-339; sample_beta then takes solve_full
+compute_ff!(h::Handle, entity) = check(h, ccall((:bdf_compute_ff, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, entity, C_NULL))
+set_use_ff!(h::Handle, entity, use_ff::Bool) = check(h, ccall((:bdf_set_use_ff, LIB), Cint, (Ptr{Void}, Cint, Cint), h.ptr, entity, use_ff))
+
+## solve_full(FF, rhs, lambda) — src/sampling.jl:314-320
+function solve_full(h::Handle, entity, rhs::Matrix{Float64}, lambda)
+  x = zeros(size(rhs))
+  check(h, ccall((:bdf_solve_full, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ptr{Cdouble}), h.ptr, entity, rhs, size(rhs, 2), lambda, x))
+  return x
+end
+
+## sample_alpha — src/macau.jl:84-88: err'err on the device, then the 1x1 Wishart draw (chi2 = injected variate or NaN for Philox)
+function sample_alpha!(h::Handle, rel, alpha_lambda0, alpha_nu0; chi2 = NaN)
+  sse = Ref{Cdouble}(0.0); n = Ref{Int64}(0); alpha = Ref{Cdouble}(0.0)
+  check(h, ccall((:bdf_train_sse, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Int64}), h.ptr, rel, sse, n))
+  check(h, ccall((:bdf_sample_alpha, LIB), Cint, (Ptr{Void}, Cint, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}),
+                 h.ptr, rel, alpha_lambda0, alpha_nu0, sse[], Float64(n[]), chi2, alpha))
+  return alpha[]
+end
+
+## an entity with an explicit (e.g. work-balanced) shard map instead of the cyclic i:Nprocs:N deal; rank_of_row is 0-based
+add_entity_partitioned(h::Handle, count::Integer, rank_of_row::Vector{Int32}) =
+  check(h, ccall((:bdf_add_entity_partitioned, LIB), Cint, (Ptr{Void}, Int64, Ptr{Int32}), h.ptr, count, rank_of_row))
+
 end # module
