@@ -36,6 +36,7 @@ SIGNATURES = {
     "bdf_solve_full": (C.c_int, [H, C.c_int, c_dp, C.c_int, C.c_double, c_dp]),
     "bdf_step_nw_draw_on": (C.c_int, [H, C.c_int, C.c_void_p]),
     "bdf_add_entity_partitioned": (C.c_int, [H, C.c_int64, c_i32p]),
+    "bdf_predict_all": (C.c_int, [H, C.c_int, c_dp]),
     "bdf_train_sse": (C.c_int, [H, C.c_int, c_dp, c_i64p]),
     "bdf_sample_alpha": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_dp]),
     "bdf_sample_mode": (C.c_int, [H, C.c_int, c_dp, C.c_int64, c_dp, c_dp]),

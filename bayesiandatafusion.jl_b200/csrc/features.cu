@@ -711,6 +711,38 @@ static int solve_full_dev(bdf_t* h, EntityS& e, const double* B, double* X, doub
   return BDF_OK;
 }
 
+// pred_all(r) = udot_all(r) + mean_value — src/sampling.jl:72-97, matrix relations: sample_1' * sample_2 as one dgemm
+__global__ void add_scalar_kernel(double* __restrict__ A, int64_t n, double v) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) A[e] += v;
+}
+
+extern "C" int bdf_predict_all(bdf_t* h, int rel, double* out) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  if (!out) FAIL(BDF_ERR_INVALID, "null argument");
+  RelationS& r = h->rels[rel];
+  if (r.K != 2) FAIL(BDF_ERR_INVALID, "pred_all is implemented for 2-mode relations (the reference's tensor version enumerates every cell)");
+  if (h->world != 1) FAIL(BDF_ERR_INVALID, "pred_all runs on one GPU");
+  EntityS& a = h->ents[r.entity_of_mode[0]];
+  EntityS& b = h->ents[r.entity_of_mode[1]];
+  if (a.slot_of_row || b.slot_of_row) FAIL(BDF_ERR_INVALID, "pred_all needs the default row order");
+  CU(cudaSetDevice(h->device));
+  int rc = dense_handles(h);
+  if (rc) return rc;
+  const size_t n = (size_t)a.N * b.N;
+  if ((rc = bdf_ensure_arena(h, sizeof(double) * n))) return rc;
+  double* Y = reinterpret_cast<double*>(h->arena);
+  const double one = 1.0, zero = 0.0;
+  // factor buffers are row-major N × ld = column-major ld × N: Y (N1 × N2, column-major) = U1·U2ᵀ
+  if (cublasDgemm((cublasHandle_t)h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)a.N, (int)b.N, h->D, &one, a.U, h->ld, b.U, h->ld, &zero, Y, (int)a.N) != CUBLAS_STATUS_SUCCESS)
+    FAIL(BDF_ERR_CUDA, "cublasDgemm failed");
+  add_scalar_kernel<<<grid_for((int64_t)n), 256, 0, h->stream>>>(Y, (int64_t)n, r.mean);
+  h->launches += 2;
+  CU(cudaMemcpyAsync(out, Y, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
 extern "C" int bdf_set_features_dense(bdf_t* h, int entity, int64_t m, int64_t n, const double* F) {
   CHECK_H(); CHECK_ENT(entity);
   if (!F || m < 1 || n < 1) FAIL(BDF_ERR_INVALID, "null or empty feature matrix");

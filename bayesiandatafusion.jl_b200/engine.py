@@ -336,6 +336,12 @@ class Engine:
         self._ck(self.lib.bdf_debug_phase_clocks(self.h, entity, _dp(out), C.byref(n)))
         return dict(zip(["setup", "syrk", "split", "build", "factor", "solve", "total"], out)), n.value
 
+    def predict_all(self, rel: int, shape):
+        """pred_all(r) — src/sampling.jl:92-97: every cell of a 2-mode relation, (N1, N2)."""
+        out = np.zeros(shape, order="F")
+        self._ck(self.lib.bdf_predict_all(self.h, rel, _dp(out)))
+        return out
+
     def train_sse(self, rel: int):
         """err'err of src/macau.jl:86 over this rank's share of the training table; returns (sse, count)."""
         sse = C.c_double()

@@ -15,6 +15,7 @@ from typing import Callable, Optional
 
 import numpy as np
 
+from .data_reading import write_binary_matrix
 from .engine import Engine
 from .relation_data import RelationData
 
@@ -63,7 +64,8 @@ def bartlett_factor(rng: np.random.Generator, D: int, nu: float):
 
 def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.nan, burnin: int = 500, psamples: int = 200,
           verbose: bool = True, full_lambda_u: bool = True, reset_model: bool = True, compute_ff_size: int = 6500,
-          tol: float = math.nan, output: str = "", clamp=(), f: Optional[Callable] = None, rmse_train: bool = False,
+          tol: float = math.nan, output: str = "", output_beta: bool = False, output_type: str = "binary", full_prediction: bool = False,
+          clamp=(), f: Optional[Callable] = None, rmse_train: bool = False,
           backend: str = "cuda", device: int = 0, seed: int = 0, host_noise: Optional[np.random.Generator] = None,
           engine: Optional[Engine] = None):
     """Same keywords as src/macau.jl:3-22 where they apply to this path, plus the switch flag `backend` (only "cuda"
@@ -109,6 +111,7 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
     probe_rat_all = np.zeros(ntest)
     probe_stdev = np.zeros(ntest)
     counter_prob = 1
+    yhat_full = np.zeros(tuple(rel.data.dims), order="F") if full_prediction else None
     rmse_avg = roc_avg = err_avg = math.nan
     f_output = []
     if math.isnan(tol):
@@ -160,10 +163,23 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         probe_rat = eng.predict(r_id, rel.test_ids) if ntest else np.zeros(0)
         if i > burnin:
             if output:
+                # saving latent vectors to disk — src/macau.jl:149-162 (Float32, num_latent × count as Julia holds model.sample)
+                if output_type not in ("binary", "csv"):
+                    raise ValueError('output_type must be "binary" or "csv"')
+                ndigits = int(math.floor(math.log10(psamples))) + 1
+                nstr = str(i - burnin).rjust(ndigits, "0")
                 for e, en in zip(ents, data.entities):
-                    ndigits = int(math.floor(math.log10(psamples))) + 1
-                    nstr = str(i - burnin).rjust(ndigits, "0")
-                    write_binary_matrix(f"{output}-{en.name}-{nstr}.binary", eng.get_factors(e).astype(np.float32))
+                    dumps = [("", eng.get_factors(e).T)]
+                    if output_beta and en.hasFeatures():
+                        dumps.append((".beta", eng.get_beta(e)))
+                    for tag, X in dumps:
+                        X32 = np.asarray(X, dtype=np.float32)
+                        if output_type == "binary":
+                            write_binary_matrix(f"{output}-{en.name}-{nstr}{tag}.binary", X32)
+                        else:
+                            np.savetxt(f"{output}-{en.name}-{nstr}{tag}.csv", X32, delimiter=",", fmt="%.9g")
+            if full_prediction:
+                yhat_full += eng.predict_all(r_id, tuple(rel.data.dims))  # pred_all — src/macau.jl:145-146
             if i == burnin + 1:
                 if verbose:
                     print("--------- Burn-in complete, averaging posterior samples ----------")
@@ -215,6 +231,8 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             train_count[:, m] = cnt[rel.test_ids[:, m]]
         result["predictions"] = {"ids": rel.test_ids.copy(), "values": rel.test_values.copy(), "pred": pred, "stdev": stdev}
         result["train_counts"] = train_count
+    if full_prediction:
+        result["predictions_full"] = yhat_full / psamples  # src/macau.jl:228-230
     if rmse_train:
         tr = eng.predict(r_id, rel.data.ids)
         result["RMSE_train"] = float(np.sqrt(np.mean((rel.data.values - makeClamped(tr, clamp)) ** 2)))
@@ -224,18 +242,3 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
     if engine is None:
         eng.close()
     return result
-
-
-def write_binary_matrix(filename: str, X: np.ndarray):
-    """src/data_reading.jl:93-99 — Int64 nrows, Int64 ncols, column-major payload. X is (count, num_latent) C-order,
-    i.e. the num_latent × count column-major matrix the reference writes."""
-    with open(filename, "wb") as fh:
-        np.array([X.shape[1], X.shape[0]], dtype=np.int64).tofile(fh)
-        np.ascontiguousarray(X).tofile(fh)
-
-
-def read_binary_float32(filename: str) -> np.ndarray:
-    """src/data_reading.jl:61-67. Returns (ncols, nrows) C-order = nrows × ncols column-major."""
-    with open(filename, "rb") as fh:
-        nrows, ncols = np.fromfile(fh, dtype=np.int64, count=2)
-        return np.fromfile(fh, dtype=np.float32, count=int(nrows * ncols)).reshape(int(ncols), int(nrows))

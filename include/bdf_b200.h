@@ -135,6 +135,10 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
 int bdf_train_sse(bdf_t* h, int rel, double* sse, int64_t* count);
 int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, double sse, double count, double chi2_variate, double* alpha_out);
 
+/* pred_all(r) = udot_all(r) + mean_value — src/sampling.jl:72-97, used by macau(full_prediction = true), src/macau.jl:145-146: every cell of a
+ * 2-mode relation, out is N1 × N2 column-major (cuBLAS dgemm of the two factor matrices; one GPU). */
+int bdf_predict_all(bdf_t* h, int rel, double* out);
+
 /* ---- Macau side features: the link-matrix (beta) path ------------------------------------------------------------- */
 
 /* Entity(F = SparseBinMatrix(m, n, rows, cols)) — src/parallel_matrix.jl:9-24: registers a sparse 0/1 feature matrix given

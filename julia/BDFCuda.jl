@@ -146,4 +146,11 @@ end
 add_entity_partitioned(h::Handle, count::Integer, rank_of_row::Vector{Int32}) =
   check(h, ccall((:bdf_add_entity_partitioned, LIB), Cint, (Ptr{Void}, Int64, Ptr{Int32}), h.ptr, count, rank_of_row))
 
+## pred_all(r) — src/sampling.jl:92-97 (macau(full_prediction = true), src/macau.jl:145-146)
+function predict_all(h::Handle, rel, n1::Integer, n2::Integer)
+  out = zeros(n1, n2)
+  check(h, ccall((:bdf_predict_all, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, rel, out))
+  return out
+end
+
 end # module

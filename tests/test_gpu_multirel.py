@@ -161,3 +161,40 @@ def test_macau_with_two_relations_and_alpha_sampling():
     assert np.isfinite(res["RMSE"]) and res["RMSE"] < 0.45 * base
     # the sampled precisions settle near the planted noise level 1/0.3^2 ≈ 11
     assert 6.0 < r1.model.alpha < 18.0 and 6.0 < r2.model.alpha < 18.0
+
+
+def test_pred_all_full_prediction_and_output_dumps(tmp_path):
+    """pred_all (src/sampling.jl:72-97, test/basic.jl:168-174 identity: pred_all[i, j] == pred of that cell), macau(full_prediction,
+    output, output_beta) — src/macau.jl:145-162, 228-230."""
+    import scipy.sparse as sp
+
+    import bdf_b200
+    from bdf_b200 import data_reading as dr
+
+    rng = np.random.default_rng(8)
+    N, M, D = 40, 25, 6
+    U, V = rng.standard_normal((N, D)), rng.standard_normal((M, D))
+    eng = bdf_b200.Engine(D)
+    e1, e2 = eng.add_entity(N), eng.add_entity(M)
+    ids = np.stack([rng.integers(1, N + 1, 200), rng.integers(1, M + 1, 200)], 1)
+    rel = eng.add_relation([e1, e2], ids, rng.standard_normal(200))
+    eng.set_relation_params(rel, 2.0, 0.25)
+    eng.set_factors(e1, U)
+    eng.set_factors(e2, V)
+    full = eng.predict_all(rel, (N, M))
+    assert rel_err(full, U @ V.T + 0.25) <= 1e-13
+    cells = np.stack([rng.integers(1, N + 1, 30), rng.integers(1, M + 1, 30)], 1)
+    assert rel_err(full[cells[:, 0] - 1, cells[:, 1] - 1], eng.predict(rel, cells)) <= 1e-13
+    eng.close()
+    # driver level
+    F = sp.random(N, 9, 0.4, random_state=4, format="csc")
+    F.data[:] = 1.0
+    Y = sp.csc_matrix(np.where(rng.random((N, M)) < 0.4, U[:, :2] @ V[:, :2].T, 0.0))
+    rd = bdf_b200.RelationData(Y, feat1=F, class_cut=0.0, alpha=5.0)
+    out = str(tmp_path / "run")
+    res = bdf_b200.macau(rd, num_latent=4, burnin=3, psamples=4, verbose=False, full_prediction=True, output=out, output_beta=True, seed=2)
+    assert res["predictions_full"].shape == (N, M) and np.all(np.isfinite(res["predictions_full"]))
+    S = dr.read_binary_float32(f"{out}-E1-4.binary")           # the last sample, as Float32, num_latent × count
+    assert S.shape == (4, N) and np.allclose(S.T, rd.entities[0].model.sample, rtol=1e-6, atol=1e-6)
+    B = dr.read_binary_float32(f"{out}-E1-4.beta.binary")
+    assert B.shape == (9, 4) and np.allclose(B, rd.entities[0].model.beta, rtol=1e-6, atol=1e-6)

@@ -82,13 +82,30 @@ def test_auc_clamp_and_binary_io():
     from bdf_b200.macau import makeClamped
 
     assert list(makeClamped(np.array([0.0, 3.0, 9.0]), [1.0, 5.0])) == [1.0, 3.0, 5.0]
-    X = np.arange(12, dtype=np.float32).reshape(4, 3)  # 4 instances × 3 latents
+    # on-disk formats of src/data_reading.jl: Int64 headers, column-major payloads, 1-based Int32 indices
+    from bdf_b200 import data_reading as dr
+
+    X = np.arange(12, dtype=np.float32).reshape(3, 4)     # Julia's model.sample: 3 latents × 4 instances
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "m.binary")
-        bdf_b200.write_binary_matrix(p, X)
-        hdr = np.fromfile(p, dtype=np.int64, count=2)
-        assert list(hdr) == [3, 4]                        # Int64 nrows (latents), ncols (instances): src/data_reading.jl:93-99
-        assert np.array_equal(bdf_b200.read_binary_float32(p), X)
+        dr.write_binary_matrix(p, X)
+        raw = open(p, "rb").read()
+        assert list(np.frombuffer(raw[:16], dtype="<i8")) == [3, 4]          # nrows, ncols — src/data_reading.jl:93-99
+        assert np.array_equal(np.frombuffer(raw[16:], dtype="<f4"), X.T.ravel())  # column-major payload
+        assert np.array_equal(dr.read_binary_float32(p), X)
+        dr.write_binary_matrix(p, X.astype(np.int32))
+        assert np.array_equal(dr.read_binary_int32(p), X.astype(np.int32))
+        M = sp.random(9, 7, 0.3, random_state=2, format="csc")
+        dr.write_sparse_float64(p, M)
+        assert (dr.read_sparse_float64(p) != M).nnz == 0
+        dr.write_sparse_float32(p, M)
+        r, c, v = dr.read_sparse_float32(p)
+        assert np.array_equal(sp.csc_matrix((v, (r - 1, c - 1)), shape=M.shape).toarray(), M.astype(np.float32).toarray())
+        dr.write_sparse_binary_matrix(p, M)
+        hdr = np.fromfile(p, dtype="<i8", count=3)
+        assert list(hdr) == [9, 7, M.nnz]                                    # src/data_reading.jl:122-132
+        F = dr.read_sparse_binary_matrix(p)
+        assert F.shape == (9, 7) and np.array_equal(sp.csc_matrix((np.ones(len(F.rows)), (F.rows - 1, F.cols - 1)), shape=F.shape).toarray(), (M != 0).toarray())
 
 
 def test_macau_rejects_what_is_not_on_the_device_path():
