@@ -37,6 +37,11 @@ SIGNATURES = {
     "bdf_step_nw_draw_on": (C.c_int, [H, C.c_int, C.c_void_p]),
     "bdf_add_entity_partitioned": (C.c_int, [H, C.c_int64, c_i32p]),
     "bdf_predict_all": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_set_relation_features": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, c_dp]),
+    "bdf_sample_beta_rel": (C.c_int, [H, C.c_int, C.c_double, c_dp, c_dp, c_dp]),
+    "bdf_get_relation_beta": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_set_relation_beta": (C.c_int, [H, C.c_int, c_dp]),
+    "bdf_predict_f": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp, c_dp]),
     "bdf_train_sse": (C.c_int, [H, C.c_int, c_dp, c_i64p]),
     "bdf_sample_alpha": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_dp]),
     "bdf_sample_mode": (C.c_int, [H, C.c_int, c_dp, C.c_int64, c_dp, c_dp]),

@@ -342,10 +342,11 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
     RelationS& rel = h->rels[e.uses[i].first];
     ModeIndex& mi = rel.modes[e.uses[i].second];
     RelTab& t = p.rt[i];
-    t.col0 = mi.col[0]; t.col1 = rel.K > 2 ? mi.col[1] : nullptr; t.val = mi.val;
+    t.col0 = mi.col[0]; t.col1 = rel.K > 2 ? mi.col[1] : nullptr;
+    t.val = rel.F ? mi.val_adj : mi.val;  // with relation features the offset is per observation: linear_values[getI(...)], src/sampling.jl:273
     t.P0 = h->ents[mi.other_entity[0]].U;
     t.P1 = rel.K > 2 ? h->ents[mi.other_entity[1]].U : (tensor ? h->ones : nullptr);
-    t.alpha = rel.alpha; t.mean = rel.mean;
+    t.alpha = rel.alpha; t.mean = rel.F ? 0.0 : rel.mean;
   }
   p.ld = h->ld; p.Uout = e.U; p.slot_base = (int64_t)h->rank * e.Nper; p.row_of_slot = e.row_of_slot;
   { int np = 0; for (int r = 0; r < 8; r++) if (e.peerU[r]) p.peer_out[np++] = e.peerU[r]; }
@@ -395,6 +396,32 @@ __global__ void sse_items_kernel(const int32_t* __restrict__ item_row, const int
   if (lane == 0) partial[item] = acc;
 }
 
+// res[perm[o]] = value − udot − mean for every training observation (table order) — the residual of sample_beta_rel, src/sampling.jl:327
+__global__ void residual_items_kernel(const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_beg, const int32_t* __restrict__ item_len,
+                                      int n_items, const int32_t* __restrict__ col0, const int32_t* __restrict__ col1, const double* __restrict__ val,
+                                      const uint32_t* __restrict__ perm, const double* __restrict__ U, const double* __restrict__ P0,
+                                      const double* __restrict__ P1, int64_t slot_base, int ld, int D, double mean, double* __restrict__ res) {
+  const int lane = threadIdx.x & 31;
+  const int item = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (item >= n_items) return;
+  const double* u = U + (size_t)(slot_base + item_row[item]) * ld;
+  const int64_t b = item_beg[item];
+  const int n = item_len[item];
+  for (int o = 0; o < n; o++) {
+    const double* p0 = P0 + (size_t)__ldg(col0 + b + o) * ld;
+    const double* p1 = P1 ? P1 + (size_t)__ldg(col1 + b + o) * ld : nullptr;
+    double s = 0.0;
+    for (int k = lane; k < D; k += 32) {
+      double t = u[k] * __ldg(p0 + k);
+      if (p1) t *= __ldg(p1 + k);
+      s += t;
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+    if (lane == 0) res[perm[b + o]] = __ldg(val + b + o) - s - mean;
+  }
+}
+
 // out[0] = Σ partial (fixed order: thread-strided sums, then a tree over the block), out[1] = optional alpha draw
 __global__ void sse_reduce_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
   __shared__ double sh[256];
@@ -421,6 +448,22 @@ __global__ void alpha_draw_kernel(double sse, double n, double lambda0, double n
 
 }  // namespace
 
+// residuals of relation `rel` in table order into r.res (world == 1)
+int bdf_relation_residuals(bdf_t* h, int rel) {
+  RelationS& r = h->rels[rel];
+  ModeIndex& mi = r.modes[0];
+  EntityS& e = h->ents[r.entity_of_mode[0]];
+  if (mi.n_items > 0) {
+    const int wpb = 8;
+    residual_items_kernel<<<(mi.n_items + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(
+        mi.item_row, mi.item_beg, mi.item_len, mi.n_items, mi.col[0], mi.col[1], mi.val, mi.perm, e.U, h->ents[mi.other_entity[0]].U,
+        r.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr, (int64_t)h->rank * e.Nper, h->ld, h->D, r.mean, r.res);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  return BDF_OK;
+}
+
 // statistics of an arbitrary row-major (rows × ld) buffer into a [count, colsum(D), Gram(D×D)] stats block (features.cu uses it for betaᵀbeta)
 int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, int64_t nrows, double* stats) {
   const int nblk = launch_stats_partials(h, X, sub, slot0, nrows);
@@ -441,6 +484,7 @@ int bdf_ensure_arena(bdf_t* h, size_t bytes) {
 }
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
 void bdf_dense_teardown(bdf_t* h);
+int bdf_refresh_relation_offsets(bdf_t* h, int rel);
 
 namespace {
 
@@ -550,11 +594,15 @@ int bdf_destroy(bdf_t* h) {
     cudaFree(e.f_val_csr); cudaFree(e.f_val_csc); cudaFree(e.f_dense); cudaFree(e.FF);
     free_work_list(e.merged);
   }
+  for (auto& r : h->rels) {
+    cudaFree(r.F); cudaFree(r.FF); cudaFree(r.beta); cudaFree(r.linear); cudaFree(r.res);
+  }
   for (auto& r : h->rels)
     for (int m = 0; m < r.K; m++) {
       ModeIndex& mi = r.modes[m];
       cudaFree(mi.row_ptr); cudaFree(mi.col[0]); cudaFree(mi.col[1]); cudaFree(mi.val);
       free_work_list(mi);
+      cudaFree(mi.perm); cudaFree(mi.val_adj);
     }
   cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->ones); cudaFree(h->arena);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -719,6 +767,8 @@ int bdf_add_relation(bdf_t* h, int K, const int* entity_of_mode, int64_t nnz, co
     }
     TRY(dev_alloc(h, &mi.val, (size_t)std::max<int64_t>(mi.nnz, 1)));
     gather_val_kernel<<<grid_for(mi.nnz), 256, 0, h->stream>>>(idx2, lb[0], mi.nnz, d_vals, mi.val);
+    TRY(dev_alloc(h, &mi.perm, (size_t)std::max<int64_t>(mi.nnz, 1)));
+    if (mi.nnz) CUT(cudaMemcpyAsync(mi.perm, idx2 + lb[0], sizeof(uint32_t) * mi.nnz, cudaMemcpyDeviceToDevice, h->stream));
     CUT(cudaGetLastError());
     std::vector<int64_t> rp((size_t)e.Nper + 1);
     CUT(cudaMemcpyAsync(rp.data(), mi.row_ptr, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -742,6 +792,7 @@ int bdf_set_relation_params(bdf_t* h, int rel, double alpha, double mean_value) 
   if (!(alpha > 0.0)) FAIL(BDF_ERR_INVALID, "alpha must be positive");
   h->rels[rel].alpha = alpha;
   h->rels[rel].mean = mean_value;
+  if (h->rels[rel].F) return bdf_refresh_relation_offsets(h, rel);  // linear_values = mean_value + F·beta moves with the mean
   return BDF_OK;
 }
 
@@ -982,17 +1033,32 @@ int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, in
   return BDF_OK;
 }
 
-int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yhat) {
+// yhat[t] += Σ_f F[t, f]·beta[f] — the `F * r.model.beta` term of pred(r, probe_vec, F), src/sampling.jl:13
+__global__ void add_fbeta_kernel(const double* __restrict__ F, const double* __restrict__ beta, int64_t n, int64_t nF, double* __restrict__ y) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t f = 0; f < nF; f++) s = fma(F[t + f * n], beta[f], s);
+    y[t] += s;
+  }
+}
+
+int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yhat) { return bdf_predict_f(h, rel, ntest, ids, nullptr, yhat); }
+
+int bdf_predict_f(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, const double* test_F, double* yhat) {
   CHECK_H();
   if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
   if (ntest < 0 || (ntest > 0 && (!ids || !yhat))) FAIL(BDF_ERR_INVALID, "null argument");
   if (ntest == 0) return BDF_OK;
   CU(cudaSetDevice(h->device));
   RelationS& r = h->rels[rel];
+  if (r.F && !test_F) FAIL(BDF_ERR_INVALID, "the relation has features: pass the feature rows of the test observations (bdf_predict_f)");
+  if (!r.F && test_F) FAIL(BDF_ERR_INVALID, "the relation has no features");
   // staging lives in a grow-only arena of the handle: no cudaMalloc/cudaFree (both synchronise the device) per call
   const size_t b_ids = sizeof(int64_t) * ntest * r.K, b_s = sizeof(int32_t) * ntest * r.K, b_out = sizeof(double) * ntest;
+  const size_t b_f = test_F ? sizeof(double) * (size_t)ntest * r.nF : 0;
   const size_t off_s = (b_ids + 255) / 256 * 256, off_out = off_s + (b_s + 255) / 256 * 256, off_bad = off_out + (b_out + 255) / 256 * 256;
-  int rc_arena = bdf_ensure_arena(h, off_bad + 256);
+  const size_t off_f = off_bad + 256;
+  int rc_arena = bdf_ensure_arena(h, off_f + b_f + 256);
   if (rc_arena) return rc_arena;
   int64_t* d_ids = reinterpret_cast<int64_t*>(h->arena);
   int32_t* d_s = reinterpret_cast<int32_t*>(h->arena + off_s);
@@ -1008,6 +1074,12 @@ int bdf_predict(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, double* yh
   }
   predict_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(r.K, Us[0], Us[1], Us[2], d_s, d_s + ntest, d_s + 2 * ntest, h->ld, h->D, ntest, r.mean, d_out);
   h->launches += 1 + r.K;
+  if (test_F) {
+    double* d_f = reinterpret_cast<double*>(h->arena + off_f);
+    CU(cudaMemcpyAsync(d_f, test_F, b_f, cudaMemcpyHostToDevice, h->stream));
+    add_fbeta_kernel<<<grid_for(ntest), 256, 0, h->stream>>>(d_f, r.beta, ntest, r.nF, d_out);
+    h->launches++;
+  }
   int bad = 0;
   cudaError_t ce = cudaMemcpyAsync(yhat, d_out, sizeof(double) * ntest, cudaMemcpyDeviceToHost, h->stream);
   cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
@@ -1032,8 +1104,8 @@ int bdf_train_sse(bdf_t* h, int rel, double* sse, int64_t* count) {
   if (mi.n_items > 0) {
     const int wpb = 8;
     sse_items_kernel<<<(mi.n_items + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(
-        mi.item_row, mi.item_beg, mi.item_len, mi.n_items, mi.col[0], mi.col[1], mi.val, e.U, h->ents[mi.other_entity[0]].U,
-        r.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr, (int64_t)h->rank * e.Nper, h->ld, h->D, r.mean, part);
+        mi.item_row, mi.item_beg, mi.item_len, mi.n_items, mi.col[0], mi.col[1], r.F ? mi.val_adj : mi.val, e.U, h->ents[mi.other_entity[0]].U,
+        r.K > 2 ? h->ents[mi.other_entity[1]].U : nullptr, (int64_t)h->rank * e.Nper, h->ld, h->D, r.F ? 0.0 : r.mean, part);
     CU(cudaGetLastError());
   }
   sse_reduce_kernel<<<1, 256, 0, h->stream>>>(part, mi.n_items, out);

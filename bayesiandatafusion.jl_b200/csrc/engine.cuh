@@ -16,6 +16,8 @@ struct ModeIndex {            // one mode of one relation, restricted to the row
   int64_t* row_ptr = nullptr; // [nrows+1] device
   int32_t* col[2] = {nullptr, nullptr};  // partner slot indices per other mode (device)
   double* val = nullptr;
+  uint32_t* perm = nullptr;   // [nnz] position in the relation's observation table of each CSR entry (relation-level features index by it)
+  double* val_adj = nullptr;  // [nnz] val − F·beta_rel (relation with features: the per-observation offset replaces mean_value, src/sampling.jl:273)
   int other_entity[2] = {-1, -1};
   // work list
   int n_items = 0, n_split = 0;
@@ -42,6 +44,13 @@ struct RelationS {
   int64_t nnz = 0;
   double alpha = 1.0, mean = 0.0;
   ModeIndex modes[3];
+  // relation-level features (Relation.F, src/RelationData.jl:127-160): F is nnz × nF column-major in table order
+  int64_t nF = 0;
+  double* F = nullptr;
+  double* FF = nullptr;       // FᵀF, nF × nF (r.temp.FF)
+  double* beta = nullptr;     // nF (r.model.beta)
+  double* linear = nullptr;   // nnz, F·beta without the mean (r.temp.linear_values − mean_value), table order
+  double* res = nullptr;      // nnz work vector (table order)
 };
 
 struct EntityS {

@@ -26,6 +26,8 @@ using namespace bdf;
 
 int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, int64_t nrows, double* stats);
 int bdf_check_err_flag(bdf_t* h);
+int bdf_relation_residuals(bdf_t* h, int rel);
+int bdf_refresh_relation_offsets(bdf_t* h, int rel);
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
 
 namespace {
@@ -741,6 +743,151 @@ extern "C" int bdf_predict_all(bdf_t* h, int rel, double* out) {
   CU(cudaMemcpyAsync(out, Y, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BDF_OK;
+}
+
+// ---- relation-level features (N3): sample_beta_rel, src/sampling.jl:322-337; linear_values, src/macau.jl:89-92 --------------------------
+//   res    = values − udot(r) − mean_value
+//   aFt_y  = α·Fᵀ(res + α^(-1/2)·z1) + sqrt(λ)·z2         z1 ~ N(0, I_nnz), z2 ~ N(0, I_nF) injected or Philox
+//   beta   = (α·FF + λ·I) \ aFt_y                        FF = FᵀF precomputed (reset!, src/RelationData.jl:350-352)
+//   linear_values = mean_value + F·beta                   the per-observation offset of the row draws and of pred(r)
+__global__ void relfeat_noise_kernel(double* __restrict__ res, const double* __restrict__ z1, int64_t n, double sc, uint64_t seed, uint64_t sweep,
+                                     uint32_t stream) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
+    res[o] += sc * (z1 ? z1[o] : philox_normal(seed, sweep, stream, (uint64_t)o, 0));
+}
+__global__ void relfeat_rhs_kernel(double* __restrict__ rhs, const double* __restrict__ z2, int64_t nF, double alpha, double sl, uint64_t seed,
+                                   uint64_t sweep, uint32_t stream) {
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += (int64_t)gridDim.x * blockDim.x)
+    rhs[f] = alpha * rhs[f] + sl * (z2 ? z2[f] : philox_normal(seed, sweep, stream, (uint64_t)f, 1));
+}
+__global__ void relfeat_k_kernel(const double* __restrict__ FF, int64_t nF, double alpha, double lambda, double* __restrict__ K) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nF * nF; e += (int64_t)gridDim.x * blockDim.x)
+    K[e] = alpha * FF[e] + ((e % nF == e / nF) ? lambda : 0.0);
+}
+__global__ void relfeat_adj_kernel(const double* __restrict__ val, const uint32_t* __restrict__ perm, const double* __restrict__ linear, double mean,
+                                   int64_t n, double* __restrict__ out) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
+    out[o] = val[o] - (mean + linear[perm[o]]);
+}
+
+// val_adj of every mode from the current beta: linear = F·beta, val_adj = val − (mean + linear)
+int bdf_refresh_relation_offsets(bdf_t* h, int rel) {
+  RelationS& r = h->rels[rel];
+  int rc = dense_handles(h);
+  if (rc) return rc;
+  const double one = 1.0, zero = 0.0;
+  if (r.nnz > 0 && cublasDgemv((cublasHandle_t)h->cublas, CUBLAS_OP_N, (int)r.nnz, (int)r.nF, &one, r.F, (int)r.nnz, r.beta, 1, &zero, r.linear, 1) != CUBLAS_STATUS_SUCCESS)
+    FAIL(BDF_ERR_CUDA, "cublasDgemv failed");
+  for (int m = 0; m < r.K; m++) {
+    ModeIndex& mi = r.modes[m];
+    relfeat_adj_kernel<<<grid_for(mi.nnz), 256, 0, h->stream>>>(mi.val, mi.perm, r.linear, r.mean, mi.nnz, mi.val_adj);
+  }
+  h->launches += 1 + r.K;
+  CU(cudaGetLastError());
+  return BDF_OK;
+}
+
+extern "C" int bdf_set_relation_features(bdf_t* h, int rel, int64_t nnz, int64_t nF, const double* F) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  RelationS& r = h->rels[rel];
+  if (!F || nF < 1 || nF > 32768) FAIL(BDF_ERR_INVALID, "bad feature matrix");
+  if (nnz != r.nnz) FAIL(BDF_ERR_INVALID, "Number of rows in the relation's feature matrix must equal the number of training observations");
+  if (h->world != 1) FAIL(BDF_ERR_INVALID, "relation-level features are single-GPU in this version");
+  CU(cudaSetDevice(h->device));
+  int rc = dense_handles(h);
+  if (rc) return rc;
+  cudaFree(r.F); cudaFree(r.FF); cudaFree(r.beta); cudaFree(r.linear); cudaFree(r.res);
+  r.F = r.FF = r.beta = r.linear = r.res = nullptr;
+  r.nF = nF;
+  const size_t n1 = (size_t)std::max<int64_t>(nnz, 1);
+  if ((rc = dalloc(h, &r.F, n1 * nF)) || (rc = dalloc(h, &r.FF, (size_t)nF * nF)) || (rc = dalloc(h, &r.beta, (size_t)nF)) || (rc = dalloc(h, &r.linear, n1)) ||
+      (rc = dalloc(h, &r.res, n1)))
+    return rc;
+  CU(cudaMemcpyAsync(r.F, F, sizeof(double) * (size_t)nnz * nF, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(r.beta, 0, sizeof(double) * nF, h->stream));  // beta = zeros(nF)
+  const double one = 1.0, zero = 0.0;
+  if (nnz > 0 && cublasDgemm((cublasHandle_t)h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)nF, (int)nF, (int)nnz, &one, r.F, (int)nnz, r.F, (int)nnz, &zero, r.FF, (int)nF) !=
+                     CUBLAS_STATUS_SUCCESS)
+    FAIL(BDF_ERR_CUDA, "cublasDgemm failed");
+  for (int m = 0; m < r.K; m++) {
+    ModeIndex& mi = r.modes[m];
+    cudaFree(mi.val_adj);
+    mi.val_adj = nullptr;
+    if ((rc = dalloc(h, &mi.val_adj, (size_t)std::max<int64_t>(mi.nnz, 1)))) return rc;
+  }
+  if ((rc = bdf_refresh_relation_offsets(h, rel))) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+extern "C" int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const double* z1, const double* z2, double* beta_out) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  RelationS& r = h->rels[rel];
+  if (!r.F) FAIL(BDF_ERR_STATE, "the relation has no features (bdf_set_relation_features)");
+  if (!(lambda_beta > 0.0)) FAIL(BDF_ERR_INVALID, "lambda_beta must be positive");
+  CU(cudaSetDevice(h->device));
+  int rc = dense_handles(h);
+  if (rc) return rc;
+  cublasHandle_t cb = (cublasHandle_t)h->cublas;
+  cusolverDnHandle_t cs = (cusolverDnHandle_t)h->cusolver;
+  const int nF = (int)r.nF;
+  const int64_t nnz = r.nnz;
+  int lwork = 0;
+  double *K = nullptr, *rhs = nullptr, *work = nullptr, *dz1 = nullptr, *dz2 = nullptr;
+  int* info = nullptr;
+  auto cleanup = [&]() { cudaFree(K); cudaFree(rhs); cudaFree(work); cudaFree(dz1); cudaFree(dz2); cudaFree(info); };
+  if ((rc = dalloc(h, &K, (size_t)nF * nF)) || (rc = dalloc(h, &rhs, (size_t)nF)) || (rc = dalloc(h, &info, 1))) { cleanup(); return rc; }
+  if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, nF, K, nF, &lwork) != CUSOLVER_STATUS_SUCCESS) { cleanup(); FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed"); }
+  if ((rc = dalloc(h, &work, (size_t)std::max(lwork, 1)))) { cleanup(); return rc; }
+  if (z1) { if ((rc = dalloc(h, &dz1, (size_t)std::max<int64_t>(nnz, 1)))) { cleanup(); return rc; } cudaMemcpyAsync(dz1, z1, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->stream); }
+  if (z2) { if ((rc = dalloc(h, &dz2, (size_t)nF))) { cleanup(); return rc; } cudaMemcpyAsync(dz2, z2, sizeof(double) * nF, cudaMemcpyHostToDevice, h->stream); }
+  if ((rc = bdf_relation_residuals(h, rel))) { cleanup(); return rc; }
+  const uint32_t st = 0x500u + 4u * (uint32_t)rel;
+  relfeat_noise_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(r.res, dz1, nnz, 1.0 / sqrt(r.alpha), h->seed, h->sweep, st);
+  const double one = 1.0, zero = 0.0;
+  cublasStatus_t s0 = nnz > 0 ? cublasDgemv(cb, CUBLAS_OP_T, (int)nnz, nF, &one, r.F, (int)nnz, r.res, 1, &zero, rhs, 1) : CUBLAS_STATUS_SUCCESS;
+  if (nnz == 0) cudaMemsetAsync(rhs, 0, sizeof(double) * nF, h->stream);
+  relfeat_rhs_kernel<<<grid_for(nF), 256, 0, h->stream>>>(rhs, dz2, nF, r.alpha, sqrt(lambda_beta), h->seed, h->sweep, st + 1);
+  relfeat_k_kernel<<<grid_for((int64_t)nF * nF), 256, 0, h->stream>>>(r.FF, nF, r.alpha, lambda_beta, K);
+  int hinfo[2] = {0, 0};
+  cusolverStatus_t s1 = cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, nF, K, nF, work, lwork, info);
+  cudaMemcpyAsync(&hinfo[0], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cusolverStatus_t s2 = cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, nF, 1, K, nF, rhs, nF, info);
+  cudaMemcpyAsync(&hinfo[1], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cudaMemcpyAsync(r.beta, rhs, sizeof(double) * nF, cudaMemcpyDeviceToDevice, h->stream);
+  h->launches += 7;
+  rc = bdf_refresh_relation_offsets(h, rel);
+  if (!rc && beta_out) cudaMemcpyAsync(beta_out, r.beta, sizeof(double) * nF, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t ce = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (rc) return rc;
+  if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  if (s0 != CUBLAS_STATUS_SUCCESS || s1 != CUSOLVER_STATUS_SUCCESS || s2 != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cuBLAS/cuSOLVER call failed");
+  if (hinfo[0] != 0 || hinfo[1] != 0) FAIL(BDF_ERR_NUMERIC, "sample_beta_rel: alpha*FF + lambda*I is not positive definite");
+  return BDF_OK;
+}
+
+extern "C" int bdf_get_relation_beta(bdf_t* h, int rel, double* beta) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  RelationS& r = h->rels[rel];
+  if (!r.F || !beta) FAIL(BDF_ERR_STATE, "the relation has no features");
+  CU(cudaMemcpyAsync(beta, r.beta, sizeof(double) * r.nF, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
+extern "C" int bdf_set_relation_beta(bdf_t* h, int rel, const double* beta) {
+  CHECK_H();
+  if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
+  RelationS& r = h->rels[rel];
+  if (!r.F || !beta) FAIL(BDF_ERR_STATE, "the relation has no features");
+  CU(cudaMemcpyAsync(r.beta, beta, sizeof(double) * r.nF, cudaMemcpyHostToDevice, h->stream));
+  int rc = bdf_refresh_relation_offsets(h, rel);
+  CU(cudaStreamSynchronize(h->stream));
+  return rc;
 }
 
 extern "C" int bdf_set_features_dense(bdf_t* h, int entity, int64_t m, int64_t n, const double* F) {

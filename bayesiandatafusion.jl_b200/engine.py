@@ -355,7 +355,34 @@ class Engine:
         self._ck(self.lib.bdf_sample_alpha(self.h, rel, alpha_lambda0, alpha_nu0, sse, float(count), chi2, C.byref(out)))
         return out.value
 
-    def predict(self, rel: int, ids):
+    def set_relation_features(self, rel: int, F):
+        """Relation.F (nnz × nF, rows in the order of the table given to add_relation); FF = F'F, beta = 0 on the device."""
+        Fd = np.asfortranarray(F, dtype=np.float64)
+        self._ck(self.lib.bdf_set_relation_features(self.h, rel, Fd.shape[0], Fd.shape[1], _dp(Fd)))
+        self.rel_nF = getattr(self, "rel_nF", {})
+        self.rel_nF[rel] = int(Fd.shape[1])
+
+    def sample_beta_rel(self, rel: int, lambda_beta: float, z1=None, z2=None):
+        """sample_beta_rel (src/sampling.jl:322-337) + linear_values update (src/macau.jl:90-91); returns beta (nF)."""
+        beta = np.zeros(self.rel_nF[rel])
+        z1 = _f64(z1) if z1 is not None else None
+        z2 = _f64(z2) if z2 is not None else None
+        self._ck(self.lib.bdf_sample_beta_rel(self.h, rel, float(lambda_beta), _dp(z1), _dp(z2), _dp(beta)))
+        return beta
+
+    def set_relation_beta(self, rel: int, beta):
+        self._ck(self.lib.bdf_set_relation_beta(self.h, rel, _dp(_f64(beta))))
+
+    def predict(self, rel: int, ids, test_F=None):
+        if test_F is not None:
+            ids = np.asfortranarray(ids, dtype=np.int64)
+            Fd = np.asfortranarray(test_F, dtype=np.float64)
+            out = np.zeros(ids.shape[0])
+            self._ck(self.lib.bdf_predict_f(self.h, rel, C.c_int64(ids.shape[0]), ids.ctypes.data_as(_lib.c_i64p), _dp(Fd), _dp(out)))
+            return out
+        return self._predict_plain(rel, ids)
+
+    def _predict_plain(self, rel: int, ids):
         ids = np.asfortranarray(ids, dtype=np.int64)
         out = np.zeros(ids.shape[0])
         self._ck(self.lib.bdf_predict(self.h, rel, C.c_int64(ids.shape[0]), ids.ctypes.data_as(_lib.c_i64p), _dp(out)))

@@ -76,9 +76,6 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         raise ValueError('backend must be "cuda": this package is the CUDA engine; the Julia path lives in the reference')
     if not data.relations:
         raise ValueError("RelationData holds no relation")
-    for r in data.relations:
-        if r.hasFeatures():
-            raise NotImplementedError("relation-level features are not on the device path yet (SURVEY §8f N3)")
     rel = data.relations[0]  # predictions / RMSE are reported for the first relation, as in src/macau.jl:142-143
     if verbose:
         print("Model setup")
@@ -95,6 +92,10 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
     for r in data.relations:
         rid = eng.add_relation([eid[id(en)] for en in r.entities], r.data.ids, r.data.values)
         eng.set_relation_params(rid, r.model.alpha, r.model.mean_value)
+        if r.hasFeatures():
+            if r.F.shape[0] != r.numData():
+                raise ValueError("Relation.F must have one row per training observation")
+            eng.set_relation_features(rid, r.F)  # temp.FF = F'F, linear_values = mean_value — reset!, src/RelationData.jl:349-353
         r_ids.append(rid)
     r_id = r_ids[0]
     for e, en in zip(ents, data.entities):
@@ -127,6 +128,11 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
                 sse, n = eng.train_sse(rid)
                 c2 = host_noise.chisquare(r.model.alpha_nu0 + n) if host_noise is not None else math.nan
                 r.model.alpha = eng.sample_alpha(rid, r.model.alpha_lambda0, r.model.alpha_nu0, sse, n, c2)
+                eng.set_relation_params(rid, r.model.alpha, r.model.mean_value)
+            if r.hasFeatures():  # src/macau.jl:89-92
+                z1 = host_noise.standard_normal(r.numData()) if host_noise is not None else None
+                z2 = host_noise.standard_normal(r.F.shape[1]) if host_noise is not None else None
+                r.model.beta = eng.sample_beta_rel(rid, r.model.lambda_beta, z1, z2)
         # Sampling latent vectors — src/macau.jl:96-134 (entities in several relations: sample_user2_all!, :109-118)
         for e, en in zip(ents, data.entities):
             mj = en.model
@@ -160,7 +166,7 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
                     en.lambda_beta, _ = eng.sample_lambda_beta(e, en.model.Lambda, en.nu, en.mu, g)
         eng.advance_sweep()
 
-        probe_rat = eng.predict(r_id, rel.test_ids) if ntest else np.zeros(0)
+        probe_rat = eng.predict(r_id, rel.test_ids, rel.test_F if rel.hasFeatures() else None) if ntest else np.zeros(0)
         if i > burnin:
             if output:
                 # saving latent vectors to disk — src/macau.jl:149-162 (Float32, num_latent × count as Julia holds model.sample)
@@ -179,6 +185,8 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
                         else:
                             np.savetxt(f"{output}-{en.name}-{nstr}{tag}.csv", X32, delimiter=",", fmt="%.9g")
             if full_prediction:
+                if rel.hasFeatures():
+                    raise ValueError("Prediction of all elements is not possible when Relation has features.")  # src/sampling.jl:93-95
                 yhat_full += eng.predict_all(r_id, tuple(rel.data.dims))  # pred_all — src/macau.jl:145-146
             if i == burnin + 1:
                 if verbose:

@@ -117,6 +117,8 @@ class Relation:
     def __init__(self, data: IndexedDF, name: str, entities: Optional[List[Entity]] = None, class_cut: float = 0.0, alpha: float = 1.0):
         self.data = data
         self.name = name
+        self.F = None        # relation-level features: one row per training observation (src/RelationData.jl:127-130)
+        self.test_F = None
         self.entities: List[Entity] = list(entities) if entities else []
         K = len(data.dims)
         self.test_ids = np.zeros((0, K), dtype=np.int64)
@@ -146,7 +148,7 @@ class Relation:
         return self.test_ids.shape[0]
 
     def hasFeatures(self):
-        return False  # relation-level features are out of scope
+        return self.F is not None and self.F.shape[0] > 0 and self.F.shape[1] > 0  # src/RelationData.jl:178
 
 
 def assignToTest(r: Relation, ntest_or_ids, rng: Optional[np.random.Generator] = None):
@@ -158,14 +160,28 @@ def assignToTest(r: Relation, ntest_or_ids, rng: Optional[np.random.Generator] =
         test_id = np.asarray(ntest_or_ids, dtype=np.int64)
     r.test_ids = r.data.ids[test_id - 1].copy()
     r.test_values = r.data.values[test_id - 1].copy()
+    if r.hasFeatures():  # src/RelationData.jl:205-210
+        F = np.asarray(r.F, dtype=np.float64)
+        train = np.ones(F.shape[0], dtype=bool)
+        train[test_id - 1] = False
+        r.test_F = F[test_id - 1]
+        r.F = F[train]
     r.data = r.data.removeSamples(test_id)
     r.test_label = r.test_values < r.class_cut
     return None
 
 
-def setTest(r: Relation, test_ids, test_values):
-    """setTest! — src/RelationData.jl:207-230."""
+def setTest(r: Relation, test_ids, test_values, test_feat=None):
+    """setTest! — src/RelationData.jl:214-233."""
     test_ids = np.asarray(test_ids, dtype=np.int64)
+    if r.hasFeatures() and test_feat is None:
+        raise ValueError("Relation has features, please supply features with test data:\nsetTest(rel, test_df, test_features")
+    if r.hasFeatures() and np.shape(test_feat)[1] != r.F.shape[1]:
+        raise ValueError("The test_feat must have the same number of columns as relation.F.")
+    if r.hasFeatures() and np.shape(test_feat)[0] != test_ids.shape[0]:
+        raise ValueError("The test_feat must have the same number of rows as test_df.")
+    if r.hasFeatures():
+        r.test_F = np.asarray(test_feat, dtype=np.float64)
     if test_ids.ndim != 2 or test_ids.shape[1] != len(r.data.dims):
         raise ValueError("The number of columns in test_df must be the same as in relation.data.df.")
     r.test_ids = test_ids

@@ -139,6 +139,21 @@ int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, 
  * 2-mode relation, out is N1 × N2 column-major (cuBLAS dgemm of the two factor matrices; one GPU). */
 int bdf_predict_all(bdf_t* h, int rel, double* out);
 
+/* ---- relation-level features (Relation.F: one feature row per training observation) — src/macau.jl:89-92, src/sampling.jl:322-337 ---- */
+/* r.F (nnz × nF column-major, rows in the order of the observation table given to bdf_add_relation); computes r.temp.FF = F'F, sets
+ * beta = 0 and linear_values = mean_value (reset!, src/RelationData.jl:349-353). From then on the row draws and bdf_train_sse use
+ * the per-observation offset linear_values[i] in place of mean_value (src/sampling.jl:273, :17-19). One GPU. */
+int bdf_set_relation_features(bdf_t* h, int rel, int64_t nnz, int64_t nF, const double* F);
+/* r.model.beta = sample_beta_rel(r); r.temp.linear_values = mean_value + F*beta. z1 (nnz) and z2 (nF) are the injected standard normals
+ * behind randn(N) and randn(F) (consumed in that order), NULL = Philox. K = alpha*FF + lambda*I is SPD: Cholesky (cuSOLVER) for the
+ * reference's `\`. beta_out (nF) may be NULL. */
+int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const double* z1, const double* z2, double* beta_out);
+int bdf_get_relation_beta(bdf_t* h, int rel, double* beta);
+int bdf_set_relation_beta(bdf_t* h, int rel, const double* beta);
+/* pred(r, probe_vec, F) = udot + F*beta + mean_value — src/sampling.jl:9-14; test_F is ntest × nF column-major (NULL only for a relation
+ * without features, where this is bdf_predict). */
+int bdf_predict_f(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, const double* test_F, double* yhat);
+
 /* ---- Macau side features: the link-matrix (beta) path ------------------------------------------------------------- */
 
 /* Entity(F = SparseBinMatrix(m, n, rows, cols)) — src/parallel_matrix.jl:9-24: registers a sparse 0/1 feature matrix given

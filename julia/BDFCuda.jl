@@ -153,4 +153,18 @@ function predict_all(h::Handle, rel, n1::Integer, n2::Integer)
   return out
 end
 
+## relation-level features: r.F (numData(r) x nF), sample_beta_rel (src/sampling.jl:322-337), pred(r, probe_vec, F) (:9-14)
+set_relation_features(h::Handle, rel, F::Matrix{Float64}) =
+  check(h, ccall((:bdf_set_relation_features, LIB), Cint, (Ptr{Void}, Cint, Int64, Int64, Ptr{Cdouble}), h.ptr, rel, size(F, 1), size(F, 2), F))
+function sample_beta_rel!(h::Handle, rel, lambda_beta, nF::Int; z1 = C_NULL, z2 = C_NULL)
+  beta = zeros(nF)
+  check(h, ccall((:bdf_sample_beta_rel, LIB), Cint, (Ptr{Void}, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, rel, lambda_beta, z1, z2, beta))
+  return beta
+end
+function predict(h::Handle, rel, ids::Matrix{Int64}, test_F::Matrix{Float64})
+  yhat = zeros(size(ids, 1))
+  check(h, ccall((:bdf_predict_f, LIB), Cint, (Ptr{Void}, Cint, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, rel, size(ids, 1), ids, test_F, yhat))
+  return yhat
+end
+
 end # module

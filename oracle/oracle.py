@@ -233,6 +233,15 @@ def bartlett_factor(rng: np.random.Generator, D: int, nu: float):
     return A
 
 
+def sample_beta_rel(F, values, udot, mean_value, alpha, lambda_beta, z1, z2):
+    """sample_beta_rel — src/sampling.jl:322-337: res = values − udot − mean; aFt_y = α·F'(res + α^(-1/2)·randn(N)) + sqrt(λ)·randn(F);
+    K = α·FF + λ·I; K \\ aFt_y (LU, as Julia's `\\`). z1, z2 are the injected randn(N), randn(F) (drawn in that order)."""
+    F = np.asarray(F, dtype=np.float64)
+    res = np.asarray(values, dtype=np.float64) - np.asarray(udot, dtype=np.float64) - mean_value
+    aFt_y = alpha * (F.T @ (res + alpha ** -0.5 * np.asarray(z1))) + np.sqrt(lambda_beta) * np.asarray(z2)
+    return solve_full(alpha * (F.T @ F), aFt_y.reshape(-1, 1), lambda_beta)[:, 0]
+
+
 def sample_alpha(alpha_lambda0: float, alpha_nu0: float, err, chi2: float) -> float:
     """sample_alpha — src/sampling.jl:129-134: Λ = alpha_lambda0·eye(1); SW = inv(inv(Λ) + err'err);
     rand(Wishart(alpha_nu0 + n, SW))[1]. A 1×1 Wishart(ν, S) draw is S·chi2(ν) (Bartlett with a single diagonal entry
