@@ -474,6 +474,7 @@ int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, in
   return BDF_OK;
 }
 int bdf_check_err_flag(bdf_t* h) { return check_err_flag(h); }
+int bdf_copy_rows_h2d_impl(bdf_t* h, int entity, const double* host, double* dev) { return copy_rows_h2d(h, h->ents[entity], host, dev); }
 int bdf_ensure_arena(bdf_t* h, size_t bytes) {
   if (bytes <= h->arena_bytes) return BDF_OK;
   if (h->arena) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->arena)); h->arena = nullptr; h->arena_bytes = 0; }

@@ -26,6 +26,7 @@ using namespace bdf;
 
 int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, int64_t nrows, double* stats);
 int bdf_check_err_flag(bdf_t* h);
+int bdf_copy_rows_h2d_impl(bdf_t* h, int entity, const double* host, double* dev);
 int bdf_relation_residuals(bdf_t* h, int rel);
 int bdf_refresh_relation_offsets(bdf_t* h, int rel);
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
@@ -272,7 +273,8 @@ __global__ void __launch_bounds__(256) color_matrix_kernel(const double* __restr
 // e_r: injected standard normals (row-major rows × ld) or the Philox stream `stream`.
 __global__ void __launch_bounds__(128) colored_rows_kernel(const double* __restrict__ U, const double* __restrict__ mu, const double* __restrict__ Cm,
                                                            const double* __restrict__ E, int64_t rows, int ld, int D, double scale,
-                                                           uint64_t seed, uint64_t sweep, uint32_t stream, double* __restrict__ T, int accumulate) {
+                                                           uint64_t seed, uint64_t sweep, uint32_t stream, double* __restrict__ T, int accumulate,
+                                                           int world = 1, int64_t nper = 0, const int32_t* __restrict__ slot_tab = nullptr) {
   extern __shared__ double sh[];  // C (D×D col-major) + per-warp noise vectors
   double* Cs = sh;
   double* es = sh + (size_t)D * D;
@@ -288,7 +290,11 @@ __global__ void __launch_bounds__(128) colored_rows_kernel(const double* __restr
       if (i < D) {
         for (int k = 0; k <= i; k++) s = fma(Cs[i + (size_t)k * D], ev[k], s);  // C lower triangular
         s *= scale;
-        if (U) s += U[(size_t)r * ld + i] - mu[i];
+        if (U) {
+          // U is slot-major (the rank's replica of the whole factor matrix); T, E and the noise key are in row order
+          const int64_t us = slot_tab ? slot_tab[r] : (world > 1 ? (r % world) * nper + r / world : r);
+          s += U[(size_t)us * ld + i] - mu[i];
+        }
         if (accumulate) s += T[(size_t)r * ld + i];
       }
       T[(size_t)r * ld + i] = s;
@@ -319,6 +325,20 @@ __global__ void add_mu_kernel(const double* __restrict__ uhat, const double* __r
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int d = (int)(e % ld);
     out[e] = d < D ? uhat[e] + mu[d] : 0.0;
+  }
+}
+
+// the same through the row → slot map of a sharded entity: uhat (row order, from the feature product) → uhat and mu .+ uhat in slot order
+__global__ void add_mu_scatter_kernel(const double* __restrict__ uhat_rows, const double* __restrict__ mu, int64_t rows, int ld, int D, int world, int64_t nper,
+                                      const int32_t* __restrict__ slot_tab, double* __restrict__ uhat_slots, double* __restrict__ out) {
+  const int64_t n = rows * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / ld;
+    const int d = (int)(e % ld);
+    const int64_t us = slot_tab ? slot_tab[r] : (r % world) * nper + r / world;
+    const double v = uhat_rows[e];
+    uhat_slots[(size_t)us * ld + d] = d < D ? v : 0.0;
+    out[(size_t)us * ld + d] = d < D ? v + mu[d] : 0.0;
   }
 }
 
@@ -893,7 +913,6 @@ extern "C" int bdf_set_relation_beta(bdf_t* h, int rel, const double* beta) {
 extern "C" int bdf_set_features_dense(bdf_t* h, int entity, int64_t m, int64_t n, const double* F) {
   CHECK_H(); CHECK_ENT(entity);
   if (!F || m < 1 || n < 1) FAIL(BDF_ERR_INVALID, "null or empty feature matrix");
-  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this version");
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
   if (m != e.N) FAIL(BDF_ERR_INVALID, "Number of rows in the feature matrix must equal the entity count");
@@ -945,7 +964,6 @@ extern "C" int bdf_solve_full(bdf_t* h, int entity, const double* rhs, int ncol,
 
 extern "C" int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols) {
   CHECK_H(); CHECK_ENT(entity);
-  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this round (world must be 1)");
   EntityS& e = h->ents[entity];
   if (m != e.N) FAIL(BDF_ERR_INVALID, "DimensionMismatch: number of feature rows must equal the entity count");  // src/RelationData.jl:263-268
   if (n < 1 || n > 2000000000LL || nnz < 0 || nnz >= 2147483647LL) FAIL(BDF_ERR_INVALID, "bad feature matrix size");
@@ -968,7 +986,6 @@ extern "C" int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, 
  * 1-based. Products accumulate in Julia's order (F*x: ascending column per row; F'x: stored order per column). */
 extern "C" int bdf_set_features_csc(bdf_t* h, int entity, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
   CHECK_H(); CHECK_ENT(entity);
-  if (h->world != 1) FAIL(BDF_ERR_INVALID, "side features are single-GPU in this round (world must be 1)");
   EntityS& e = h->ents[entity];
   if (m != e.N) FAIL(BDF_ERR_INVALID, "DimensionMismatch: number of feature rows must equal the entity count");
   if (n < 1 || n > 2000000000LL || !colptr) FAIL(BDF_ERR_INVALID, "bad feature matrix size");
@@ -1092,11 +1109,21 @@ int bdf_update_uhat(bdf_t* h, int entity, const double* mu, double* uhat_out) {
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
   CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
-  spmm(h, e, false, e.beta, e.uhat);
-  add_mu_kernel<<<grid_for(e.N * h->ld), 256, 0, h->stream>>>(e.uhat, e.mu, e.N, h->ld, h->D, e.mu_rows);
+  const double* uhat_rows = e.uhat;  // row order
+  if (h->world == 1 && !e.slot_of_row) {
+    spmm(h, e, false, e.beta, e.uhat);
+    add_mu_kernel<<<grid_for(e.N * h->ld), 256, 0, h->stream>>>(e.uhat, e.mu, e.N, h->ld, h->D, e.mu_rows);
+  } else {
+    // sharded entity: every rank holds the full beta and F, computes F·beta for all rows (row order) and files it by slot
+    if ((rc = bdf_ensure_arena(h, sizeof(double) * (size_t)e.N * h->ld))) return rc;
+    double* tmp = reinterpret_cast<double*>(h->arena);
+    spmm(h, e, false, e.beta, tmp);
+    add_mu_scatter_kernel<<<grid_for(e.N * h->ld), 256, 0, h->stream>>>(tmp, e.mu, e.N, h->ld, h->D, h->world, e.Nper, e.slot_of_row, e.uhat, e.mu_rows);
+    uhat_rows = tmp;
+  }
   h->launches++;
   CU(cudaGetLastError());
-  if (uhat_out) CU(cudaMemcpy2DAsync(uhat_out, sizeof(double) * h->D, e.uhat, sizeof(double) * h->ld, sizeof(double) * h->D, (size_t)e.N, cudaMemcpyDeviceToHost, h->stream));
+  if (uhat_out) CU(cudaMemcpy2DAsync(uhat_out, sizeof(double) * h->D, uhat_rows, sizeof(double) * h->ld, sizeof(double) * h->D, (size_t)e.N, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BDF_OK;
 }
@@ -1114,7 +1141,7 @@ int bdf_sample_mode_uhat(bdf_t* h, int entity, const double* Lambda, const doubl
   const double* zd = nullptr;
   if (z) {
     if (!e.Z) { if ((rc = dalloc(h, &e.Z, un))) return rc; CU(cudaMemsetAsync(e.Z, 0, un * 8, h->stream)); }
-    CU(cudaMemcpy2DAsync(e.Z, sizeof(double) * h->ld, z, sizeof(double) * h->D, sizeof(double) * h->D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = bdf_copy_rows_h2d_impl(h, entity, z, e.Z))) return rc;  // D×N host matrix → slot-major
     zd = e.Z;
   }
   if ((rc = bdf_sample_entity_impl(h, entity, e.mu_rows, h->ld, e.Lambda, zd))) return rc;
@@ -1128,7 +1155,7 @@ int bdf_nw_stats_uhat(bdf_t* h, int entity, double* N, double* NU, double* NS) {
   if (rc) return rc;
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
-  if ((rc = bdf_stats_of(h, e.U, e.uhat, 0, e.N, e.stats))) return rc;
+  if ((rc = bdf_stats_of(h, e.U, e.uhat, (int64_t)h->rank * e.Nper, e.nlocal, e.stats))) return rc;  // this rank's rows (all-reduce: caller)
   const int D = h->D;
   std::vector<double> buf((size_t)1 + D + (size_t)D * D);
   CU(cudaMemcpyAsync(buf.data(), e.stats, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -1186,7 +1213,7 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   cudaFuncSetAttribute(colored_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const uint32_t s0 = 0x200u + 8u * (uint32_t)entity;
   // T = (U − mu) + C·E1 ; rhs = Fᵀ·T ; rhs += sqrt(lambda_beta)·C·E2
-  colored_rows_kernel<<<grid_for(e.N, 4), 128, smem, h->stream>>>(e.U, e.mu, Cm, E1d, e.N, ld, D, 1.0, h->seed, h->sweep, s0, T, 0);
+  colored_rows_kernel<<<grid_for(e.N, 4), 128, smem, h->stream>>>(e.U, e.mu, Cm, E1d, e.N, ld, D, 1.0, h->seed, h->sweep, s0, T, 0, h->world, e.Nper, e.slot_of_row);
   spmm(h, e, true, T, rhs);
   colored_rows_kernel<<<grid_for(e.numF, 4), 128, smem, h->stream>>>(nullptr, nullptr, Cm, E2d, e.numF, ld, D, sqrt(lambda_beta), h->seed, h->sweep, s0 + 1, rhs, 1);
   h->launches += 3;

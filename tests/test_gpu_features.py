@@ -244,3 +244,63 @@ def test_general_sparse_features_match_julia_summation_order(D):
     res = bdf_b200.macau(rd, burnin=3, psamples=3, num_latent=5, verbose=False)
     assert rd.entities[0].model.beta.shape == (numF, 5) and np.isfinite(res["RMSE"])
     eng.close()
+
+
+@pytest.mark.parametrize("partition", ["cyclic", "balanced"])
+def test_feature_path_on_sharded_entities(partition):
+    """world = 3 handles on one GPU: every rank keeps the whole F and beta, draws the same beta from its replica of U, files uhat by
+    slot, samples only its rows and reduces only its rows' statistics (the caller all-reduces them)."""
+    import bdf_b200
+    from bdf_b200.shard import balanced_partition
+
+    rng = np.random.default_rng(77)
+    N, M, numF, D, W = 90, 11, 40, 16, 3
+    dens = rng.random((N, numF)) < 0.15
+    r, c = np.nonzero(dens)
+    rows, cols = (r + 1).astype(np.int32), (c + 1).astype(np.int32)
+    nnz = 700
+    ids = np.stack([rng.integers(1, N + 1, nnz), rng.integers(1, M + 1, nnz)], 1).astype(np.int64)
+    ids[:200, 0] = 9
+    vals = rng.standard_normal(nnz)
+    mean = float(vals.mean())
+    U, V = rng.standard_normal((N, D)) * 0.5, rng.standard_normal((M, D)) * 0.5
+    beta0 = rng.standard_normal((numF, D)) * 0.2
+    mu = rng.standard_normal(D) * 0.3
+    G = rng.standard_normal((D, D)) * 0.2
+    Lambda = G @ G.T + 2.0 * np.eye(D)
+    maps = [balanced_partition(np.bincount(ids[:, 0] - 1, minlength=N), W, 10.0), balanced_partition(np.bincount(ids[:, 1] - 1, minlength=M), W, 10.0)]
+    owner = maps[0] if partition == "balanced" else np.arange(N) % W
+    E1, E2, Z = rng.standard_normal((N, D)), rng.standard_normal((numF, D)), rng.standard_normal((N, D))
+    uhat_o = orc.f_mul_beta_sbm(N, numF, rows, cols, beta0)
+    Uo = [U.copy(), V.copy()]
+    orc.sample_latent_all(orc.FastIDF(ids, vals, [N, M]), 0, Uo, 2.0, mean, mu + uhat_o, Lambda, Z)
+    rhs_o = orc.beta_rhs_sbm(U, mu, orc.color_noise(Lambda, E1), orc.color_noise(Lambda, E2), rows, cols, numF, 3.0)
+    beta_o, _ = orc.solve_cg2(N, numF, rows, cols, rhs_o, 3.0, tol=np.finfo(float).eps * numF)
+    got_rows = U.copy()
+    tot = [0.0, np.zeros(D), np.zeros((D, D))]
+    for rk in range(W):
+        eng = bdf_b200.Engine(D, rank=rk, world=W)
+        if partition == "balanced":
+            e1, e2 = eng.add_entity_partitioned(N, maps[0]), eng.add_entity_partitioned(M, maps[1])
+        else:
+            e1, e2 = eng.add_entity(N), eng.add_entity(M)
+        rel = eng.add_relation([e1, e2], ids, vals)
+        eng.set_relation_params(rel, 2.0, mean)
+        eng.set_features(e1, bdf_b200.SparseBinMatrix(rows, cols, N, numF))
+        eng.set_factors(e1, U)
+        eng.set_factors(e2, V)
+        eng.set_beta(e1, beta0)
+        assert rel_err(eng.update_uhat(e1, mu, want=True), uhat_o) <= 1e-12
+        n, NU, NS = eng.nw_stats_uhat(e1)               # this rank's rows only
+        tot[0] += n; tot[1] += NU; tot[2] += NS
+        beta, rhs, _ = eng.sample_beta(e1, mu, Lambda, 3.0, E1=E1, E2=E2, want_rhs=True)   # from the full replica: same on every rank
+        assert rel_err(rhs, rhs_o) <= 1e-12 and rel_err(beta, beta_o) <= 1e-10
+        eng.set_beta(e1, beta0)
+        eng.update_uhat(e1, mu)
+        eng.sample_mode_uhat(e1, Lambda, Z)
+        mine = owner == rk
+        got_rows[mine] = eng.get_factors(e1)[mine]
+        eng.close()
+    n_o, NU_o, NS_o = orc.nw_stats(U, uhat_o)
+    assert tot[0] == n_o and rel_err(tot[1], NU_o) <= 1e-10 and rel_err(tot[2], NS_o) <= 1e-10
+    assert rel_err(got_rows, Uo[0]) <= 1e-10
