@@ -112,11 +112,19 @@ class DistributedSweep:
             mine = {e: engine.ipc_export(e) for e in self.entities}
             everyone = [None] * engine.world
             dist.all_gather_object(everyone, mine, group=group)
-            for r, handles in enumerate(everyone):
-                if r != engine.rank:
-                    for e in self.entities:
-                        engine.ipc_import(e, r, handles[e])
-            dist.barrier(group=group)
+            ok = 1
+            try:
+                for r, handles in enumerate(everyone):
+                    if r != engine.rank:
+                        for e in self.entities:
+                            engine.ipc_import(e, r, handles[e])
+            except Exception as exc:  # no peer access between some pair of GPUs: every rank falls back to the NCCL all-gather
+                ok = 0
+                print(f"[bdf_b200] rank {engine.rank}: peer mapping failed ({exc}); using the NCCL all-gather", flush=True)
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            # (replicas already mapped on some ranks keep receiving peer stores; the all-gather then rewrites the same values)
+            self.fused = bool(flag.item())
 
         # The Normal-Wishart draw of an entity is first needed by that entity's NEXT half-sweep, so it runs on a high-priority side
         # stream beside the following entity's row kernel (same kernels, same Philox streams: results are unchanged)
