@@ -167,4 +167,67 @@ function predict(h::Handle, rel, ids::Matrix{Int64}, test_F::Matrix{Float64})
   return yhat
 end
 
+## ---- the rest of the sweep: features on an entity (src/macau.jl:102-105, 124-129), device-resident sweeps, multi-GPU plumbing ----
+set_seed(h::Handle, seed::Integer) = check(h, ccall((:bdf_set_seed, LIB), Cint, (Ptr{Void}, UInt64), h.ptr, seed))
+advance_sweep(h::Handle) = check(h, ccall((:bdf_advance_sweep, LIB), Cint, (Ptr{Void},), h.ptr))
+synchronize(h::Handle) = check(h, ccall((:bdf_synchronize, LIB), Cint, (Ptr{Void},), h.ptr))
+
+## mj.uhat = F_mul_beta(en)'; mu_matrix = mj.mu .+ mj.uhat (kept on the device for sample_mode_uhat!)
+function update_uhat!(h::Handle, entity, mu::Vector{Float64}, uhat::Matrix{Float64})
+  check(h, ccall((:bdf_update_uhat, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, mu, uhat))
+end
+sample_mode_uhat!(h::Handle, entity, Lambda_u::Matrix{Float64}; z = C_NULL) =
+  check(h, ccall((:bdf_sample_mode_uhat, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, Lambda_u, z))
+function nw_stats_uhat(h::Handle, entity, D::Int)
+  N = Ref{Cdouble}(0.0); NU = zeros(D); NS = zeros(D, D)
+  check(h, ccall((:bdf_nw_stats_uhat, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, N, NU, NS))
+  return N[], NU, NS
+end
+function beta_gram(h::Handle, entity, D::Int)
+  BtB = zeros(D, D)
+  check(h, ccall((:bdf_beta_gram, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, entity, BtB))
+  return BtB
+end
+get_beta!(h::Handle, entity, beta::Matrix{Float64}) = check(h, ccall((:bdf_get_beta, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, entity, beta))
+set_beta(h::Handle, entity, beta::Matrix{Float64}) = check(h, ccall((:bdf_set_beta, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}), h.ptr, entity, beta))
+
+## AtA_mul_B!(y, F, x, lambda) and cg_AtA / solve_cg2 for a CudaSBM operator type (src/parallel_cg.jl:7-14, 63-94)
+function ata_mul(h::Handle, entity, x::Vector{Float64}, lambda)
+  y = zeros(length(x))
+  check(h, ccall((:bdf_ata_mul, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}), h.ptr, entity, x, lambda, y))
+  return y
+end
+function solve_cg2(h::Handle, entity, rhs::Matrix{Float64}, lambda; tol = NaN, maxiter = 0)
+  x = zeros(size(rhs)); iters = zeros(Cint, size(rhs, 2))
+  check(h, ccall((:bdf_cg_solve, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Cint, Cdouble, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cint}),
+                 h.ptr, entity, rhs, size(rhs, 2), lambda, tol, maxiter, x, iters))
+  return x
+end
+
+## device-resident sweeps (no host buffers): for each entity {latents, Normal-Wishart statistics, (mu, Lambda) draw}
+sweep!(h::Handle, n::Integer = 1) = check(h, ccall((:bdf_sweep, LIB), Cint, (Ptr{Void}, Cint), h.ptr, n))
+step_sample!(h::Handle, entity) = check(h, ccall((:bdf_step_sample, LIB), Cint, (Ptr{Void}, Cint), h.ptr, entity))
+step_nw_stats!(h::Handle, entity) = check(h, ccall((:bdf_step_nw_stats, LIB), Cint, (Ptr{Void}, Cint), h.ptr, entity))
+step_nw_draw!(h::Handle, entity) = check(h, ccall((:bdf_step_nw_draw, LIB), Cint, (Ptr{Void}, Cint), h.ptr, entity))
+function get_hyper(h::Handle, entity, D::Int)
+  mu = zeros(D); Lambda = zeros(D, D)
+  check(h, ccall((:bdf_get_hyper, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, mu, Lambda))
+  return mu, Lambda
+end
+
+## multi-GPU (one Julia process per GPU): exchange the 64-byte handles of ipc_export between the processes, ipc_import the peers';
+## the row kernel then stores every drawn row into all replicas. stats_dev / factors_dev give device pointers for NCCL or CUDA-aware MPI.
+function ipc_export(h::Handle, entity)
+  buf = zeros(UInt8, 64)
+  check(h, ccall((:bdf_ipc_export, LIB), Cint, (Ptr{Void}, Cint, Ptr{UInt8}), h.ptr, entity, buf))
+  return buf
+end
+ipc_import(h::Handle, entity, peer_rank::Integer, handle::Vector{UInt8}) =
+  check(h, ccall((:bdf_ipc_import, LIB), Cint, (Ptr{Void}, Cint, Cint, Ptr{UInt8}), h.ptr, entity, peer_rank, handle))
+function stats_dev(h::Handle, entity)
+  p = Ref{Ptr{Void}}(C_NULL); n = Ref{Int64}(0)
+  check(h, ccall((:bdf_stats_dev, LIB), Cint, (Ptr{Void}, Cint, Ptr{Ptr{Void}}, Ptr{Int64}), h.ptr, entity, p, n))
+  return p[], n[]
+end
+
 end # module

@@ -52,3 +52,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), f"{f} mentions the oracle"
+
+
+def test_julia_glue_binds_only_declared_symbols_with_matching_arity():
+    """julia/BDFCuda.jl is the reference-side binding a maintainer adds; it cannot run here, so at least
+    every `ccall((:sym, LIB), Cint, (argtypes...), ...)` must name a declared entry and pass as many arguments as the
+    C prototype takes."""
+    src = open(os.path.join(ROOT, "julia", "BDFCuda.jl")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(bdf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    calls = re.findall(r"ccall\(\(:(bdf_[a-z0-9_]+), LIB\),\s*\w+,\s*\(([^()]*(?:\([^()]*\)[^()]*)*)\)", src, flags=re.S)
+    assert len(calls) >= 25
+    for name, argtypes in calls:
+        assert name in protos, f"BDFCuda.jl binds {name}, which include/bdf_b200.h does not declare"
+        nargs = len([a for a in re.split(r",\s*(?![^{}]*\})", argtypes.strip().rstrip(",")) if a.strip()])
+        assert nargs == protos[name], f"{name}: Julia passes {nargs} arguments, the C prototype takes {protos[name]}"
