@@ -218,7 +218,7 @@ class RelationData:
         r.model.alpha_sample = bool(alpha_sample)
         if K == 2:
             feats = [feat1, feat2]
-            enames = [entity1, entity2]
+            enames = list(names) if names else [entity1, entity2]  # the DataFrame form names entities after its columns (:282)
         else:
             feats = [None] * K
             enames = list(names) if names else [f"E{i + 1}" for i in range(K)]
@@ -281,3 +281,13 @@ class SparseBinMatrix:
 
     def size(self, d=None):
         return self.shape if d is None else self.shape[d - 1]
+
+    def __getitem__(self, key):
+        """sbm[rows::Vector{Bool}, :] — src/parallel_matrix.jl:26-43: keep the flagged rows (renumbered 1..sum(rows)), list order kept."""
+        rows = key[0] if isinstance(key, tuple) else key
+        rows = np.asarray(rows, dtype=bool)
+        if rows.shape != (self.m,):
+            raise ValueError("DimensionMismatch: length(rows) must equal size(sbm,1)")
+        idx = rows[self.rows - 1]
+        rsum = np.cumsum(rows)
+        return SparseBinMatrix(rsum[self.rows[idx] - 1].astype(np.int32), self.cols[idx], int(rows.sum()), self.n)

@@ -164,3 +164,27 @@ def test_balanced_partition_levels_heavy_tailed_work():
         cyc = np.bincount(np.arange(n) % world, weights=deg + 20.0, minlength=world)
         if world == 8:
             assert cyc.max() / cyc.mean() > 1.05  # the cyclic deal is what it fixes
+
+
+def test_sbm_row_subsetting_known_answers():
+    """test/sbm.jl:6-32."""
+    rows = np.array([1, 2, 3, 2, 3, 4, 1, 2, 3, 4])
+    cols = np.array([1, 1, 1, 2, 2, 2, 3, 3, 3, 3])
+    m = bdf_b200.SparseBinMatrix(rows, cols)
+    assert m.size() == (4, 3)
+    m2 = m[np.array([True, False, True, False]), :]
+    assert m2.size() == (2, 3) and len(m2.rows) == 5
+    assert list(m2.rows) == [1, 2, 2, 1, 2] and list(m2.cols) == [1, 1, 2, 3, 3]
+    A = sp.random(100, 50, 0.2, random_state=3, format="csc")
+    A.data[:] = 1.0
+    coo = A.tocoo()
+    Asbm = bdf_b200.SparseBinMatrix(coo.row + 1, coo.col + 1, 100, 50)
+    z = np.zeros(100, dtype=bool)
+    z[:20] = True
+    z[39] = True
+    z[59:80] = True
+    Az = Asbm[z, :]
+    Az2 = sp.coo_matrix((np.ones(len(Az.rows)), (Az.rows - 1, Az.cols - 1)), shape=(int(z.sum()), 50)).toarray()
+    assert np.array_equal(A.toarray()[z], Az2)
+    with pytest.raises(ValueError):
+        Asbm[np.ones(5, dtype=bool)]
