@@ -738,17 +738,44 @@ __global__ void add_scalar_kernel(double* __restrict__ A, int64_t n, double v) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) A[e] += v;
 }
 
+// every cell of a 3-mode relation, column-major N1 × N2 × N3 (first index fastest)
+__global__ void pred_all3_kernel(const double* __restrict__ U1, const double* __restrict__ U2, const double* __restrict__ U3, int64_t n1, int64_t n2,
+                                 int64_t n3, int ld, int D, double mean, double* __restrict__ out) {
+  const int64_t n = n1 * n2 * n3;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const double* a = U1 + (size_t)(e % n1) * ld;
+    const double* b = U2 + (size_t)((e / n1) % n2) * ld;
+    const double* c = U3 + (size_t)(e / (n1 * n2)) * ld;
+    double s = 0.0;
+    for (int k = 0; k < D; k++) s += a[k] * b[k] * c[k];
+    out[e] = s + mean;
+  }
+}
+
 extern "C" int bdf_predict_all(bdf_t* h, int rel, double* out) {
   CHECK_H();
   if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
   if (!out) FAIL(BDF_ERR_INVALID, "null argument");
   RelationS& r = h->rels[rel];
-  if (r.K != 2) FAIL(BDF_ERR_INVALID, "pred_all is implemented for 2-mode relations (the reference's tensor version enumerates every cell)");
   if (h->world != 1) FAIL(BDF_ERR_INVALID, "pred_all runs on one GPU");
   EntityS& a = h->ents[r.entity_of_mode[0]];
   EntityS& b = h->ents[r.entity_of_mode[1]];
   if (a.slot_of_row || b.slot_of_row) FAIL(BDF_ERR_INVALID, "pred_all needs the default row order");
   CU(cudaSetDevice(h->device));
+  if (r.K == 3) {  // the reference enumerates every cell (src/sampling.jl:78-89); so does this kernel, one thread per cell
+    EntityS& c = h->ents[r.entity_of_mode[2]];
+    if (c.slot_of_row) FAIL(BDF_ERR_INVALID, "pred_all needs the default row order");
+    const size_t n3 = (size_t)a.N * b.N * c.N;
+    int rc3 = bdf_ensure_arena(h, sizeof(double) * n3);
+    if (rc3) return rc3;
+    double* Y3 = reinterpret_cast<double*>(h->arena);
+    pred_all3_kernel<<<grid_for((int64_t)n3), 256, 0, h->stream>>>(a.U, b.U, c.U, a.N, b.N, c.N, h->ld, h->D, r.mean, Y3);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, Y3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BDF_OK;
+  }
   int rc = dense_handles(h);
   if (rc) return rc;
   const size_t n = (size_t)a.N * b.N;

@@ -114,7 +114,14 @@ class RelationModel:
 class Relation:
     """src/RelationData.jl:127-160."""
 
-    def __init__(self, data: IndexedDF, name: str, entities: Optional[List[Entity]] = None, class_cut: float = 0.0, alpha: float = 1.0):
+    def __init__(self, data, name: str, entities: Optional[List[Entity]] = None, class_cut: float = 0.0, alpha: float = 1.0):
+        if hasattr(data, "tocoo"):  # Relation(data::SparseMatrixCSC, name, entities) — src/RelationData.jl:163-169 (findnz order)
+            if entities is not None and len(entities) != 2:
+                raise ValueError("For matrix relation the number of entities has to be 2.")
+            coo = data.tocsc().tocoo()
+            data = IndexedDF(np.stack([coo.row + 1, coo.col + 1], axis=1).astype(np.int64), coo.data, list(data.shape))
+        elif not isinstance(data, IndexedDF):
+            data = IndexedDF(*data)
         self.data = data
         self.name = name
         self.F = None        # relation-level features: one row per training observation (src/RelationData.jl:127-130)
@@ -204,6 +211,9 @@ class RelationData:
         self.entities: List[Entity] = []
         self.relations: List[Relation] = []
         if Am is None:
+            return
+        if isinstance(Am, Relation):  # RelationData(r::Relation) — src/RelationData.jl:307-311
+            self.addRelation(Am)
             return
         if hasattr(Am, "tocoo"):  # sparse matrix: column-major nonzero order like Julia's SparseMatrixCSC (:292-298)
             coo = Am.tocsc().tocoo()

@@ -136,7 +136,8 @@ int bdf_train_sse(bdf_t* h, int rel, double* sse, int64_t* count);
 int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, double sse, double count, double chi2_variate, double* alpha_out);
 
 /* pred_all(r) = udot_all(r) + mean_value — src/sampling.jl:72-97, used by macau(full_prediction = true), src/macau.jl:145-146: every cell of a
- * 2-mode relation, out is N1 × N2 column-major (cuBLAS dgemm of the two factor matrices; one GPU). */
+ * relation, column-major: N1 × N2 for a matrix relation (one cuBLAS dgemm of the two factor matrices), N1 × N2 × N3 for a 3-mode tensor
+ * (one thread per cell, like the reference's enumeration :78-89; test/parallel_latent_tensor.jl:33-39). One GPU. */
 int bdf_predict_all(bdf_t* h, int rel, double* out);
 
 /* ---- relation-level features (Relation.F: one feature row per training observation) — src/macau.jl:89-92, src/sampling.jl:322-337 ---- */

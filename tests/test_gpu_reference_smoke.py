@@ -74,3 +74,47 @@ def test_beta_saving_jl(tmp_path):
     assert b1.shape == (3, 2)   # features × latents
     b10 = dr.read_binary_float32(out + "-A-10.beta.binary")
     assert np.allclose(b10, rd.entities[0].model.beta.astype(np.float32), rtol=1e-6, atol=1e-7)
+
+
+def test_custom_rd_jl_macau_part():
+    """test/custom_rd.jl:32-41: macau on hand-built entities with dense features, and on RelationData(r) from a sparse matrix."""
+    import bdf_b200
+    from bdf_b200.relation_data import Entity, Relation
+
+    rng = np.random.default_rng(0)
+    genes, pheno = Entity("genes"), Entity("pheno")
+    genes.F = rng.random((100, 5))
+    genes.lambda_beta = 3.0
+    pheno.F = rng.random((50, 8))
+    ids = np.stack([rng.integers(1, 101, 1050), rng.integers(1, 51, 1050)], 1)
+    ids[0] = [100, 50]
+    rd = bdf_b200.RelationData()
+    rd.addRelation(Relation((ids, rng.random(1050)), "HPO", [genes, pheno], class_cut=0.5))
+    res = bdf_b200.macau(rd, burnin=10, psamples=10, verbose=False)
+    assert genes.model.beta.shape == (5, 10) and pheno.model.beta.shape == (8, 10) and res["gpu_launches"] > 0
+    r2 = Relation(sp.random(100, 50, 0.01, random_state=1, format="csc"), "HPO2", [Entity("genes2"), Entity("pheno2")])
+    bdf_b200.macau(bdf_b200.RelationData(r2), burnin=2, psamples=2, verbose=False)
+
+
+def test_parallel_latent_tensor_jl():
+    """test/parallel_latent_tensor.jl: 15 × 20 × 2 rank-2 tensor; entity names from the table columns; pred_all of a tensor equals
+    the product of the three latent vectors of a cell plus the mean (:33-39)."""
+    import bdf_b200
+
+    rng = np.random.default_rng(6)
+    A, B, Cc = rng.standard_normal((15, 2)), rng.standard_normal((20, 2)), rng.standard_normal((2, 2))
+    X = np.einsum("id,jd,kd->ijk", A, B, Cc)
+    ii, jj, kk = np.meshgrid(np.arange(1, 16), np.arange(1, 21), np.arange(1, 3), indexing="ij")
+    ids = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], 1).astype(np.int64)
+    rd = bdf_b200.RelationData((ids, X.ravel().copy(), [15, 20, 2]), names=["A", "B", "C"])
+    assert [e.name for e in rd.entities] == ["A", "B", "C"]
+    bdf_b200.assignToTest(rd.relations[0], 10, rng)
+    eng = bdf_b200.Engine(2)
+    res = bdf_b200.macau(rd, burnin=50, psamples=10, num_latent=2, verbose=False, engine=eng)
+    assert np.isfinite(res["RMSE"])
+    Yhat = eng.predict_all(0, (15, 20, 2))
+    assert Yhat.shape == X.shape
+    s = [e.model.sample for e in rd.entities]
+    want = float(np.sum(s[0][3] * s[1][1] * s[2][0])) + rd.relations[0].model.mean_value   # Yhat[4,2,1]
+    assert abs(Yhat[3, 1, 0] - want) <= 1e-12 * max(1.0, abs(want))
+    eng.close()

@@ -188,3 +188,26 @@ def test_sbm_row_subsetting_known_answers():
     assert np.array_equal(A.toarray()[z], Az2)
     with pytest.raises(ValueError):
         Asbm[np.ones(5, dtype=bool)]
+
+
+def test_custom_rd_jl_host_part():
+    """test/custom_rd.jl:6-31,36-41 — entities with features, Relation with entities, addRelation!, RelationData(r)."""
+    from bdf_b200.relation_data import Entity, Relation
+
+    rng = np.random.default_rng(0)
+    genes, pheno = Entity("genes"), Entity("pheno")
+    genes.F = rng.random((100, 5))
+    genes.lambda_beta = 3.0
+    pheno.F = rng.random((50, 8))
+    ids = np.stack([rng.integers(1, 101, 1050), rng.integers(1, 51, 1050)], 1)
+    ids[0] = [100, 50]
+    r = Relation((ids, rng.random(1050)), "HPO", [genes, pheno], class_cut=0.5)
+    rd = bdf_b200.RelationData()
+    rd.addRelation(r)
+    assert r.class_cut == 0.5 and genes.count == r.size(1) and pheno.count == r.size(2)
+    assert len(genes.relations) == 1 and len(pheno.relations) == 1 and len(r.entities) == 2
+    assert len(rd.relations) == 1 and len(rd.entities) == 2
+    r2 = Relation(sp.random(100, 50, 0.01, random_state=1, format="csc"), "HPO2", [Entity("genes2"), Entity("pheno2")])
+    assert r2.size() == (100, 50) and len(r2.entities) == 2
+    rd2 = bdf_b200.RelationData(r2)
+    assert len(rd2.relations) == 1 and len(rd2.entities) == 2
