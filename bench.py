@@ -105,7 +105,8 @@ def cpu_sweeps(D, scale, steps, warmup, threads=None):
     """The restated-reference CPU path (oracle) on a bounded sample: same generator at `scale`, all host threads."""
     from oracle import oracle as orc
 
-    threads = threads or orc.max_threads()
+    # all host threads: under torchrun OMP_NUM_THREADS is forced to 1, the oracle's shard count is an explicit num_threads clause
+    threads = threads or max(orc.max_threads(), len(os.sched_getaffinity(0)))
     # both modes shrink by `scale`, so the per-row degrees (208 / 5618 on average) and hence the per-row work stay those
     # of the full workload and the cost is exactly linear in the sample size
     n1, n2, nnz = max(64, int(N_USERS * scale)), max(16, int(N_ITEMS * scale)), max(1000, int(NNZ * scale))
