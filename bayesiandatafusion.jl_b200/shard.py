@@ -162,6 +162,8 @@ class DistributedSweep:
         """Order every outstanding draw before whatever the caller enqueues next on the current stream."""
         import torch
 
+        if not self.draw_done:
+            return
         main = torch.cuda.current_stream()
         for e in list(self.draw_done):
             main.wait_event(self.draw_done.pop(e))
