@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE: an Engine look-alike backed by the CPU oracle, so that the host-side driver (`bdf_b200.macau`) — loop order,
+posterior averaging, RMSE / dump bookkeeping, alpha and multi-relation plumbing — can be exercised by the `-m "not gpu"` suite.
+It is not part of the product and is never imported by it (the product has no CPU path); it lives under tests/ for that reason."""
+import numpy as np
+
+from oracle import oracle as orc
+
+
+class OracleEngine:
+    def __init__(self, num_latent, seed=0):
+        self.D = num_latent
+        self.rng = np.random.default_rng(seed)
+        self.U, self.rels, self.alpha, self.mean, self.stats = [], [], [], [], {}
+        self.launches = 0
+        self.calls = []
+
+    def set_seed(self, seed):
+        self.rng = np.random.default_rng(seed)
+
+    def add_entity(self, count):
+        self.U.append(np.zeros((count, self.D)))
+        return len(self.U) - 1
+
+    def add_relation(self, entities, ids, vals):
+        self.rels.append((list(entities), np.asarray(ids, dtype=np.int64), np.asarray(vals, dtype=np.float64)))
+        self.alpha.append(1.0)
+        self.mean.append(0.0)
+        return len(self.rels) - 1
+
+    def set_relation_params(self, rel, alpha, mean):
+        self.alpha[rel], self.mean[rel] = float(alpha), float(mean)
+
+    def set_factors(self, e, U):
+        self.U[e] = np.array(U, dtype=np.float64)
+
+    def get_factors(self, e):
+        return self.U[e].copy()
+
+    def sample_mode(self, e, mu, Lambda, z):
+        """sample_user2_all!: every row of entity e from all relations it takes part in (src/sampling.jl:251-289)."""
+        self.calls.append(("sample", e))
+        N = self.U[e].shape[0]
+        Z = self.rng.standard_normal((N, self.D)) if z is None else z
+        out = np.empty_like(self.U[e])
+        uses = [(r, ents.index(e)) for r, (ents, _, _) in enumerate(self.rels) if e in ents]
+        order = {r: np.argsort(self.rels[r][1][:, m], kind="stable") for r, m in uses}
+        for i in range(N):
+            rl = []
+            for r, m in uses:
+                ents, ids, vals = self.rels[r]
+                o = order[r]
+                lo, hi = np.searchsorted(ids[o, m], [i + 1, i + 2])
+                sel = o[lo:hi]
+                others = [k for k in range(len(ents)) if k != m]
+                rl.append({"U": [self.U[ents[k]] for k in others], "ids": [ids[sel, k] for k in others], "vals": vals[sel],
+                           "offset": self.mean[r], "alpha": self.alpha[r]})
+            out[i] = orc.sample_row(self.D, rl, mu if np.ndim(mu) == 1 else mu[i], Lambda, Z[i])
+        self.U[e] = out
+
+    def nw_stats(self, e):
+        self.calls.append(("stats", e))
+        self.stats[e] = orc.nw_stats(self.U[e])
+        return self.stats[e]
+
+    def nw_sample(self, e, mu0, b0, Tinv, nu, bartlettA=None, z=None):
+        self.calls.append(("draw", e))
+        N, NU, NS = self.stats[e]
+        mu_N, beta_N, T_N, nu_N = orc.cond_normal_wishart(N, NU, NS, np.asarray(mu0), b0, np.asarray(Tinv), nu)
+        A = orc.bartlett_factor(self.rng, self.D, nu_N) if bartlettA is None else bartlettA
+        zz = self.rng.standard_normal(self.D) if z is None else z
+        return orc.nw_rand(mu_N, beta_N, T_N, A, zz)
+
+    def train_sse(self, rel):
+        ents, ids, vals = self.rels[rel]
+        err = orc.pred(ids, [self.U[k] for k in ents], self.mean[rel]) - vals
+        return float(err @ err), len(vals)
+
+    def sample_alpha(self, rel, lambda0, nu0, sse, n, chi2=float("nan")):
+        self.calls.append(("alpha", rel))
+        c2 = self.rng.chisquare(nu0 + n) if chi2 != chi2 else chi2
+        self.alpha[rel] = (1.0 / (1.0 / lambda0 + sse)) * c2
+        return self.alpha[rel]
+
+    def advance_sweep(self):
+        self.calls.append(("sweep",))
+
+    def predict(self, rel, ids, test_F=None):
+        ents, _, _ = self.rels[rel]
+        return orc.pred(np.asarray(ids), [self.U[k] for k in ents], self.mean[rel])
+
+    def predict_all(self, rel, shape):
+        ents, _, _ = self.rels[rel]
+        return self.U[ents[0]] @ self.U[ents[1]].T + self.mean[rel]
+
+    def close(self):
+        pass

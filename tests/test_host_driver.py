@@ -1,0 +1,68 @@
+"""Host-side driver logic of `bdf_b200.macau` on CPU, with the engine replaced by the oracle-backed look-alike of
+tests/oracle_engine.py: loop order of src/macau.jl:84-140, posterior averaging and its bookkeeping (src/macau.jl:164-203,
+222-241), sample dumps, full_prediction, several relations per entity with sampled alpha."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import bdf_b200  # noqa: E402
+from bdf_b200 import data_reading as dr  # noqa: E402
+from bdf_b200.relation_data import Entity, IndexedDF, Relation, assignToTest  # noqa: E402
+from oracle_engine import OracleEngine  # noqa: E402
+
+
+def test_bpmf_loop_order_averaging_dumps_and_full_prediction(tmp_path):
+    rng = np.random.default_rng(1)
+    N, M, k = 30, 20, 2
+    A, B = rng.standard_normal((N, k)), rng.standard_normal((M, k))
+    Y = sp.csc_matrix(np.where(rng.random((N, M)) < 0.5, A @ B.T + 0.05 * rng.standard_normal((N, M)), 0.0))
+    rd = bdf_b200.RelationData(Y, class_cut=0.0, alpha=5.0)
+    assignToTest(rd.relations[0], 40, rng)
+    eng = OracleEngine(3)
+    out = str(tmp_path / "run")
+    res = bdf_b200.macau(rd, num_latent=3, burnin=8, psamples=12, verbose=False, engine=eng, host_noise=np.random.default_rng(2),
+                         output=out, full_prediction=True, rmse_train=True, clamp=[-10.0, 10.0])
+    # Gauss-Seidel order per iteration: entity 1 {latents, stats, draw}, entity 2 {latents, stats, draw}, sweep counter
+    per = [("sample", 0), ("stats", 0), ("draw", 0), ("sample", 1), ("stats", 1), ("draw", 1), ("sweep",)]
+    assert eng.calls == per * 20
+    base = float(np.sqrt(np.mean((rd.relations[0].test_values - rd.relations[0].model.mean_value) ** 2)))
+    assert res["RMSE"] < 0.5 * base and res["RMSE_train"] < 0.5 * base
+    p = res["predictions"]
+    assert p["pred"].shape == (40,) and np.all(p["stdev"] >= 0) and res["train_counts"].shape == (40, 2)
+    assert res["predictions_full"].shape == (N, M)
+    i, j = p["ids"][0] - 1
+    assert abs(res["predictions_full"][i, j] - p["pred"][0]) < 1e-9   # both are posterior means over the same 12 samples
+    # 12 dumps per entity, zero-padded to the width of psamples, Float32, num_latent × count; the last one is the final sample
+    for en in rd.entities:
+        files = sorted(f for f in os.listdir(tmp_path) if f.startswith(f"run-{en.name}-"))
+        assert files == [f"run-{en.name}-{s:02d}.binary" for s in range(1, 13)]
+        S = dr.read_binary_float32(os.path.join(tmp_path, files[-1]))
+        assert S.shape == (3, en.count) and np.allclose(S.T, en.model.sample, rtol=1e-6, atol=1e-6)
+
+
+def test_two_relations_with_sampled_alpha_on_the_driver():
+    rng = np.random.default_rng(5)
+    nA, nB, nC, D0 = 40, 25, 15, 2
+    A, B, Cm = (rng.standard_normal((n, D0)) for n in (nA, nB, nC))
+
+    def table(X, Y, nnz):
+        i = np.stack([rng.integers(1, X.shape[0] + 1, nnz), rng.integers(1, Y.shape[0] + 1, nnz)], 1).astype(np.int64)
+        return IndexedDF(i, np.einsum("ij,ij->i", X[i[:, 0] - 1], Y[i[:, 1] - 1]) + 0.3 * rng.standard_normal(nnz), [X.shape[0], Y.shape[0]])
+
+    a, b, c = Entity("a"), Entity("b"), Entity("c")
+    r1 = Relation(table(A, B, 700), "ab", [a, b], alpha=1.0)
+    r2 = Relation(table(A, Cm, 450), "ac", [a, c], alpha=1.0)
+    r1.model.alpha_sample = r2.model.alpha_sample = True
+    assignToTest(r1, 70, rng)
+    rd = bdf_b200.RelationData()
+    rd.addRelation(r1)
+    rd.addRelation(r2)
+    eng = OracleEngine(3)
+    res = bdf_b200.macau(rd, num_latent=3, burnin=10, psamples=10, verbose=False, engine=eng, host_noise=np.random.default_rng(3))
+    assert eng.calls[:2] == [("alpha", 0), ("alpha", 1)] and eng.calls[2] == ("sample", 0)   # src/macau.jl:84-88 precede the entity loop
+    base = float(np.sqrt(np.mean((r1.test_values - r1.model.mean_value) ** 2)))
+    assert res["RMSE"] < 0.6 * base
+    assert 4.0 < r1.model.alpha < 25.0 and 4.0 < r2.model.alpha < 25.0   # planted noise precision 1/0.3² ≈ 11
