@@ -52,6 +52,47 @@ class ShardPlan:
         return np.asarray(S)[self.slot(np.arange(self.count))]
 
 
+class MapShardPlan:
+    """Slot layout of an entity created with `bdf_add_entity_partitioned`: an explicit `rank_of_row` map (e.g. from
+    `balanced_partition`). Rows keep their relative order inside a shard, every shard is padded to the largest one, rank r's rows
+    occupy slots [r·nper, r·nper + nlocal(r)) — the host mirror of the device's slot_of_row table, same interface as ShardPlan."""
+
+    def __init__(self, rank_of_row, world: int):
+        self.rank_of_row = np.asarray(rank_of_row, dtype=np.int64)
+        self.count, self.world = int(self.rank_of_row.shape[0]), int(world)
+        if self.count and (self.rank_of_row.min() < 0 or self.rank_of_row.max() >= world):
+            raise ValueError("rank_of_row entries must lie in 0..world-1")
+        cnt = np.bincount(self.rank_of_row, minlength=world)
+        self.nper = int(max(1, cnt.max())) if self.count else 1
+        self._cnt = cnt
+        pos = np.zeros(self.count, dtype=np.int64)
+        for r in range(world):
+            idx = np.flatnonzero(self.rank_of_row == r)
+            pos[idx] = np.arange(idx.shape[0])
+        self._slot = self.rank_of_row * self.nper + pos
+
+    def owner(self, i):
+        return self.rank_of_row[np.asarray(i)]
+
+    def slot(self, i):
+        return self._slot[np.asarray(i)]
+
+    def nlocal(self, rank: int) -> int:
+        return int(self._cnt[rank])
+
+    def local_rows(self, rank: int):
+        return np.flatnonzero(self.rank_of_row == rank)
+
+    def to_slots(self, U):
+        U = np.asarray(U)
+        out = np.zeros((self.world * self.nper,) + U.shape[1:], dtype=U.dtype)
+        out[self._slot] = U
+        return out
+
+    def from_slots(self, S):
+        return np.asarray(S)[self._slot]
+
+
 class _DevArray:
     """Minimal __cuda_array_interface__ holder so torch can view a raw device pointer without copying."""
 

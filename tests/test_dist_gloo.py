@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bdf_b200.shard import ShardPlan
+from bdf_b200.shard import MapShardPlan, ShardPlan, balanced_partition
 from oracle import oracle as orc
 
 
@@ -27,19 +27,25 @@ def _problem():
     return dims, D, ids, vals, U, mu, Lambda, Z
 
 
-def _worker(rank, world, port, out):
+def _plans(dims, ids, world, partition):
+    if partition == "cyclic":
+        return [ShardPlan(d, world) for d in dims]
+    return [MapShardPlan(balanced_partition(np.bincount(ids[:, m] - 1, minlength=d), world, 5.0), world) for m, d in enumerate(dims)]
+
+
+def _worker(rank, world, port, out, partition):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dims, D, ids, vals, U, mu, Lambda, Z = _problem()
-    plans = [ShardPlan(d, world) for d in dims]
+    plans = _plans(dims, ids, world, partition)
     # every rank holds slot-ordered replicas of all factor matrices (like the device buffers)
     S = [torch.from_numpy(p.to_slots(u)) for p, u in zip(plans, U)]
     stats_all = []
     for mode in range(2):
         plan = plans[mode]
         Unat = [plans[m].from_slots(S[m].numpy()) for m in range(2)]
-        # this rank samples only its rows: keep the observations of rows i % world == rank
-        mine = (ids[:, mode] - 1) % world == rank
+        # this rank samples only its rows: keep the observations of the rows it owns
+        mine = plan.owner(ids[:, mode] - 1) == rank
         idf = orc.FastIDF(ids[mine], vals[mine], dims)
         Uw = [u.copy() for u in Unat]
         orc.sample_latent_all(idf, mode, Uw, 1.5, 0.2, mu, Lambda, Z[mode])
@@ -57,12 +63,13 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_sharded_sweep_equals_unsharded(tmp_path):
+@pytest.mark.parametrize("partition", ["cyclic", "balanced"])
+def test_sharded_sweep_equals_unsharded(tmp_path, partition):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, partition), nprocs=2, join=True)
     got = np.load(out)
     dims, D, ids, vals, U, mu, Lambda, Z = _problem()
     idf = orc.FastIDF(ids, vals, dims)

@@ -211,3 +211,16 @@ def test_custom_rd_jl_host_part():
     assert r2.size() == (100, 50) and len(r2.entities) == 2
     rd2 = bdf_b200.RelationData(r2)
     assert len(rd2.relations) == 1 and len(rd2.entities) == 2
+
+
+def test_map_shard_plan_mirrors_the_partitioned_entity_layout():
+    from bdf_b200.shard import MapShardPlan
+
+    r = np.array([2, 0, 0, 1, 2, 2, 0, 2])
+    plan = MapShardPlan(r, 3)
+    assert plan.nper == 4 and [plan.nlocal(k) for k in range(3)] == [3, 1, 4]
+    assert list(plan.slot(np.arange(8))) == [8, 0, 1, 4, 9, 10, 2, 11]   # rank·nper + position inside the shard, order kept
+    assert list(plan.local_rows(2)) == [0, 4, 5, 7]
+    U = np.random.default_rng(0).standard_normal((8, 3))
+    S = plan.to_slots(U)
+    assert S.shape == (12, 3) and np.array_equal(plan.from_slots(S), U) and np.all(S[3] == 0) and np.all(S[5:8] == 0)
