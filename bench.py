@@ -9,7 +9,11 @@ statistics → (mu, Lambda) draw}. Default workload: D=100 (the configuration BA
 
   value         device-resident sweeps/s (inputs in HBM, Philox noise, CUDA events on the engine's stream, max over ranks)
   e2e           sweeps/s through the public host API (`macau()`-style sequence of C-ABI calls with HOST buffers: mu/Lambda
-                H2D, Normal-Wishart statistics and hyper-parameters D2H, test-set ids H2D and predictions D2H every sweep)
+                H2D, Normal-Wishart statistics and hyper-parameters D2H, test-set ids H2D and predictions D2H every sweep);
+                at N > 1 every rank runs that sequence on its shard (statistics all-reduced on the device in between, each
+                rank predicting 1/N of the held-out set), wall clock, max over ranks
+  N > 1         rows sharded over the ranks by a work-balanced map (--partition balanced, default) or the reference's
+                cyclic deal (--partition cyclic); drawn rows are stored into every peer replica by the row kernel
   roofline      the row-draw kernel: algorithmic FP64 flops per launch (SURVEY §8d formula) ÷ its CUDA-event duration,
                 against the FP64 DMMA peak measured on this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no
                 FP64 figure)
