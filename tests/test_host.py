@@ -224,3 +224,29 @@ def test_map_shard_plan_mirrors_the_partitioned_entity_layout():
     U = np.random.default_rng(0).standard_normal((8, 3))
     S = plan.to_slots(U)
     assert S.shape == (12, 3) and np.array_equal(plan.from_slots(S), U) and np.all(S[3] == 0) and np.all(S[5:8] == 0)
+
+
+def test_c5_shard_generator_partitions_the_table():
+    """tools/bench_c5.py: counter-based chunks, per-rank shard tables. Every observation a rank needs for a mode (its row in that
+    mode is local) is in the rank's table, in table order, and the degrees agree with the full table."""
+    from bdf_b200.shard import balanced_partition
+    from tools.bench_c5 import chunk, degrees, shard_table
+
+    n1, n2, nnz, W, cs = 500, 60, 20_000, 4, 3_000
+    parts = [chunk(c, n1, n2, nnz, chunk_size=cs) for c in range((nnz + cs - 1) // cs)]
+    i1, i2, v = (np.concatenate([p[k] for p in parts]) for k in range(3))
+    assert len(v) == nnz and i1.min() >= 1 and i1.max() <= n1 and i2.max() <= n2
+    again = chunk(2, n1, n2, nnz, chunk_size=cs)
+    assert np.array_equal(again[0], parts[2][0]) and np.array_equal(again[2], parts[2][2])   # pure function of (seed, chunk)
+    d1, d2 = degrees(n1, n2, nnz, chunk_size=cs)
+    assert np.array_equal(d1, np.bincount(i1 - 1, minlength=n1)) and np.array_equal(d2, np.bincount(i2 - 1, minlength=n2))
+    o1, o2 = balanced_partition(d1, W, 8.0), balanced_partition(d2, W, 8.0)
+    total = 0
+    for r in range(W):
+        ids, vals = shard_table(r, o1, o2, n1, n2, nnz, chunk_size=cs)
+        need1, need2 = o1[i1 - 1] == r, o2[i2 - 1] == r
+        mine1, mine2 = o1[ids[:, 0] - 1] == r, o2[ids[:, 1] - 1] == r
+        assert np.array_equal(ids[mine1], np.stack([i1[need1], i2[need1]], 1)) and np.array_equal(vals[mine1], v[need1])
+        assert np.array_equal(ids[mine2], np.stack([i1[need2], i2[need2]], 1)) and np.array_equal(vals[mine2], v[need2])
+        total += len(vals)
+    assert nnz <= total <= 2 * nnz
