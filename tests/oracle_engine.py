@@ -92,5 +92,62 @@ class OracleEngine:
         ents, _, _ = self.rels[rel]
         return self.U[ents[0]] @ self.U[ents[1]].T + self.mean[rel]
 
+    # ---- entity side features (Macau): dense restatement, small sizes only ---------------------------------------------------
+    def set_features(self, e, F):
+        if hasattr(F, "rows") and hasattr(F, "cols"):
+            Fd = np.zeros(F.shape)
+            np.add.at(Fd, (np.asarray(F.rows) - 1, np.asarray(F.cols) - 1), 1.0)
+        elif hasattr(F, "toarray"):
+            Fd = F.toarray().astype(np.float64)
+        else:
+            Fd = np.asarray(F, dtype=np.float64)
+        self.F = getattr(self, "F", {})
+        self.beta = getattr(self, "beta", {})
+        self.uhat = getattr(self, "uhat", {})
+        self.FF = getattr(self, "FF", {})
+        self.F[e], self.beta[e], self.uhat[e] = Fd, np.zeros((Fd.shape[1], self.D)), np.zeros((Fd.shape[0], self.D))
+
+    def compute_ff(self, e, want=False):
+        self.calls.append(("ff", e))
+        self.FF[e] = self.F[e].T @ self.F[e]
+        return self.FF[e] if want else None
+
+    def update_uhat(self, e, mu, want=False):
+        self.calls.append(("uhat", e))
+        self.uhat[e] = self.F[e] @ self.beta[e]              # mj.uhat = F_mul_beta(en)' — src/macau.jl:103
+        self._mu_rows = np.asarray(mu) + self.uhat[e]
+        return self.uhat[e].copy() if want else None
+
+    def sample_mode_uhat(self, e, Lambda, z=None):
+        self.sample_mode(e, self._mu_rows, Lambda, z)
+
+    def nw_stats_uhat(self, e):
+        self.calls.append(("stats", e))
+        self.stats[e] = orc.nw_stats(self.U[e], self.uhat[e])   # U = mj.sample - mj.uhat — src/macau.jl:124
+        return self.stats[e]
+
+    def beta_gram(self, e):
+        return self.beta[e].T @ self.beta[e]
+
+    def sample_beta(self, e, mu, Lambda, lambda_beta, tol=float("nan"), E1=None, E2=None, want_rhs=False):
+        self.calls.append(("beta", e, e in self.FF))
+        F = self.F[e]
+        N, numF = F.shape
+        E1 = self.rng.standard_normal((N, self.D)) if E1 is None else E1
+        E2 = self.rng.standard_normal((numF, self.D)) if E2 is None else E2
+        rhs = F.T @ ((self.U[e] - np.asarray(mu)) + orc.color_noise(Lambda, E1)) + np.sqrt(lambda_beta) * orc.color_noise(Lambda, E2)
+        self.beta[e] = orc.solve_full(F.T @ F, rhs, lambda_beta)   # CG and the FF solve have the same solution
+        it = np.zeros(self.D, dtype=np.int32)
+        return (self.beta[e].copy(), rhs, it) if want_rhs else (self.beta[e].copy(), it)
+
+    def sample_lambda_beta(self, e, Lambda, nu, mu, gamma_variate=float("nan")):
+        self.calls.append(("lambda_beta", e))
+        numF = self.F[e].shape[1]
+        g = self.rng.standard_gamma((nu + numF * self.D) / 2.0) if gamma_variate != gamma_variate else gamma_variate
+        return orc.lambda_beta(orc.btb(self.beta[e]), Lambda, numF, nu, mu, g)
+
+    def get_beta(self, e):
+        return self.beta[e].copy()
+
     def close(self):
         pass

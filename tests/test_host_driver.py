@@ -66,3 +66,28 @@ def test_two_relations_with_sampled_alpha_on_the_driver():
     base = float(np.sqrt(np.mean((r1.test_values - r1.model.mean_value) ** 2)))
     assert res["RMSE"] < 0.6 * base
     assert 4.0 < r1.model.alpha < 25.0 and 4.0 < r2.model.alpha < 25.0   # planted noise precision 1/0.3² ≈ 11
+
+
+def test_macau_feature_branch_on_the_driver():
+    """Entity with side features: uhat before the latents, statistics of U − uhat, nu/Tinv corrections of full_lambda_u
+    (src/macau.jl:120-130), beta and lambda_beta after the entity loop (:138-140), compute_ff_size choosing the FF solve."""
+    rng = np.random.default_rng(9)
+    N, M, numF, k = 60, 25, 6, 2
+    F = rng.standard_normal((N, numF))
+    Uo, Vo = F @ rng.standard_normal((numF, k)) * 0.5, rng.standard_normal((M, k))
+    Y = sp.csc_matrix(np.where(rng.random((N, M)) < 0.3, Uo @ Vo.T + 0.1 * rng.standard_normal((N, M)), 0.0))
+    rd = bdf_b200.RelationData(Y, feat1=F, class_cut=0.0, alpha=5.0)
+    assignToTest(rd.relations[0], 60, rng)
+    eng = OracleEngine(3)
+    res = bdf_b200.macau(rd, num_latent=3, burnin=10, psamples=10, verbose=False, engine=eng, host_noise=np.random.default_rng(4))
+    assert rd.entities[0].use_FF and eng.calls[0] == ("ff", 0)   # numF <= compute_ff_size: reset! precomputes FF
+    per = [("uhat", 0), ("sample", 0), ("stats", 0), ("draw", 0), ("sample", 1), ("stats", 1), ("draw", 1), ("beta", 0, True), ("lambda_beta", 0), ("sweep",)]
+    assert eng.calls[1:] == per * 20
+    base = float(np.std(Y.data))
+    assert res["RMSE"] < 0.6 * base and rd.entities[0].lambda_beta > 0
+    assert rd.entities[0].model.beta.shape == (numF, 3) and np.any(rd.entities[0].model.beta)
+    # compute_ff_size = 0 keeps the CG path: no FF is formed
+    rd2 = bdf_b200.RelationData(Y, feat1=F, class_cut=0.0, alpha=5.0)
+    eng2 = OracleEngine(3)
+    bdf_b200.macau(rd2, num_latent=3, burnin=1, psamples=1, verbose=False, engine=eng2, compute_ff_size=0)
+    assert not rd2.entities[0].use_FF and ("ff", 0) not in eng2.calls and ("beta", 0, False) in eng2.calls
