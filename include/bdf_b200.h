@@ -160,7 +160,9 @@ int bdf_predict_f(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, const do
 /* Entity(F = SparseBinMatrix(m, n, rows, cols)) — src/parallel_matrix.jl:9-24: registers a sparse 0/1 feature matrix given
  * as COO index lists (Int32, 1-based, any order, duplicates counted twice). Builds the CSR of F (the SparseBinMatrixCSR
  * constructor, src/sparsebin_csr.jl:22-37: stable sort by row) and of Fᵀ on the device, allocates beta = zeros(n, D)
- * (src/RelationData.jl:76). m must equal the entity count (src/RelationData.jl:263-268). */
+ * (src/RelationData.jl:76). m must equal the entity count (src/RelationData.jl:263-268). With world > 1 every rank registers the whole
+ * F and keeps the whole beta: the beta draw is replicated (identical on all ranks), uhat is filed by slot, each rank samples and reduces
+ * its own rows. */
 int bdf_set_features_sbm(bdf_t* h, int entity, int64_t m, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols);
 /* Entity(F = ::SparseMatrixCSC{Float64,Int64}) — a general sparse feature matrix given by Julia's CSC fields (colptr n+1, rowval nnz,
  * nzval nnz; 1-based), as in the reference's own tests (test/parallel_latent_basic.jl:4, test/parallel_mult.jl:4-18). Products
