@@ -28,19 +28,10 @@ def AUC_ROC(truth, score) -> float:
     nneg = truth.size - npos
     if npos == 0 or nneg == 0:
         return math.nan
-    order = np.argsort(score, kind="stable")
-    ranks = np.empty(truth.size)
-    ranks[order] = np.arange(1, truth.size + 1)
-    # average ranks over ties
-    s_sorted = score[order]
-    i = 0
-    while i < truth.size:
-        j = i
-        while j + 1 < truth.size and s_sorted[j + 1] == s_sorted[i]:
-            j += 1
-        if j > i:
-            ranks[order[i:j + 1]] = 0.5 * (i + j) + 1.0
-        i = j + 1
+    # average ranks over ties (1-based), vectorised: a tie group occupying sorted positions a..b gets rank (a + b)/2 + 1
+    uniq, inv, cnt = np.unique(score, return_inverse=True, return_counts=True)
+    last = np.cumsum(cnt)
+    ranks = (last - 0.5 * (cnt - 1))[inv]
     return float((ranks[truth].sum() - npos * (npos + 1) / 2.0) / (npos * nneg))
 
 

@@ -43,6 +43,20 @@ class OracleEngine:
         Z = self.rng.standard_normal((N, self.D)) if z is None else z
         out = np.empty_like(self.U[e])
         uses = [(r, ents.index(e)) for r, (ents, _, _) in enumerate(self.rels) if e in ents]
+        if len(uses) == 1:
+            # one relation: the multi-worker half-sweep of the C oracle (sample_latent_all2!, src/sampling.jl:149-172) — same
+            # arithmetic as the per-row call below, OpenMP over cyclic shards, needed for MovieLens-sized tables
+            r, m = uses[0]
+            ents, ids, vals = self.rels[r]
+            self._idf = getattr(self, "_idf", {})
+            if r not in self._idf:
+                self._idf[r] = orc.FastIDF(ids, vals, [self.U[k].shape[0] for k in ents])
+            Us = [self.U[k] for k in ents]
+            Us[m] = out
+            orc.sample_latent_all(self._idf[r], m, Us, self.alpha[r], self.mean[r], mu, Lambda, np.ascontiguousarray(Z),
+                                  nshards=max(1, min(orc.max_threads(), 16)))
+            self.U[e] = out
+            return
         order = {r: np.argsort(self.rels[r][1][:, m], kind="stable") for r, m in uses}
         for i in range(N):
             rl = []
