@@ -61,6 +61,13 @@ SIGNATURES = {
     "bdf_synchronize": (C.c_int, [H]),
     "bdf_launch_count": (C.c_int64, [H]),
     "bdf_predict": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp]),
+    "bdf_set_test": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp, c_dp, C.c_double]),
+    "bdf_test_reset": (C.c_int, [H, C.c_int]),
+    "bdf_predict_accumulate": (C.c_int, [H, C.c_int, C.c_int, C.c_double, C.c_double, c_dp]),
+    "bdf_get_test_predictions": (C.c_int, [H, C.c_int, c_dp, c_dp, c_dp]),
+    "bdf_set_async": (C.c_int, [H, C.c_int]),
+    "bdf_nw_sample_async": (C.c_int, [H, C.c_int, c_dp, C.c_double, c_dp, C.c_double, c_dp, c_dp]),
+    "bdf_nw_sample_fetch": (C.c_int, [H, C.c_int, c_dp, c_dp]),
     "bdf_set_features_sbm": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, c_i32p, c_i32p]),
     "bdf_set_features_csc": (C.c_int, [H, C.c_int, C.c_int64, C.c_int64, c_i64p, c_i64p, c_dp]),
     "bdf_debug_features_csr": (C.c_int, [H, C.c_int, C.c_int, c_i32p, c_i32p]),

@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if ptxas_v else []
     jobs = []
-    for name in ("engine", "features"):
+    for name in ("engine", "features", "predict"):
         if force or _stale(os.path.join(OBJ, f"{name}.o"), deps):
             jobs.append((os.path.join(CSRC, f"{name}.cu"), os.path.join(OBJ, f"{name}.o"), extra))
     only = os.environ.get("BDF_BUILD_DPS")  # dev builds: recompile only these padded dimensions (others keep their objects)
@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
                 print(f"[bdf build] {os.path.basename(obj)}")
                 if ptxas_v:
                     print(log)
-    objs = [os.path.join(OBJ, "engine.o"), os.path.join(OBJ, "features.o")] + [os.path.join(OBJ, f"row_inst_{dp}.o") for dp in DPS]
+    objs = [os.path.join(OBJ, "engine.o"), os.path.join(OBJ, "features.o"), os.path.join(OBJ, "predict.o")] + [os.path.join(OBJ, f"row_inst_{dp}.o") for dp in DPS]
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
            "-lcublas", "-lcusolver", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]  # dense features / FF direct solve (A9) are library calls
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -198,6 +198,12 @@ int check_err_flag(bdf_t* h) {
   return BDF_OK;
 }
 
+// a draw started by bdf_nw_sample_async writes e.mu / e.Lambda and uses h->scratch on the side stream: order it before main-stream work
+int join_draw(bdf_t* h, EntityS& e) {
+  if (e.draw_pending) { CU(cudaStreamWaitEvent(h->stream, e.ev_done, 0)); e.draw_pending = false; }
+  return BDF_OK;
+}
+
 int ensure_ws(bdf_t* h, size_t bytes) {
   if (bytes <= h->ws_bytes) return BDF_OK;
   if (h->ws) {
@@ -318,6 +324,7 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
   EntityS& e = h->ents[entity];
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
   if (e.uses.size() > BDF_MAX_USES) FAIL(BDF_ERR_INVALID, "an entity may take part in at most 6 relations");
+  { int rcj = join_draw(h, e); if (rcj) return rcj; }
   // an entity in several relations (src/sampling.jl:251-289) runs off a merged work list, rebuilt when a relation was added
   const ModeIndex* wl = &h->rels[e.uses[0].first].modes[e.uses[0].second];
   if (e.uses.size() > 1) {
@@ -355,8 +362,13 @@ int sample_entity(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, con
   prep_lambda(h, Lambda_dev, mu_ld ? nullptr : mu_dev, h->D, h->DP, h->lt, h->lt + 64 * (h->DP / 8) * (h->DP / 8 + 1) / 2);
   h->launches++;
   p.D = h->D; p.rank = h->rank; p.world = h->world;
-  p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag; p.dbg = dbg;
+  p.seed = h->seed; p.sweep = h->sweep; p.entity = entity; p.err_flag = h->err_flag;
+#ifdef BDF_DEBUG
+  p.dbg = dbg;
   { const char* f = getenv("BDF_DEBUG_FLAGS"); p.flags = f ? atoi(f) : 0; }
+#else
+  (void)dbg;
+#endif
   return launch_rows(h, p, wl->n_items, tensor);
 }
 
@@ -474,6 +486,10 @@ int bdf_stats_of(bdf_t* h, const double* X, const double* sub, int64_t slot0, in
   return BDF_OK;
 }
 int bdf_check_err_flag(bdf_t* h) { return check_err_flag(h); }
+int bdf_join_side(bdf_t* h) {
+  for (auto& e : h->ents) { int rc = join_draw(h, e); if (rc) return rc; }
+  return BDF_OK;
+}
 int bdf_copy_rows_h2d_impl(bdf_t* h, int entity, const double* host, double* dev) { return copy_rows_h2d(h, h->ents[entity], host, dev); }
 int bdf_ensure_arena(bdf_t* h, size_t bytes) {
   if (bytes <= h->arena_bytes) return BDF_OK;
@@ -481,6 +497,14 @@ int bdf_ensure_arena(bdf_t* h, size_t bytes) {
   bytes = bytes + bytes / 4;
   CU(cudaMalloc((void**)&h->arena, bytes));
   h->arena_bytes = bytes;
+  return BDF_OK;
+}
+int bdf_ensure_arena2(bdf_t* h, size_t bytes) {
+  if (bytes <= h->arena2_bytes) return BDF_OK;
+  if (h->arena2) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->arena2)); h->arena2 = nullptr; h->arena2_bytes = 0; }
+  bytes = bytes + bytes / 4;
+  CU(cudaMalloc((void**)&h->arena2, bytes));
+  h->arena2_bytes = bytes;
   return BDF_OK;
 }
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
@@ -510,20 +534,22 @@ int draw_entity(bdf_t* h, int entity, const double* mu0_dev, double b0, const do
   EntityS& e = h->ents[entity];
   NWDrawParams p{};
   p.D = h->D; p.stats = e.stats; p.mu0 = mu0_dev; p.Tinv = Tinv_dev; p.b0 = b0; p.nu = nu; p.A_inj = A_dev; p.z_inj = z_dev;
-  p.seed = h->seed; p.sweep = h->sweep; p.stream = 0x100u + 8u * (uint32_t)entity; p.scratch = h->scratch;
+  p.seed = h->seed; p.sweep = h->sweep; p.stream = philox_stream(PHILOX_NW, 4u * (uint32_t)entity);  // the draw uses streams +0 … +3
+  p.scratch = h->scratch;
   p.mu_out = e.mu; p.Lam_out = e.Lambda; p.err_flag = h->err_flag;
+#ifdef BDF_DEBUG
   p.debug = getenv("BDF_DEBUG_NW") != nullptr;
+#endif
   const size_t dd8 = sizeof(double) * (size_t)h->D * h->D;
   p.nsm = 2 * dd8 <= 227 * 1024 ? 2 : (dd8 <= 227 * 1024 ? 1 : 0);
   // on a side stream the draw runs next to the following half-sweep's row kernel: the no-shared-memory, <= 64-register variant fits
   // into the slot one retiring row CTA leaves behind (the row kernel owns all shared memory and registers of an SM otherwise)
   if (side) p.nsm = 0;
   cudaStream_t st = side ? side : h->stream;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!(h->smem_optin & BDF_OPTIN_NWDRAW)) {
     CU(cudaFuncSetAttribute(nw_draw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(nw_draw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+    h->smem_optin |= BDF_OPTIN_NWDRAW;
   }
   if (p.nsm == 2) nw_draw_kernel<2><<<1, 256, 2 * dd8, st>>>(p);
   else if (p.nsm == 1) nw_draw_kernel<1><<<1, 256, dd8, st>>>(p);
@@ -584,11 +610,13 @@ int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
 int bdf_destroy(bdf_t* h) {
   if (!h) return BDF_OK;
   cudaSetDevice(h->device);
+  if (h->side) cudaStreamSynchronize(h->side);
   cudaStreamSynchronize(h->stream);
   bdf_dense_teardown(h);
   for (auto& e : h->ents) {
     for (int r = 0; r < 8; r++) if (e.peerU[r]) cudaIpcCloseMemHandle(e.peerU[r]);
     cudaFree(e.slot_of_row); cudaFree(e.row_of_slot);
+    cudaFree(e.inj); if (e.pinned) cudaFreeHost(e.pinned); if (e.ev_done) cudaEventDestroy(e.ev_done);
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);
     cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
     cudaFree(e.sp_items[0]); cudaFree(e.sp_items[1]); cudaFree(e.sp_long[0]); cudaFree(e.sp_long[1]); cudaFree(e.sp_part);
@@ -597,6 +625,7 @@ int bdf_destroy(bdf_t* h) {
   }
   for (auto& r : h->rels) {
     cudaFree(r.F); cudaFree(r.FF); cudaFree(r.beta); cudaFree(r.linear); cudaFree(r.res);
+    bdf_free_test(r);
   }
   for (auto& r : h->rels)
     for (int m = 0; m < r.K; m++) {
@@ -605,7 +634,9 @@ int bdf_destroy(bdf_t* h) {
       free_work_list(mi);
       cudaFree(mi.perm); cudaFree(mi.val_adj);
     }
-  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->ones); cudaFree(h->arena);
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->ones); cudaFree(h->arena); cudaFree(h->arena2);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return BDF_OK;
@@ -866,6 +897,7 @@ int bdf_sample_mode(bdf_t* h, int entity, const double* mu, int64_t mu_ld, const
   const int D = h->D;
   const size_t un = (size_t)e.Nper * h->world * h->ld;
   int rc;
+  if ((rc = join_draw(h, e))) return rc;
   CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * D * D, cudaMemcpyHostToDevice, h->stream));
   const double* mu_dev = e.mu;
   int64_t mu_pitch = 0;
@@ -884,6 +916,7 @@ int bdf_sample_mode(bdf_t* h, int entity, const double* mu, int64_t mu_ld, const
     z_dev = e.Z;
   }
   if ((rc = sample_entity(h, entity, mu_dev, mu_pitch, e.Lambda, z_dev))) return rc;
+  if (h->async_mode && !z) return BDF_OK;  // deferred: the flag is read by the next synchronising call (injected noise lives in the arena: drain)
   return check_err_flag(h);
 }
 
@@ -910,11 +943,14 @@ int bdf_nw_sample(bdf_t* h, int entity, const double* mu0, double b0, const doub
   EntityS& e = h->ents[entity];
   const int D = h->D;
   const size_t dd = (size_t)D * D;
+  { int rcj = bdf_join_side(h); if (rcj) return rcj; }
   CU(cudaMemcpyAsync(e.hyper, mu0, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(e.hyper + D, Tinv, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
   double* A_dev = nullptr; double* z_dev = nullptr; double* stage = nullptr;
   if (bartlettA || z) {
-    CU(cudaMalloc((void**)&stage, sizeof(double) * (dd + D)));
+    int rca = bdf_ensure_arena(h, sizeof(double) * (dd + D));  // injected variates are staged in the handle's grow-only arena
+    if (rca) return rca;
+    stage = reinterpret_cast<double*>(h->arena);
     if (bartlettA) { A_dev = stage; CU(cudaMemcpyAsync(A_dev, bartlettA, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream)); }
     if (z) { z_dev = stage + dd; CU(cudaMemcpyAsync(z_dev, z, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream)); }
   }
@@ -922,8 +958,66 @@ int bdf_nw_sample(bdf_t* h, int entity, const double* mu0, double b0, const doub
   if (!rc && mu_out) { cudaError_t ce = cudaMemcpyAsync(mu_out, e.mu, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream); if (ce != cudaSuccess) rc = BDF_ERR_CUDA; }
   if (!rc && Lambda_out) { cudaError_t ce = cudaMemcpyAsync(Lambda_out, e.Lambda, sizeof(double) * dd, cudaMemcpyDeviceToHost, h->stream); if (ce != cudaSuccess) rc = BDF_ERR_CUDA; }
   if (!rc) rc = check_err_flag(h); else cudaStreamSynchronize(h->stream);
-  if (stage) cudaFree(stage);
   return rc;
+}
+
+int bdf_set_async(bdf_t* h, int on) { CHECK_H(); h->async_mode = on != 0; return BDF_OK; }
+
+int bdf_nw_sample_async(bdf_t* h, int entity, const double* mu0, double b0, const double* Tinv, double nu, const double* bartlettA, const double* z) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!mu0 || !Tinv) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  const int D = h->D;
+  const size_t dd = (size_t)D * D;
+  if (!h->side) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  }
+  if (!e.pinned) {
+    CU(cudaMallocHost((void**)&e.pinned, sizeof(double) * (dd + D + 1)));
+    CU(cudaMalloc((void**)&e.inj, sizeof(double) * (dd + D)));
+    CU(cudaEventCreateWithFlags(&e.ev_done, cudaEventDisableTiming));
+  }
+  int rc;
+  if ((rc = join_draw(h, e))) return rc;
+  CU(cudaMemcpyAsync(e.hyper, mu0, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(e.hyper + D, Tinv, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
+  double* A_dev = nullptr; double* z_dev = nullptr;
+  if (bartlettA) { A_dev = e.inj; CU(cudaMemcpyAsync(A_dev, bartlettA, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream)); }
+  if (z) { z_dev = e.inj + dd; CU(cudaMemcpyAsync(z_dev, z, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream)); }
+  CU(cudaEventRecord(h->ev_ready, h->stream));      // statistics, hyper-priors and variates are in place
+  CU(cudaStreamWaitEvent(h->side, h->ev_ready, 0));
+  if ((rc = draw_entity(h, entity, e.hyper, b0, e.hyper + D, nu, A_dev, z_dev, h->side))) return rc;
+  CU(cudaMemcpyAsync(e.pinned, e.mu, sizeof(double) * D, cudaMemcpyDeviceToHost, h->side));
+  CU(cudaMemcpyAsync(e.pinned + D, e.Lambda, sizeof(double) * dd, cudaMemcpyDeviceToHost, h->side));
+  CU(cudaMemcpyAsync(e.pinned + D + dd, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->side));
+  CU(cudaEventRecord(e.ev_done, h->side));
+  e.draw_pending = true;
+  return BDF_OK;
+}
+
+int bdf_nw_sample_fetch(bdf_t* h, int entity, double* mu_out, double* Lambda_out) {
+  CHECK_H(); CHECK_ENT(entity);
+  CU(cudaSetDevice(h->device));
+  EntityS& e = h->ents[entity];
+  if (!e.ev_done) FAIL(BDF_ERR_STATE, "no bdf_nw_sample_async call to fetch");
+  const int D = h->D;
+  const size_t dd = (size_t)D * D;
+  CU(cudaEventSynchronize(e.ev_done));
+  int rc = join_draw(h, e);
+  if (rc) return rc;
+  if (mu_out) memcpy(mu_out, e.pinned, sizeof(double) * D);
+  if (Lambda_out) memcpy(Lambda_out, e.pinned + D, sizeof(double) * dd);
+  int flag = 0;
+  memcpy(&flag, e.pinned + D + dd, sizeof(int));
+  if (flag) {
+    CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+    FAIL(BDF_ERR_NUMERIC, flag & 1 ? "row draw: precision matrix not positive definite" : "Normal-Wishart draw: matrix not positive definite");
+  }
+  return BDF_OK;
 }
 
 int bdf_step_sample(bdf_t* h, int entity) {
@@ -991,7 +1085,7 @@ int bdf_debug_row_noise(bdf_t* h, int entity, uint64_t sweep, double* z) {
   EntityS& e = h->ents[entity];
   double* d = nullptr;
   CU(cudaMalloc((void**)&d, sizeof(double) * (size_t)e.N * h->D));
-  row_noise_kernel<<<grid_for(e.N * h->D), 256, 0, h->stream>>>(d, h->D, e.N, h->seed, sweep, (uint32_t)entity);
+  row_noise_kernel<<<grid_for(e.N * h->D), 256, 0, h->stream>>>(d, h->D, e.N, h->seed, sweep, philox_stream(PHILOX_ROW, (uint32_t)entity));
   cudaError_t ce = cudaMemcpyAsync(z, d, sizeof(double) * (size_t)e.N * h->D, cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
   cudaFree(d);
@@ -1001,6 +1095,10 @@ int bdf_debug_row_noise(bdf_t* h, int entity, uint64_t sweep, double* z) {
 
 int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, int64_t* n_items) {
   CHECK_H(); CHECK_ENT(entity);
+#ifndef BDF_DEBUG
+  (void)mean_cycles; (void)n_items;
+  FAIL(BDF_ERR_STATE, "phase clocks are compiled out of the release library (build with BDF_EXTRA_NVCC=-DBDF_DEBUG)");
+#else
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
@@ -1032,6 +1130,7 @@ int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, in
   }
   if (n_items) *n_items = cnt;
   return BDF_OK;
+#endif
 }
 
 // yhat[t] += Σ_f F[t, f]·beta[f] — the `F * r.model.beta` term of pred(r, probe_vec, F), src/sampling.jl:13
@@ -1122,8 +1221,9 @@ int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, 
   if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
   if (!alpha_out || !(alpha_lambda0 > 0.0) || !(sse >= 0.0)) FAIL(BDF_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(h->device));
+  { int rcj = bdf_join_side(h); if (rcj) return rcj; }  // h->scratch is shared with an in-flight asynchronous draw
   double* out = h->scratch;
-  alpha_draw_kernel<<<1, 32, 0, h->stream>>>(sse, count, alpha_lambda0, alpha_nu0, chi2_variate, h->seed, h->sweep, 0x400u + (uint32_t)rel, out);
+  alpha_draw_kernel<<<1, 32, 0, h->stream>>>(sse, count, alpha_lambda0, alpha_nu0, chi2_variate, h->seed, h->sweep, philox_stream(PHILOX_ALPHA, (uint32_t)rel), out);
   h->launches++;
   CU(cudaMemcpyAsync(alpha_out, out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

@@ -51,6 +51,17 @@ struct RelationS {
   double* beta = nullptr;     // nF (r.model.beta)
   double* linear = nullptr;   // nnz, F·beta without the mean (r.temp.linear_values − mean_value), table order
   double* res = nullptr;      // nnz work vector (table order)
+  // held-out observations registered with bdf_set_test and their posterior accumulators (predict.cu)
+  int64_t ntest = 0;
+  int32_t* t_slot[3] = {nullptr, nullptr, nullptr};  // factor slots per mode
+  double* t_vals = nullptr;   // test values
+  double* t_F = nullptr;      // ntest × nF relation-level feature rows (column-major)
+  double* t_last = nullptr;   // probe_rat: the current sample's predictions
+  double* t_avg = nullptr;    // probe_rat_all: running posterior mean
+  double* t_sq = nullptr;     // probe_stdev: running sum of squares
+  double* t_part = nullptr;   // reduction scratch
+  double t_cut = 0.0;         // class_cut
+  int64_t t_counter = 0;      // posterior samples accumulated
 };
 
 struct EntityS {
@@ -69,6 +80,11 @@ struct EntityS {
   double* hyper = nullptr;    // [mu0(D), WI(D*D), b0, nu0] device copy for the draw kernel
   std::vector<double> mu0, WI;
   double b0 = 2.0, nu0 = 0.0;
+  // bdf_nw_sample_async / _fetch: injected-variate staging, pinned result buffer [mu(D), Lambda(D*D), err flag], completion event
+  double* inj = nullptr;
+  double* pinned = nullptr;
+  cudaEvent_t ev_done = nullptr;
+  bool draw_pending = false;
   std::vector<std::pair<int, int>> uses;  // (relation, mode) pairs this entity takes part in
   ModeIndex merged;                       // work list over ALL uses (only its item_*/split_* fields), built lazily when uses.size() > 1
   size_t merged_uses = 0;                 // number of uses the merged list was built for
@@ -116,6 +132,9 @@ struct EntityS {
 
 struct bdf_handle;
 int bdf_ensure_arena(bdf_handle* h, size_t bytes);
+int bdf_ensure_arena2(bdf_handle* h, size_t bytes);
+int bdf_check_err_flag(bdf_handle* h);
+void bdf_free_test(bdf::RelationS& r);
 
 struct bdf_handle {
   int device = 0, D = 0, ld = 0, DP = 0, NW = 1, rank = 0, world = 1;
@@ -136,6 +155,15 @@ struct bdf_handle {
   void* cusolver = nullptr;
   char* arena = nullptr;  // grow-only staging for host-facing calls (predict ids/slots/output, beta sampler temporaries)
   size_t arena_bytes = 0;
+  char* arena2 = nullptr;  // second grow-only region: solver work space that must coexist with arena-resident operands
+  size_t arena2_bytes = 0;
   int64_t pst = 0;  // doubles per parked partial for this D
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: the opt-in is remembered per handle (a handle is bound to one
+  // device), one bit per kernel family — not in a process-wide static
+  uint32_t smem_optin = 0;
+  bool async_mode = false;          // bdf_set_async
+  cudaStream_t side = nullptr;      // high-priority side stream of bdf_nw_sample_async (created on first use)
+  cudaEvent_t ev_ready = nullptr;
   std::string err;
 };
+enum { BDF_OPTIN_ROWS = 1, BDF_OPTIN_ROWS_TENSOR = 2, BDF_OPTIN_STATS = 4, BDF_OPTIN_NWDRAW = 8, BDF_OPTIN_COLORED = 16, BDF_OPTIN_ROWS_WS = 32 };

@@ -30,6 +30,7 @@ int bdf_copy_rows_h2d_impl(bdf_t* h, int entity, const double* host, double* dev
 int bdf_relation_residuals(bdf_t* h, int rel);
 int bdf_refresh_relation_offsets(bdf_t* h, int rel);
 int bdf_sample_entity_impl(bdf_t* h, int entity, const double* mu_dev, int64_t mu_ld, const double* Lambda_dev, const double* Z_dev);
+int bdf_join_side(bdf_t* h);
 
 namespace {
 
@@ -600,23 +601,21 @@ int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda
 }
 
 int upload_rowmajor(bdf_t* h, const double* host_cm, int64_t rows, int ncol, double* dev_rm) {
-  double* stage = nullptr;
-  CU(cudaMalloc((void**)&stage, sizeof(double) * (size_t)rows * ncol));
+  int rc = bdf_ensure_arena2(h, sizeof(double) * (size_t)rows * ncol);  // staging in the second arena: no cudaMalloc per call
+  if (rc) return rc;
+  double* stage = reinterpret_cast<double*>(h->arena2);
   CU(cudaMemcpyAsync(stage, host_cm, sizeof(double) * (size_t)rows * ncol, cudaMemcpyHostToDevice, h->stream));
   to_rowmajor_kernel<<<grid_for(rows * h->ld), 256, 0, h->stream>>>(stage, rows, ncol, h->ld, dev_rm);
-  cudaError_t ce = cudaStreamSynchronize(h->stream);
-  cudaFree(stage);
-  if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  CU(cudaStreamSynchronize(h->stream));
   return BDF_OK;
 }
 int download_colmajor(bdf_t* h, const double* dev_rm, int64_t rows, int ncol, double* host_cm) {
-  double* stage = nullptr;
-  CU(cudaMalloc((void**)&stage, sizeof(double) * (size_t)rows * ncol));
+  int rc = bdf_ensure_arena2(h, sizeof(double) * (size_t)rows * ncol);
+  if (rc) return rc;
+  double* stage = reinterpret_cast<double*>(h->arena2);
   to_colmajor_kernel<<<grid_for(rows * ncol), 256, 0, h->stream>>>(dev_rm, rows, ncol, h->ld, stage);
-  cudaError_t ce = cudaMemcpyAsync(host_cm, stage, sizeof(double) * (size_t)rows * ncol, cudaMemcpyDeviceToHost, h->stream);
-  cudaError_t ce2 = cudaStreamSynchronize(h->stream);
-  cudaFree(stage);
-  if (ce != cudaSuccess || ce2 != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+  CU(cudaMemcpyAsync(host_cm, stage, sizeof(double) * (size_t)rows * ncol, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return BDF_OK;
 }
 
@@ -711,10 +710,14 @@ static int solve_full_dev(bdf_t* h, EntityS& e, const double* B, double* X, doub
   const int n = (int)e.numF, D = h->D;
   int lwork = 0;
   if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, n, e.FF, n, &lwork) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
-  double *A = nullptr, *Bc = nullptr, *work = nullptr;
-  int* info = nullptr;
-  auto cleanup = [&]() { cudaFree(A); cudaFree(Bc); cudaFree(work); cudaFree(info); };
-  if ((rc = dalloc(h, &A, (size_t)n * n)) || (rc = dalloc(h, &Bc, (size_t)n * D)) || (rc = dalloc(h, &work, (size_t)std::max(lwork, 1))) || (rc = dalloc(h, &info, 1))) { cleanup(); return rc; }
+  // work space from the handle's second grow-only arena (the first one holds the caller's B / X): no cudaMalloc per draw
+  const size_t nA = ((size_t)n * n + 31) / 32 * 32, nB = ((size_t)n * D + 31) / 32 * 32, nW = ((size_t)std::max(lwork, 1) + 31) / 32 * 32;
+  if ((rc = bdf_ensure_arena2(h, sizeof(double) * (nA + nB + nW + 32)))) return rc;
+  double* A = reinterpret_cast<double*>(h->arena2);
+  double* Bc = A + nA;
+  double* work = Bc + nB;
+  int* info = reinterpret_cast<int*>(work + nW);
+  auto cleanup = [&]() {};
   cudaMemcpyAsync(A, e.FF, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, h->stream);
   add_diag_kernel<<<grid_for(n), 256, 0, h->stream>>>(A, n, lambda);
   to_colmajor_kernel<<<grid_for((int64_t)n * D), 256, 0, h->stream>>>(B, n, D, h->ld, Bc);
@@ -882,16 +885,22 @@ extern "C" int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const 
   const int nF = (int)r.nF;
   const int64_t nnz = r.nnz;
   int lwork = 0;
-  double *K = nullptr, *rhs = nullptr, *work = nullptr, *dz1 = nullptr, *dz2 = nullptr;
-  int* info = nullptr;
-  auto cleanup = [&]() { cudaFree(K); cudaFree(rhs); cudaFree(work); cudaFree(dz1); cudaFree(dz2); cudaFree(info); };
-  if ((rc = dalloc(h, &K, (size_t)nF * nF)) || (rc = dalloc(h, &rhs, (size_t)nF)) || (rc = dalloc(h, &info, 1))) { cleanup(); return rc; }
-  if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, nF, K, nF, &lwork) != CUSOLVER_STATUS_SUCCESS) { cleanup(); FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed"); }
-  if ((rc = dalloc(h, &work, (size_t)std::max(lwork, 1)))) { cleanup(); return rc; }
-  if (z1) { if ((rc = dalloc(h, &dz1, (size_t)std::max<int64_t>(nnz, 1)))) { cleanup(); return rc; } cudaMemcpyAsync(dz1, z1, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->stream); }
-  if (z2) { if ((rc = dalloc(h, &dz2, (size_t)nF))) { cleanup(); return rc; } cudaMemcpyAsync(dz2, z2, sizeof(double) * nF, cudaMemcpyHostToDevice, h->stream); }
+  // temporaries from the handle's second grow-only arena: no cudaMalloc per draw
+  if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, nF, r.FF, nF, &lwork) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+  auto up32 = [](size_t x) { return (x + 31) / 32 * 32; };
+  const size_t nK = up32((size_t)nF * nF), nR = up32((size_t)nF), nW = up32((size_t)std::max(lwork, 1)), nZ1 = z1 ? up32((size_t)std::max<int64_t>(nnz, 1)) : 0, nZ2 = z2 ? nR : 0;
+  if ((rc = bdf_ensure_arena2(h, sizeof(double) * (nK + nR + nW + nZ1 + nZ2 + 32)))) return rc;
+  double* K = reinterpret_cast<double*>(h->arena2);
+  double* rhs = K + nK;
+  double* work = rhs + nR;
+  double* dz1 = z1 ? work + nW : nullptr;
+  double* dz2 = z2 ? work + nW + nZ1 : nullptr;
+  int* info = reinterpret_cast<int*>(work + nW + nZ1 + nZ2);
+  auto cleanup = [&]() {};
+  if (z1) cudaMemcpyAsync(dz1, z1, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->stream);
+  if (z2) cudaMemcpyAsync(dz2, z2, sizeof(double) * nF, cudaMemcpyHostToDevice, h->stream);
   if ((rc = bdf_relation_residuals(h, rel))) { cleanup(); return rc; }
-  const uint32_t st = 0x500u + 4u * (uint32_t)rel;
+  const uint32_t st = philox_stream(PHILOX_RELFEAT, 2u * (uint32_t)rel);
   relfeat_noise_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(r.res, dz1, nnz, 1.0 / sqrt(r.alpha), h->seed, h->sweep, st);
   const double one = 1.0, zero = 0.0;
   cublasStatus_t s0 = nnz > 0 ? cublasDgemv(cb, CUBLAS_OP_T, (int)nnz, nF, &one, r.F, (int)nnz, r.res, 1, &zero, rhs, 1) : CUBLAS_STATUS_SUCCESS;
@@ -1135,6 +1144,7 @@ int bdf_update_uhat(bdf_t* h, int entity, const double* mu, double* uhat_out) {
   if (!mu) FAIL(BDF_ERR_INVALID, "null argument");
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
+  if ((rc = bdf_join_side(h))) return rc;
   CU(cudaMemcpyAsync(e.mu, mu, sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
   const double* uhat_rows = e.uhat;  // row order
   if (h->world == 1 && !e.slot_of_row) {
@@ -1164,6 +1174,7 @@ int bdf_sample_mode_uhat(bdf_t* h, int entity, const double* Lambda, const doubl
   CU(cudaSetDevice(h->device));
   EntityS& e = h->ents[entity];
   const size_t un = (size_t)e.Nper * h->world * h->ld;
+  if ((rc = bdf_join_side(h))) return rc;
   CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * h->D * h->D, cudaMemcpyHostToDevice, h->stream));
   const double* zd = nullptr;
   if (z) {
@@ -1172,6 +1183,7 @@ int bdf_sample_mode_uhat(bdf_t* h, int entity, const double* Lambda, const doubl
     zd = e.Z;
   }
   if ((rc = bdf_sample_entity_impl(h, entity, e.mu_rows, h->ld, e.Lambda, zd))) return rc;
+  if (h->async_mode && !z) return BDF_OK;  // deferred, see bdf_set_async
   return bdf_check_err_flag(h);
 }
 
@@ -1218,6 +1230,7 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   if (!mu || !Lambda) FAIL(BDF_ERR_INVALID, "null argument");
   if (!(lambda_beta > 0.0)) FAIL(BDF_ERR_INVALID, "lambda_beta must be positive");
   CU(cudaSetDevice(h->device));
+  if ((rc = bdf_join_side(h))) return rc;  // e.mu / e.Lambda / h->scratch may still belong to an asynchronous draw
   EntityS& e = h->ents[entity];
   const int D = h->D, ld = h->ld;
   const size_t dd = (size_t)D * D;
@@ -1237,8 +1250,11 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   if (E1) cudaMemcpy2DAsync(E1d, sizeof(double) * ld, E1, sizeof(double) * D, sizeof(double) * D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream);
   if (E2) cudaMemcpy2DAsync(E2d, sizeof(double) * ld, E2, sizeof(double) * D, sizeof(double) * D, (size_t)e.numF, cudaMemcpyHostToDevice, h->stream);
   const size_t smem = sizeof(double) * (dd + 4 * (size_t)D);
-  cudaFuncSetAttribute(colored_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const uint32_t s0 = 0x200u + 8u * (uint32_t)entity;
+  if (!(h->smem_optin & BDF_OPTIN_COLORED)) {
+    CU(cudaFuncSetAttribute(colored_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (128 * 128 + 4 * 128))));
+    h->smem_optin |= BDF_OPTIN_COLORED;
+  }
+  const uint32_t s0 = philox_stream(PHILOX_BETA, 2u * (uint32_t)entity);  // +0: rand(mv, N), +1: rand(mv, numF)
   // T = (U − mu) + C·E1 ; rhs = Fᵀ·T ; rhs += sqrt(lambda_beta)·C·E2
   colored_rows_kernel<<<grid_for(e.N, 4), 128, smem, h->stream>>>(e.U, e.mu, Cm, E1d, e.N, ld, D, 1.0, h->seed, h->sweep, s0, T, 0, h->world, e.Nper, e.slot_of_row);
   spmm(h, e, true, T, rhs);
@@ -1293,11 +1309,12 @@ int bdf_sample_lambda_beta(bdf_t* h, int entity, const double* Lambda, double nu
   if (rc) return rc;
   if (!Lambda || !lambda_beta_out) FAIL(BDF_ERR_INVALID, "null argument");
   CU(cudaSetDevice(h->device));
+  if ((rc = bdf_join_side(h))) return rc;
   EntityS& e = h->ents[entity];
   CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * h->D * h->D, cudaMemcpyHostToDevice, h->stream));
   if ((rc = bdf_stats_of(h, e.beta, nullptr, 0, e.numF, e.btb))) return rc;
   double* out = h->scratch;  // 2 doubles
-  lambda_beta_kernel<<<1, 32, 0, h->stream>>>(e.btb, e.Lambda, h->D, (double)e.numF, nu, mu, gamma_variate, h->seed, h->sweep, 0x300u + (uint32_t)entity, out);
+  lambda_beta_kernel<<<1, 32, 0, h->stream>>>(e.btb, e.Lambda, h->D, (double)e.numF, nu, mu, gamma_variate, h->seed, h->sweep, philox_stream(PHILOX_LAMBDA_BETA, (uint32_t)entity), out);
   h->launches++;
   double res[2];
   CU(cudaMemcpyAsync(res, out, sizeof(res), cudaMemcpyDeviceToHost, h->stream));

@@ -28,6 +28,11 @@ __host__ __device__ inline u32x4 philox4x32_10(u32x4 ctr, uint32_t k0, uint32_t 
   return ctr;
 }
 
+// Stream ids: the sampler kind in the high byte, the entity / relation index (< 2^24) below it, so the streams of different
+// samplers can never overlap however many entities or relations a model has.
+enum PhiloxKind : uint32_t { PHILOX_ROW = 0, PHILOX_NW = 1, PHILOX_BETA = 2, PHILOX_LAMBDA_BETA = 3, PHILOX_ALPHA = 4, PHILOX_RELFEAT = 5 };
+__host__ __device__ constexpr uint32_t philox_stream(PhiloxKind kind, uint32_t index) { return ((uint32_t)kind << 24) | (index & 0xFFFFFFu); }
+
 // two independent uniforms in (0,1) with 52 random bits each
 __host__ __device__ inline void philox_uniform2(uint64_t seed, uint64_t sweep, uint32_t stream, uint64_t row, uint32_t idx,
                                                 double& u1, double& u2) {
@@ -35,7 +40,7 @@ __host__ __device__ inline void philox_uniform2(uint64_t seed, uint64_t sweep, u
   c.x = (uint32_t)row;
   c.y = (uint32_t)(row >> 32) ^ (idx << 8);
   c.z = (uint32_t)sweep;
-  c.w = (uint32_t)(sweep >> 32) ^ (stream << 16);
+  c.w = (uint32_t)(sweep >> 32) ^ stream;  // the whole 32-bit stream id (see philox_stream): sweep counters stay far below 2^32
   const u32x4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const uint64_t a = ((uint64_t)r.x << 32) | r.y, b = ((uint64_t)r.z << 32) | r.w;
   u1 = ((double)(a >> 12) + 0.5) * (1.0 / 4503599627370496.0);

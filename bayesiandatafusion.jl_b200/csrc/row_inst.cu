@@ -25,10 +25,10 @@ static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : BDF_NW_BIG);
 template <bool TENSOR>
 static int launch_rows_t(bdf_t* h, const RowParams& p, int n_items) {
   using K = RowKernel<kDP, kNW, TENSOR>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const uint32_t bit = TENSOR ? BDF_OPTIN_ROWS_TENSOR : BDF_OPTIN_ROWS;
+  if (!(h->smem_optin & bit)) {
     CU(cudaFuncSetAttribute(row_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
-    attr_done = true;
+    h->smem_optin |= bit;
   }
   if (n_items > 0) {
     row_kernel<K><<<n_items, K::NTHR, K::SMEM_BYTES, h->stream>>>(p);
@@ -45,11 +45,10 @@ int CAT(bdf_launch_rows_, BDF_DP)(bdf_t* h, const RowParams& p, int n_items, boo
 // returns the number of partials written to h->ws (each tri(D+1) doubles), or a negative error
 int CAT(bdf_launch_stats_, BDF_DP)(bdf_t* h, const double* U, const double* uhat, int64_t slot0, int64_t nrows) {
   using K = RowKernel<kDP, kNW, false>;
-  static bool attr_done = false;
   const size_t smem = sizeof(double) * K::SBUFSZ;
-  if (!attr_done) {
+  if (!(h->smem_optin & BDF_OPTIN_STATS)) {
     CU(cudaFuncSetAttribute(stats_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    h->smem_optin |= BDF_OPTIN_STATS;
   }
   int64_t nblk = (nrows + 4 * K::SKS - 1) / (4 * K::SKS);
   if (nblk > 296) nblk = 296;

@@ -102,8 +102,10 @@ struct RowParams {
   int entity;
   int* err_flag;
   int n_items;
-  int flags;       // debug: bit 0 = return after the syrk (timing experiments only; results invalid)
+#ifdef BDF_DEBUG  // profiling builds only (tools/phase_probe*.py): the release library carries neither the fields nor the code
+  int flags;       // bit 0 = return after the syrk, bit 1 = no DMMAs, bit 2 = no gather (timing experiments only; results invalid)
   long long* dbg;  // optional per-item phase clocks [n_items][8] (bdf_debug_phase_clocks), else nullptr
+#endif
 };
 
 template <int N, class F, int... Is>
@@ -181,6 +183,16 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 }
 
 __host__ __device__ constexpr int tri(int i) { return i * (i + 1) / 2; }
+
+// ---- shared-memory layout of an 8×8 tile (64 doubles): element (k, m) lives at 8k + (m ^ 4·bit1(k)), i.e. rows 2, 3, 6, 7 have
+// their two 4-column halves swapped. A tile is written in the DMMA accumulator layout (lane = 4·row + q holds columns 2q, 2q+1: one
+// double2 per lane, 16 contiguous doubles per quarter-warp) and read back TRANSPOSED as a DMMA operand fragment (lane = 4·m + k
+// holds element (k, m)). Without the swap the fragment read of a half-warp touches rows k = 0…3 × columns m = 0…3 = words
+// {0-3, 8-11, 16-19, 24-27}, two rows per bank group: a 2-way conflict on every LDS.64 of the factorisation (ncu: 25 % of all
+// shared-memory wavefronts of the kernel). With the swap rows 2, 3 move to words {20-23, 28-31} and every half-warp is conflict-free.
+__device__ __forceinline__ int tile_acc_off(int lane) { return (2 * lane) ^ (((lane >> 3) & 1) << 2); }                 // (row lane/4, cols 2q, 2q+1)
+__device__ __forceinline__ int tile_frag_off(int lane) { return 8 * (lane & 3) + ((lane >> 2) ^ ((lane & 2) << 1)); }   // element (k = lane%4, m = lane/4); k+4: +32
+__device__ __forceinline__ int tile_el(int k, int m) { return 8 * k + (m ^ ((k & 2) << 1)); }
 // inverse of t = tri(I) + J, 0 <= J <= I (t < 2^20)
 __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
   int i = (int)((sqrtf((float)(8 * t + 1)) - 1.0f) * 0.5f);
@@ -309,15 +321,19 @@ struct RowKernel {
 
     double* ring = smem;                    // [NBUF][STG]: tile (KS×S), [second tile], residuals (KS)
     double* Tl = smem;                      // Λ* / factor tiles, alias the ring after the main loop
-    double* WvT = smem + REGSZ;             // inverse diagonal blocks, transposed: WvT[p][k][m] = (W_pp⁻¹)[m][k]
+    double* WvT = smem + REGSZ;             // inverse diagonal blocks W_pp⁻¹ in the tile layout (tile_el(row, col))
     double* rhs = WvT + NB * 64;            // [DP]
     double* lmu = rhs + DP;                 // Λ·μ [DP]
     double* ys = lmu + DP;                  // W⁻¹·rhs (+ z) [DP]
     double* xs = ys + DP;                   // the draw [DP]
     double* ts = xs + DP;                   // [8]
 
+#ifdef BDF_DEBUG
 #define BDF_STAMP(k)                                                   \
   if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + (k)] = clock64()
+#else
+#define BDF_STAMP(k)
+#endif
     BDF_STAMP(0);
     double acc[TPW][2];
 #pragma unroll
@@ -386,7 +402,11 @@ struct RowKernel {
       }
     };
     __syncthreads();  // ring zero-fill and barrier init visible before any stage is issued or consumed
+#ifdef BDF_DEBUG
     const bool dbg_nogather = p.flags & 4, dbg_nocompute = p.flags & 2;  // timing experiments only (results invalid)
+#else
+    constexpr bool dbg_nogather = false, dbg_nocompute = false;
+#endif
     if (nst > 0 && !dbg_nogather) { load_meta(0); issue(0); }
     if (nst > 1 && !dbg_nogather) { load_meta(1); issue(1); }
     if (nst > 2) load_meta(2);
@@ -428,7 +448,7 @@ struct RowKernel {
       double z = 0.0;
       if (tid < D) {
         const int64_t grow0 = p.row_of_slot ? (int64_t)p.row_of_slot[slot] : (int64_t)lrow * p.world + p.rank;
-        z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, p.entity, grow0, tid);
+        z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, philox_stream(PHILOX_ROW, (uint32_t)p.entity), grow0, tid);
       }
       xs[tid] = z;
     }
@@ -513,11 +533,13 @@ struct RowKernel {
     }
 
     BDF_STAMP(3);
+#ifdef BDF_DEBUG
     if (p.flags & 1) {
       if (tid == 0 && acc[0][0] == 1.2345) p.Uout[0] = acc[0][1];
       if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + 4] = p.dbg[(size_t)item * 8 + 5] = p.dbg[(size_t)item * 8 + 6] = clock64();
       return;
     }
+#endif
     // ---- park Λ* = α·acc in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles), identity on the padding;
     //      the augmented row (i == D) carries Σ v·r and becomes rhs = Λμ + α·Σv·r ---------------------------------------------
     {
@@ -537,7 +559,7 @@ struct RowKernel {
             if (i >= D || j >= D) v.x = (i == j) ? 1.0 : 0.0;
             if (i >= D || j + 1 >= D) v.y = (i == j + 1) ? 1.0 : 0.0;
           }
-          *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + 2 * lane) = v;
+          *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + tile_acc_off(lane)) = v;
         });
       });
     }
@@ -558,14 +580,15 @@ struct RowKernel {
     const int vw = warp;
 #endif
     bool bad = false;
-    const int fo = 8 * (lane & 3) + (lane >> 2);  // fragment offset in a row-major 8×8 tile: A[m][k]=B[k][m]=tile[k][m]
+    const int fo = tile_frag_off(lane);  // operand-fragment offset in a tile: A[m][k] = B[k][m] = tile(k, m)
+    const int ao = tile_acc_off(lane);   // accumulator-layout offset (double2)
     auto factor_diag = [&](int pb) {
       // A_pp = W·Wᵀ by elimination from the last column to the first, in the DMMA accumulator layout (lane = 4·row+q
       // holds columns 2q, 2q+1); an identity block carried along ends up as W⁻¹, stored transposed in WvT[pb].
       // The next pivot is formed from pre-update values as soon as the current scale is known, so its rsqrt overlaps
       // the rank-1 update instead of waiting for it.
       const int r = lane >> 2, q = lane & 3;
-      const double2 av = *reinterpret_cast<const double2*>(Tl + 64 * (tri(pb) + pb) + 2 * lane);
+      const double2 av = *reinterpret_cast<const double2*>(Tl + 64 * (tri(pb) + pb) + ao);
       double a0 = av.x, a1 = av.y;
       double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
       double piv = __shfl_sync(0xffffffffu, a1, 4 * 7 + 3);  // a_77
@@ -601,14 +624,13 @@ struct RowKernel {
           e1 = ej1;
         }
       }
-      WvT[pb * 64 + (2 * q) * 8 + r] = e0;
-      WvT[pb * 64 + (2 * q + 1) * 8 + r] = e1;
+      *reinterpret_cast<double2*>(WvT + pb * 64 + ao) = make_double2(e0, e1);  // W_pp⁻¹ in the tile layout: element (row, col) at tile_el(row, col)
     };
     // trailing update of block row I above panel pb: tiles (I, J), J = j0 … I
     auto update_row = [&](int pb, int I, int j0, int j1) {
       const double* Pp = Tl + 64 * tri(pb) + fo;
       const double na0 = -Pp[64 * I], na1 = -Pp[64 * I + 32];
-      double* trow = Tl + 64 * tri(I) + 2 * lane;
+      double* trow = Tl + 64 * tri(I) + ao;
       // UB tiles at a time: all their operands are loaded before the first DMMA, so the shared-memory latency and the
       // two dependent DMMAs of a tile overlap across the batch (the compiler cannot hoist loads over the tile stores)
       constexpr int UB = BDF_UR_UNROLL;
@@ -640,19 +662,19 @@ struct RowKernel {
       double y0 = 0.0, y1 = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
-        y0 = fma(WvT[J * 64 + k * 8 + r8], rhs[8 * J + k], y0);
-        y1 = fma(WvT[J * 64 + (k + 1) * 8 + r8], rhs[8 * J + k + 1], y1);
+        y0 = fma(WvT[J * 64 + tile_el(r8, k)], rhs[8 * J + k], y0);
+        y1 = fma(WvT[J * 64 + tile_el(r8, k + 1)], rhs[8 * J + k + 1], y1);
       }
       if (lane < 8) ys[8 * J + r8] = y0 + y1;
       __syncwarp();
       if (update) {
         for (int c = lane; c < 8 * J; c += 32) {
-          const double* tp = Tl + 64 * (tri(J) + (c >> 3)) + (c & 7);  // R_J[k][c] = tile(J, c/8)[k][c%8]
+          const double* tp = Tl + 64 * (tri(J) + (c >> 3));  // R_J[k][c] = tile(J, c/8)(k, c%8)
           double s0 = rhs[c], s1 = 0.0;
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
-            s0 = fma(-tp[8 * k], ys[8 * J + k], s0);
-            s1 = fma(-tp[8 * k + 8], ys[8 * J + k + 1], s1);
+            s0 = fma(-tp[tile_el(k, c & 7)], ys[8 * J + k], s0);
+            s1 = fma(-tp[tile_el(k + 1, c & 7)], ys[8 * J + k + 1], s1);
           }
           rhs[c] = s0 + s1;
         }
@@ -660,26 +682,35 @@ struct RowKernel {
       }
     };
 
+#ifdef BDF_DEBUG
     long long d_b = 0, d_c = 0, d_w1 = 0, d_w2 = 0, t_x = 0;
+#define BDF_LAP(acc_) if (p.dbg) { const long long t = clock64(); acc_ += t - t_x; t_x = t; }
+#define BDF_LAP0() if (p.dbg) t_x = clock64()
+#else
+#define BDF_LAP(acc_)
+#define BDF_LAP0()
+#endif
     if (vw == 0) factor_diag(NB - 1);
     __syncthreads();
     for (int pb = NB - 1; pb > 0; pb--) {
-      if (p.dbg) t_x = clock64();
+      BDF_LAP0();
       // (b) scale the panel tiles (pb, J < pb) in place
       {
-        const double wa0 = WvT[pb * 64 + fo], wa1 = WvT[pb * 64 + 32 + fo];
+        // A operand = W_pp⁻¹[m][k], m = lane/4, k = lane%4 (+4): stored untransposed, so its fragment is read along a tile row
+        const int wo = tile_el(lane >> 2, lane & 3);
+        const double wa0 = WvT[pb * 64 + wo], wa1 = WvT[pb * 64 + (wo ^ 4)];
         for (int J = vw; J < pb; J += NW) {
           double* tp = Tl + 64 * (tri(pb) + J);
           const double b0 = tp[fo], b1 = tp[32 + fo];
           double c2[2] = {0.0, 0.0};
           dmma884(c2, wa0, b0);
           dmma884(c2, wa1, b1);
-          *reinterpret_cast<double2*>(tp + 2 * lane) = make_double2(c2[0], c2[1]);
+          *reinterpret_cast<double2*>(tp + ao) = make_double2(c2[0], c2[1]);
         }
       }
-      if (p.dbg) { const long long t = clock64(); d_b += t - t_x; t_x = t; }
+      BDF_LAP(d_b)
       __syncthreads();
-      if (p.dbg) { const long long t = clock64(); d_w1 += t - t_x; t_x = t; }
+      BDF_LAP(d_w1)
       // (c) trailing update of block rows I < pb; rows are dealt to warps 1…NW-1 in a snake so the triangle balances
       if (NW == 1) {
         backsub_step(pb, true);
@@ -701,14 +732,16 @@ struct RowKernel {
           if (wo == vw) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
         }
       }
-      if (p.dbg) { const long long t = clock64(); d_c += t - t_x; t_x = t; }
+      BDF_LAP(d_c)
       __syncthreads();
-      if (p.dbg) { const long long t = clock64(); d_w2 += t - t_x; t_x = t; }
+      BDF_LAP(d_w2)
     }
+#ifdef BDF_DEBUG
     if (p.dbg && lane == 0 && vw < 2) {
       long long* o = p.dbg + (size_t)gridDim.x * 8 + ((size_t)item * 2 + vw) * 4;
       o[0] = d_b; o[1] = d_w1; o[2] = d_c; o[3] = d_w2;
     }
+#endif
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
     BDF_STAMP(5);
 
@@ -742,19 +775,22 @@ struct RowKernel {
           double x0 = 0.0, x1 = 0.0;
 #pragma unroll
           for (int kk = 0; kk < 8; kk += 2) {
-            x0 = fma(WvT[J * 64 + r8 * 8 + kk], ts[kk], x0);
-            x1 = fma(WvT[J * 64 + r8 * 8 + kk + 1], ts[kk + 1], x1);
+            x0 = fma(WvT[J * 64 + tile_el(kk, r8)], ts[kk], x0);
+            x1 = fma(WvT[J * 64 + tile_el(kk + 1, r8)], ts[kk + 1], x1);
           }
           const double xj = x0 + x1;  // lane r8 (replicated over the 4 lane groups) holds x[8J + r8]
           if (lane < 8) xs[8 * J + r8] = xj;
+          // this lane's tile row is i%8 = lane%8 for every s2; rows 2, 3, 6, 7 store their column halves swapped (tile_el), so those
+          // lanes take x_J with its halves swapped as well and read the row as it lies in memory
+          const int hs = (lane & 2) << 1;
           double xb[8];
 #pragma unroll
-          for (int k = 0; k < 8; k++) xb[k] = __shfl_sync(0xffffffffu, xj, k);
+          for (int k = 0; k < 8; k++) xb[k] = __shfl_sync(0xffffffffu, xj, k ^ hs);
 #pragma unroll
           for (int s2 = 0; s2 < NS; s2++) {
             const int i = lane + 32 * s2;
             if (i >= 8 * (J + 1) && i < DP) {
-              const double* tp = Tl + 64 * (tri(i >> 3) + J) + 8 * (i & 7);  // R[i][8J .. 8J+7]
+              const double* tp = Tl + 64 * (tri(i >> 3) + J) + 8 * (i & 7);  // R[i][8J .. 8J+7], physical order
               const double2 t0 = *reinterpret_cast<const double2*>(tp), t1 = *reinterpret_cast<const double2*>(tp + 2);
               const double2 t2 = *reinterpret_cast<const double2*>(tp + 4), t3 = *reinterpret_cast<const double2*>(tp + 6);
               double a = fma(t0.x, xb[0], t0.y * xb[1]), b = fma(t1.x, xb[2], t1.y * xb[3]);
@@ -777,10 +813,14 @@ struct RowKernel {
         for (int j = lane; j < p.ld; j += 32) po[j] = j < D ? xs[j] : 0.0;
       }
       __syncwarp();
+#ifdef BDF_DEBUG
       if (p.dbg && lane == 0) p.dbg[(size_t)item * 8 + 6] = clock64();
+#endif
     }
   }
 #undef BDF_STAMP
+#undef BDF_LAP
+#undef BDF_LAP0
 };
 
 #ifndef BDF_MINB

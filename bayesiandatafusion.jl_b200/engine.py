@@ -162,6 +162,48 @@ class Engine:
                                         _dp(A), _dp(zz), _dp(mu), _dp(Lam)))
         return mu, Lam
 
+    def set_async(self, on: bool = True):
+        """Deferred completion of sample_mode / sample_mode_uhat (bdf_set_async)."""
+        self._ck(self.lib.bdf_set_async(self.h, int(bool(on))))
+
+    def nw_sample_async(self, entity: int, mu0, b0, Tinv, nu, bartlettA=None, z=None):
+        """Start rand(ConditionalNormalWishart(...)) of `entity` on the side stream; pair with nw_sample_fetch."""
+        A = np.asfortranarray(bartlettA, dtype=np.float64) if bartlettA is not None else None
+        zz = _f64(z) if z is not None else None
+        self._ck(self.lib.bdf_nw_sample_async(self.h, entity, _dp(_f64(mu0)), b0, _dp(np.asfortranarray(Tinv, dtype=np.float64)), nu, _dp(A), _dp(zz)))
+
+    def nw_sample_fetch(self, entity: int):
+        mu = np.zeros(self.D)
+        Lam = np.zeros((self.D, self.D), order="F")
+        self._ck(self.lib.bdf_nw_sample_fetch(self.h, entity, _dp(mu), _dp(Lam)))
+        return mu, Lam
+
+    # -- test set on the device (N1) ------------------------------------------------------------------------
+    def set_test(self, rel: int, ids, vals, test_F=None, class_cut: float = 0.0):
+        ids = np.asfortranarray(ids, dtype=np.int64)
+        vals = _f64(vals)
+        Fd = np.asfortranarray(test_F, dtype=np.float64) if test_F is not None else None
+        self._ck(self.lib.bdf_set_test(self.h, rel, C.c_int64(ids.shape[0]), ids.ctypes.data_as(_lib.c_i64p), _dp(vals), _dp(Fd), float(class_cut)))
+        self.ntest = getattr(self, "ntest", {})
+        self.ntest[rel] = int(ids.shape[0])
+
+    def test_reset(self, rel: int):
+        self._ck(self.lib.bdf_test_reset(self.h, rel))
+
+    def predict_accumulate(self, rel: int, posterior: bool, clamp=()):
+        """One iteration of src/macau.jl:143-200 on the device; returns (sse_avg, sse_sample, n_correct, ntest, counter)."""
+        lo, hi = (float(clamp[0]), float(clamp[1])) if clamp is not None and len(clamp) else (math.nan, math.nan)
+        out = np.zeros(5)
+        self._ck(self.lib.bdf_predict_accumulate(self.h, rel, int(bool(posterior)), lo, hi, _dp(out)))
+        return tuple(out)
+
+    def get_test_predictions(self, rel: int, want_last: bool = False):
+        n = self.ntest[rel]
+        avg, sq = np.zeros(n), np.zeros(n)
+        last = np.zeros(n) if want_last else None
+        self._ck(self.lib.bdf_get_test_predictions(self.h, rel, _dp(avg), _dp(sq), _dp(last)))
+        return (avg, sq, last) if want_last else (avg, sq)
+
     def step_sample(self, entity: int):
         self._ck(self.lib.bdf_step_sample(self.h, entity))
 

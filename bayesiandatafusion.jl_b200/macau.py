@@ -55,29 +55,96 @@ def bartlett_factor(rng: np.random.Generator, D: int, nu: float):
 
 def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.nan, burnin: int = 500, psamples: int = 200,
           verbose: bool = True, full_lambda_u: bool = True, reset_model: bool = True, compute_ff_size: int = 6500,
-          tol: float = math.nan, output: str = "", output_beta: bool = False, output_type: str = "binary", full_prediction: bool = False,
+          tol: float = math.nan, output: str = "", output_beta: bool = False, output_type: str = "csv", full_prediction: bool = False,
           clamp=(), f: Optional[Callable] = None, rmse_train: bool = False,
-          backend: str = "cuda", device: int = 0, seed: int = 0, host_noise: Optional[np.random.Generator] = None,
+          backend: str = "cuda", device: int = 0, devices=None, seed: int = 0, host_noise: Optional[np.random.Generator] = None,
           engine: Optional[Engine] = None):
-    """Same keywords as src/macau.jl:3-22 where they apply to this path, plus the switch flag `backend` (only "cuda"
-    exists here; the reference's `latent_pids` / `cg_pids` / `latent_blas_threads` select CPU workers and have no
-    meaning on the device) and `seed` / `host_noise`: with `host_noise` (a numpy Generator) the Normal-Wishart variates
-    are drawn on the host and injected, otherwise every draw uses the device Philox stream keyed by `seed`."""
+    """Same keywords as src/macau.jl:3-22 where they apply to this path, plus the switch flag `backend` (only "cuda" exists here; the
+    reference's `latent_pids` / `cg_pids` / `latent_blas_threads` select CPU workers and have no meaning on the device), `device` /
+    `devices` (the GPUs to use: `devices=[0, 1, 2, 3]` shards the rows of every entity over four GPUs, the counterpart of
+    `latent_pids`, src/macau.jl:12,44-66 — one worker process per extra device, see multi.py) and `seed` / `host_noise`: with
+    `host_noise` (a numpy Generator) the Normal-Wishart, alpha and lambda_beta variates are drawn on the host and injected, otherwise
+    every draw uses the device Philox stream keyed by `seed`.
+
+    State lives on the device during the run: the test set is registered once and the running posterior mean, the sum of squares,
+    the clamped RMSE and the accuracy of src/macau.jl:164-200 are accumulated there (bdf_predict_accumulate, 40 bytes back per
+    iteration); ROC needs a sort of the test predictions and is evaluated on the host when `verbose` and at the end. The host model
+    (`model.sample`, `model.beta`) is refreshed from the device before every call of `f(data)` and at the end."""
     if backend != "cuda":
         raise ValueError('backend must be "cuda": this package is the CUDA engine; the Julia path lives in the reference')
+    if output_beta and not output:  # src/macau.jl:26-28
+        raise ValueError("To output samples of beta ('output_beta = true') you have to set also output prefix, e.g., output = \"my_model\".")
+    if output_type not in ("csv", "binary"):  # src/macau.jl:30
+        raise ValueError('output_type must be either "csv" or "binary".')
     if not data.relations:
         raise ValueError("RelationData holds no relation")
+    if devices is not None and len(devices) > 1:
+        if engine is not None:
+            raise ValueError("`engine` and `devices` are mutually exclusive")
+        from .multi import macau_multi
+
+        return macau_multi(data, list(devices), dict(
+            num_latent=num_latent, lambda_beta=lambda_beta, burnin=burnin, psamples=psamples, verbose=verbose, full_lambda_u=full_lambda_u,
+            reset_model=reset_model, compute_ff_size=compute_ff_size, tol=tol, output=output, output_beta=output_beta, output_type=output_type,
+            full_prediction=full_prediction, clamp=clamp, f=f, rmse_train=rmse_train, seed=seed, host_noise=host_noise))
+    if devices is not None and len(devices) == 1:
+        device = int(devices[0])
+    eng = engine or Engine(num_latent, device=device)
+    try:
+        return _macau_loop(data, eng, None, num_latent=num_latent, lambda_beta=lambda_beta, burnin=burnin, psamples=psamples, verbose=verbose,
+                           full_lambda_u=full_lambda_u, reset_model=reset_model, compute_ff_size=compute_ff_size, tol=tol, output=output,
+                           output_beta=output_beta, output_type=output_type, full_prediction=full_prediction, clamp=clamp, f=f,
+                           rmse_train=rmse_train, seed=seed, host_noise=host_noise)
+    finally:
+        if engine is None:
+            eng.close()
+
+
+class _HostAccumulators:
+    """src/macau.jl:164-200 on the host, for engine objects without the device-side test set (test doubles passed as `engine=`)."""
+
+    def __init__(self, rel, clamp):
+        self.rel, self.clamp = rel, clamp
+        self.all = np.zeros(rel.numTest())
+        self.sq = np.zeros(rel.numTest())
+        self.counter = 0
+
+    def step(self, probe_rat, posterior):
+        if not posterior:
+            self.all = probe_rat
+        elif self.counter == 0:
+            self.all, self.sq, self.counter = probe_rat.copy(), probe_rat ** 2, 1
+        else:
+            self.all = (self.counter * self.all + probe_rat) / (self.counter + 1)
+            self.sq = self.sq + probe_rat ** 2
+            self.counter += 1
+        rel = self.rel
+        sse = float(np.sum((rel.test_values - makeClamped(self.all, self.clamp)) ** 2))
+        sse_s = float(np.sum((rel.test_values - makeClamped(probe_rat, self.clamp)) ** 2))
+        ok = float(np.sum(rel.test_label == (self.all < rel.class_cut)))
+        return sse, sse_s, ok, float(rel.numTest()), float(self.counter)
+
+
+def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, verbose, full_lambda_u, reset_model, compute_ff_size, tol,
+                output, output_beta, output_type, full_prediction, clamp, f, rmse_train, seed, host_noise):
+    """The Gibbs loop of src/macau.jl:80-254 over one engine. `comm` is None on one GPU; with several GPUs every rank runs this loop on
+    its handle (rank/world set at bdf_create) and `comm` (multi.Comm) carries the all-reduces between the kernels — the statistics of
+    ConditionalNormalWishart, the training SSE behind alpha, the test-set sums — so that every rank draws the identical hyper-parameters
+    from identical inputs; rank 0 owns the printing, the dumps and the result."""
     rel = data.relations[0]  # predictions / RMSE are reported for the first relation, as in src/macau.jl:142-143
+    lead = comm is None or comm.rank == 0
+    verbose = verbose and lead
     if verbose:
         print("Model setup")
     if reset_model:
         data.reset(num_latent, lambda_beta=lambda_beta, compute_ff_size=compute_ff_size)
     D = num_latent
     K = len(rel.entities)
-
-    eng = engine or Engine(D, device=device)
     eng.set_seed(seed)
-    ents = [eng.add_entity(en.count) for en in data.entities]
+    if comm is not None:
+        ents = [comm.add_entity(eng, en, data) for en in data.entities]
+    else:
+        ents = [eng.add_entity(en.count) for en in data.entities]
     eid = {id(en): e for e, en in zip(ents, data.entities)}
     r_ids = []
     for r in data.relations:
@@ -96,20 +163,43 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             eng.set_features(e, en.F)
             if en.use_FF:
                 eng.compute_ff(e)  # en.FF = full(At_mul_B(en.F, en.F)) — reset!, src/RelationData.jl:337-339
+    if comm is not None:
+        comm.connect(eng, ents)  # peer mappings for the fused all-gather of the drawn rows
 
     if verbose:
         print("Sampling")
     ntest = rel.numTest()
-    probe_rat_all = np.zeros(ntest)
-    probe_stdev = np.zeros(ntest)
-    counter_prob = 1
+    dev_test = ntest > 0 and hasattr(eng, "predict_accumulate")
+    if dev_test:
+        # every rank registers its share of the test set (all ranks hold every factor row); the sums are all-reduced below
+        sl = slice(None) if comm is None else slice(comm.rank, None, comm.world)
+        eng.set_test(r_id, rel.test_ids[sl], rel.test_values[sl], rel.test_F[sl] if rel.hasFeatures() else None, rel.class_cut)
+        host_acc = None
+    else:
+        host_acc = _HostAccumulators(rel, clamp) if ntest else None
+    if hasattr(eng, "set_async"):
+        eng.set_async(True)  # half-sweeps return once enqueued; a numeric failure surfaces at the next call that reads results back
+    train_rat_all, train_counter = None, 0
     yhat_full = np.zeros(tuple(rel.data.dims), order="F") if full_prediction else None
     rmse_avg = roc_avg = err_avg = math.nan
     f_output = []
-    if math.isnan(tol):
-        tol_arg = math.nan
-    else:
-        tol_arg = float(tol)
+    tol_arg = math.nan if math.isnan(tol) else float(tol)
+    stale = True  # the host model lags behind the device
+
+    def refresh_host_model():
+        for e, en in zip(ents, data.entities):
+            en.model.sample = eng.get_factors(e)
+            if en.hasFeatures():
+                en.model.beta = eng.get_beta(e)
+
+    def test_predictions():
+        """(probe_rat_all, probe_stdev) in test-set order on the lead rank."""
+        if host_acc is not None:
+            return host_acc.all, host_acc.sq
+        avg, sq = eng.get_test_predictions(r_id)
+        if comm is None:
+            return avg, sq
+        return comm.gather_strided(avg, ntest), comm.gather_strided(sq, ntest)
 
     for i in range(1, burnin + psamples + 1):
         time0 = time.time()
@@ -117,6 +207,8 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         for rid, r in zip(r_ids, data.relations):
             if r.model.alpha_sample:
                 sse, n = eng.train_sse(rid)
+                if comm is not None:
+                    sse, n = comm.allreduce_scalars([sse, n])
                 c2 = host_noise.chisquare(r.model.alpha_nu0 + n) if host_noise is not None else math.nan
                 r.model.alpha = eng.sample_alpha(rid, r.model.alpha_lambda0, r.model.alpha_nu0, sse, n, c2)
                 eng.set_relation_params(rid, r.model.alpha, r.model.mean_value)
@@ -125,6 +217,7 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
                 z2 = host_noise.standard_normal(r.F.shape[1]) if host_noise is not None else None
                 r.model.beta = eng.sample_beta_rel(rid, r.model.lambda_beta, z1, z2)
         # Sampling latent vectors — src/macau.jl:96-134 (entities in several relations: sample_user2_all!, :109-118)
+        pending = []
         for e, en in zip(ents, data.entities):
             mj = en.model
             if en.hasFeatures():
@@ -133,19 +226,32 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             else:
                 eng.sample_mode(e, mj.mu, mj.Lambda, None)
             nu, Tinv = mj.nu0, mj.WI
+            need_N = host_noise is not None
             if en.hasFeatures():
-                N, NU, NS = eng.nw_stats_uhat(e)
+                if comm is None:
+                    N, NU, NS = eng.nw_stats_uhat(e)
+                else:
+                    N = comm.nw_stats(eng, e, uhat=True)
                 if full_lambda_u:
                     nu = nu + mj.beta.shape[0]
                     Tinv = Tinv + eng.beta_gram(e) * en.lambda_beta
-            else:
+            elif comm is not None:
+                N = comm.nw_stats(eng, e, uhat=False)   # device statistics, all-reduced over the ranks
+            elif need_N or not hasattr(eng, "step_nw_stats"):
                 N, NU, NS = eng.nw_stats(e)
-            if host_noise is not None:
-                A = bartlett_factor(host_noise, D, nu + N)
-                z = host_noise.standard_normal(D)
-                mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu, A, z)
             else:
-                mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu)
+                eng.step_nw_stats(e)                    # the statistics stay on the device: the draw reads them there
+                N = float(en.count)
+            A = bartlett_factor(host_noise, D, nu + N) if host_noise is not None else None
+            z = host_noise.standard_normal(D) if host_noise is not None else None
+            if hasattr(eng, "nw_sample_async"):
+                # the draw is first needed by THIS entity's next half-sweep: it runs beside the next entity's row kernel
+                eng.nw_sample_async(e, mj.mu0, mj.b0, Tinv, nu, A, z)
+                pending.append((e, mj))
+            else:
+                mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu, A, z)
+        for e, mj in pending:
+            mj.mu, mj.Lambda = eng.nw_sample_fetch(e)
         # update_beta! — src/macau.jl:138-140, src/sampling.jl:361-370
         for e, en in zip(ents, data.entities):
             if en.hasFeatures():
@@ -156,13 +262,22 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
                         g = host_noise.standard_gamma((en.nu + en.F.shape[1] * D) / 2.0)
                     en.lambda_beta, _ = eng.sample_lambda_beta(e, en.model.Lambda, en.nu, en.mu, g)
         eng.advance_sweep()
+        stale = True
 
-        probe_rat = eng.predict(r_id, rel.test_ids, rel.test_F if rel.hasFeatures() else None) if ntest else np.zeros(0)
-        if i > burnin:
-            if output:
+        posterior = i > burnin
+        if ntest:
+            if dev_test:
+                sums = eng.predict_accumulate(r_id, posterior, clamp)
+                if comm is not None:
+                    sums = comm.allreduce_scalars(list(sums[:4])) + [sums[4]]
+            else:
+                probe_rat = eng.predict(r_id, rel.test_ids, rel.test_F if rel.hasFeatures() else None)
+                sums = host_acc.step(probe_rat, posterior)
+            rmse_avg = math.sqrt(sums[0] / sums[3])   # src/macau.jl:196
+            err_avg = sums[2] / sums[3]                # :193-194
+        if posterior:
+            if output and lead:
                 # saving latent vectors to disk — src/macau.jl:149-162 (Float32, num_latent × count as Julia holds model.sample)
-                if output_type not in ("binary", "csv"):
-                    raise ValueError('output_type must be "binary" or "csv"')
                 ndigits = int(math.floor(math.log10(psamples))) + 1
                 nstr = str(i - burnin).rjust(ndigits, "0")
                 for e, en in zip(ents, data.entities):
@@ -175,49 +290,47 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
                             write_binary_matrix(f"{output}-{en.name}-{nstr}{tag}.binary", X32)
                         else:
                             np.savetxt(f"{output}-{en.name}-{nstr}{tag}.csv", X32, delimiter=",", fmt="%.9g")
+            if rmse_train:
+                # train_rat = pred(rel) averaged over the posterior samples like probe_rat_all — src/macau.jl:164-178
+                train_rat = eng.predict(r_id, rel.data.ids, rel.F if rel.hasFeatures() else None)
+                if train_counter == 0:
+                    train_rat_all, train_counter = train_rat, 1
+                else:
+                    train_rat_all = (train_counter * train_rat_all + train_rat) / (train_counter + 1)
+                    train_counter += 1
             if full_prediction:
                 if rel.hasFeatures():
                     raise ValueError("Prediction of all elements is not possible when Relation has features.")  # src/sampling.jl:93-95
                 yhat_full += eng.predict_all(r_id, tuple(rel.data.dims))  # pred_all — src/macau.jl:145-146
-            if i == burnin + 1:
-                if verbose:
-                    print("--------- Burn-in complete, averaging posterior samples ----------")
-                counter_prob = 1
-                probe_rat_all = probe_rat.copy()
-                probe_stdev = probe_rat ** 2
-            else:
-                probe_rat_all = (counter_prob * probe_rat_all + probe_rat) / (counter_prob + 1)
-                probe_stdev = probe_stdev + probe_rat ** 2
-                counter_prob += 1
-        else:
-            probe_rat_all = probe_rat
-        if callable(f) and i > burnin:
-            f_output.append(f(data))
+            if i == burnin + 1 and verbose:
+                print("--------- Burn-in complete, averaging posterior samples ----------")
+            if callable(f) and lead:
+                if stale:
+                    refresh_host_model()  # f(data) sees the live sample / beta, as in src/macau.jl:186-189
+                    stale = False
+                f_output.append(f(data))
         time1 = time.time()
-
-        haveTest = ntest > 0
-        if haveTest:
-            correct = rel.test_label == (probe_rat_all < rel.class_cut)
-            err_avg = float(correct.mean())
-            clamped_all = makeClamped(probe_rat_all, clamp)
-            rmse_avg = float(np.sqrt(np.mean((rel.test_values - clamped_all) ** 2)))
-            roc_avg = AUC_ROC(rel.test_label, -probe_rat_all)
+        if ntest and (verbose or i == burnin + psamples):
+            if comm is None or verbose or i == burnin + psamples:
+                pa, _ = test_predictions()
+                if lead:
+                    roc_avg = AUC_ROC(rel.test_label, -pa)   # src/macau.jl:198, src/ROC.jl
         if verbose:
             print(f"{i:3d}: ROC={roc_avg:6.4f} RMSE={rmse_avg:6.4f} | " +
                   " ".join(f"{en.name[:3]}[mu:{np.linalg.norm(en.model.mu):6.2f}]" for en in data.entities) + " | " +
                   " ".join(f"{r.name[:4]}[a={r.model.alpha:2.1f}]" for r in data.relations) + f" [{time1 - time0:1.1f}s]")
 
-    # the device holds the state during the run; hand the final sample back to the host model (model.sample)
-    for e, en in zip(ents, data.entities):
-        en.model.sample = eng.get_factors(e)
-        if en.hasFeatures():
-            en.model.beta = eng.get_beta(e)
+    # the device holds the state during the run; hand the final sample back to the host model (model.sample, model.beta)
+    if stale:
+        refresh_host_model()
 
     result = {
         "num_latent": num_latent, "burnin": burnin, "psamples": psamples, "lambda_beta": data.entities[0].lambda_beta,
         "RMSE": rmse_avg, "accuracy": err_avg, "ROC": roc_avg, "latent_multi_threading": True,
     }
     if ntest > 0:
+        probe_rat_all, probe_stdev = test_predictions()
+    if ntest > 0 and lead:
         pred = makeClamped(probe_rat_all, clamp)
         if psamples >= 3:
             tmp = (probe_stdev - probe_rat_all ** 2 * psamples) / (psamples - 1)
@@ -232,12 +345,9 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
         result["train_counts"] = train_count
     if full_prediction:
         result["predictions_full"] = yhat_full / psamples  # src/macau.jl:228-230
-    if rmse_train:
-        tr = eng.predict(r_id, rel.data.ids)
-        result["RMSE_train"] = float(np.sqrt(np.mean((rel.data.values - makeClamped(tr, clamp)) ** 2)))
+    if rmse_train and train_rat_all is not None:
+        result["RMSE_train"] = float(np.sqrt(np.mean((rel.data.values - makeClamped(train_rat_all, clamp)) ** 2)))  # :222-226
     if callable(f):
         result["f_output"] = f_output
     result["gpu_launches"] = eng.launches
-    if engine is None:
-        eng.close()
     return result

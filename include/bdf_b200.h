@@ -155,6 +155,39 @@ int bdf_set_relation_beta(bdf_t* h, int rel, const double* beta);
  * without features, where this is bdf_predict). */
 int bdf_predict_f(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, const double* test_F, double* yhat);
 
+/* ---- test set and posterior accumulators on the device — src/macau.jl:142-203 ---------------------------------- */
+/* Registers the held-out observations of a relation ONCE (setTest! / assignToTest!, src/RelationData.jl:191-233): ids ntest×K
+ * column-major 1-based, vals (ntest), test_F = the relation-level feature rows (ntest × nF column-major; NULL unless the relation has
+ * features), class_cut = the threshold behind test_label (src/RelationData.jl:203). Replaces any earlier test set; ntest = 0 removes it.
+ * With world > 1 every rank registers its own share of the test set (all ranks hold every factor row) and adds up the sums below. */
+int bdf_set_test(bdf_t* h, int rel, int64_t ntest, const int64_t* ids, const double* vals, const double* test_F, double class_cut);
+/* Forget the posterior accumulators (counter_prob = 0). */
+int bdf_test_reset(bdf_t* h, int rel);
+/* One iteration of src/macau.jl:143-200 on the device: probe_rat = pred(rel, test_vec, test_F); posterior == 0 (burn-in):
+ * probe_rat_all = probe_rat; posterior != 0: the first such call sets probe_rat_all = probe_rat, probe_stdev = probe_rat.^2, later ones
+ * probe_rat_all = (counter_prob*probe_rat_all + probe_rat)/(counter_prob + 1), probe_stdev += probe_rat.^2 (:164-176). Returns
+ * out[0] = sum((test_values - makeClamped(probe_rat_all, clamp)).^2)   (rmse_avg = sqrt(out[0]/out[3]), :196)
+ * out[1] = the same for the current sample probe_rat
+ * out[2] = sum(test_label .== (probe_rat_all .< class_cut))            (err_avg = out[2]/out[3], :193-194)
+ * out[3] = ntest, out[4] = counter_prob after this call.
+ * clamp_lo / clamp_hi: NaN = not clamped (clamp = Float64[], src/sampling.jl:99-106). The only device→host traffic is these 5 doubles. */
+int bdf_predict_accumulate(bdf_t* h, int rel, int posterior, double clamp_lo, double clamp_hi, double* out5);
+/* probe_rat_all (unclamped), probe_stdev (the running sum of squares) and the last sample's probe_rat, ntest doubles each; any may be
+ * NULL. For result["predictions"] (src/macau.jl:233-241) and ROC (src/ROC.jl), which stay on the host. */
+int bdf_get_test_predictions(bdf_t* h, int rel, double* avg_out, double* sumsq_out, double* last_out);
+
+/* ---- deferred completion of the host-pointer seams ------------------------------------------------------------------------------- */
+/* on != 0: bdf_sample_mode / bdf_sample_mode_uhat return as soon as their work is enqueued (the host arrays have been copied by then);
+ * a numeric failure (precision matrix not positive definite) is reported by the next call that synchronises — bdf_nw_stats*,
+ * bdf_nw_sample*, bdf_predict*, bdf_get_*, bdf_synchronize. Default 0: every host-pointer entry returns after the stream is drained. */
+int bdf_set_async(bdf_t* h, int on);
+/* rand(ConditionalNormalWishart(...)) split in two so that the draw of one entity overlaps the next entity's half-sweep — the draw is first
+ * needed by the SAME entity's next half-sweep (src/macau.jl:96-134 keeps entities independent within an iteration). _async copies the
+ * host arguments, runs the draw on the handle's high-priority side stream and returns; _fetch blocks until that draw is done, returns
+ * (mu, Lambda) and orders it before whatever the handle does next. Same arguments and results as bdf_nw_sample. */
+int bdf_nw_sample_async(bdf_t* h, int entity, const double* mu0, double b0, const double* Tinv, double nu, const double* bartlettA, const double* z);
+int bdf_nw_sample_fetch(bdf_t* h, int entity, double* mu_out, double* Lambda_out);
+
 /* ---- Macau side features: the link-matrix (beta) path ------------------------------------------------------------- */
 
 /* Entity(F = SparseBinMatrix(m, n, rows, cols)) — src/parallel_matrix.jl:9-24: registers a sparse 0/1 feature matrix given

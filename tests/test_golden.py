@@ -8,7 +8,7 @@ import pytest
 
 from oracle import oracle as orc
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "row_draw_*.npz")))
 
 
 def load(path):

@@ -192,7 +192,7 @@ def test_pred_all_full_prediction_and_output_dumps(tmp_path):
     Y = sp.csc_matrix(np.where(rng.random((N, M)) < 0.4, U[:, :2] @ V[:, :2].T, 0.0))
     rd = bdf_b200.RelationData(Y, feat1=F, class_cut=0.0, alpha=5.0)
     out = str(tmp_path / "run")
-    res = bdf_b200.macau(rd, num_latent=4, burnin=3, psamples=4, verbose=False, full_prediction=True, output=out, output_beta=True, seed=2)
+    res = bdf_b200.macau(rd, num_latent=4, burnin=3, psamples=4, verbose=False, full_prediction=True, output=out, output_beta=True, output_type="binary", seed=2)
     assert res["predictions_full"].shape == (N, M) and np.all(np.isfinite(res["predictions_full"]))
     S = dr.read_binary_float32(f"{out}-E1-4.binary")           # the last sample, as Float32, num_latent × count
     assert S.shape == (4, N) and np.allclose(S.T, rd.entities[0].model.sample, rtol=1e-6, atol=1e-6)

@@ -24,7 +24,7 @@ def test_bpmf_loop_order_averaging_dumps_and_full_prediction(tmp_path):
     eng = OracleEngine(3)
     out = str(tmp_path / "run")
     res = bdf_b200.macau(rd, num_latent=3, burnin=8, psamples=12, verbose=False, engine=eng, host_noise=np.random.default_rng(2),
-                         output=out, full_prediction=True, rmse_train=True, clamp=[-10.0, 10.0])
+                         output=out, output_type="binary", full_prediction=True, rmse_train=True, clamp=[-10.0, 10.0])
     # Gauss-Seidel order per iteration: entity 1 {latents, stats, draw}, entity 2 {latents, stats, draw}, sweep counter
     per = [("sample", 0), ("stats", 0), ("draw", 0), ("sample", 1), ("stats", 1), ("draw", 1), ("sweep",)]
     assert eng.calls == per * 20

@@ -12,27 +12,13 @@ import torch
 sys.path.insert(0, ".")
 import bdf_b200
 
+from tools.workloads import c3_macau
+
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 D = 32
-N, NT, NNZ, NUMF, BITS = int(170000 * scale), 1000, int(1500000 * scale), int(100000 * scale), 64
-rng = np.random.default_rng(20161017 + 2)
-ids = np.stack([rng.integers(1, N + 1, NNZ), rng.integers(1, NT + 1, NNZ)], axis=1)
-vals = rng.standard_normal(NNZ)
-# 64 distinct set bits per compound, Zipf(1.1) bit popularity: weighted draws with replacement, de-duplicated per row,
-# topped up with uniform bits where a row came out short
-w = 1.0 / np.arange(1, NUMF + 1) ** 1.1
-w /= w.sum()
-draw = rng.choice(NUMF, size=(N, 2 * BITS), p=w).astype(np.int32)
-cols = np.empty((N, BITS), dtype=np.int32)
-for i in range(N):
-    u = np.unique(draw[i])
-    if len(u) >= BITS:
-        cols[i] = rng.permutation(u)[:BITS] + 1
-    else:
-        extra = np.setdiff1d(rng.permutation(NUMF)[: 4 * BITS], u)[: BITS - len(u)]
-        cols[i] = np.concatenate([u, extra]) + 1
-rows = np.repeat(np.arange(1, N + 1, dtype=np.int32), BITS)
-F = bdf_b200.SparseBinMatrix(rows, cols.ravel(), N, NUMF)
+w = c3_macau(scale, D)
+N, NT, NNZ, NUMF, BITS, ids, vals = w["N"], w["NT"], w["NNZ"], w["NUMF"], w["BITS"], w["ids"], w["vals"]
+F = bdf_b200.SparseBinMatrix(w["rows"], w["cols"], N, NUMF)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 eng = bdf_b200.Engine(D)
 eng.set_stream(stream.cuda_stream)

@@ -12,15 +12,12 @@ import torch
 sys.path.insert(0, ".")
 import bdf_b200
 
+from tools.workloads import c4_tensor
+
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 D = 30
-dims = [20000, 5000, 200]
-NNZ = int(50_000_000 * scale)
-rng = np.random.default_rng(20161017 + 3)
-ids = np.empty((NNZ, 3), dtype=np.int64, order="F")
-for m, d in enumerate(dims):
-    ids[:, m] = np.minimum((d * rng.random(NNZ) ** 2.5).astype(np.int64), d - 1) + 1   # skewed marginals, SURVEY §8d
-vals = rng.standard_normal(NNZ)
+w = c4_tensor(scale)
+dims, NNZ, ids, vals = w["dims"], w["NNZ"], w["ids"], w["vals"]
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 eng = bdf_b200.Engine(D)
 eng.set_stream(stream.cuda_stream)
