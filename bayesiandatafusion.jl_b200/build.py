@@ -12,8 +12,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libbdf_b200.so")
+# variant builds for A/B measurements: BDF_LIB_TAG=<tag> BDF_EXTRA_NVCC="-D..." → libbdf_<tag>.so from its own object directory
+TAG = os.environ.get("BDF_LIB_TAG", "")
+OBJ = os.path.join(HERE, "build_" + TAG if TAG else "build")
+LIB = os.path.join(HERE, f"libbdf_{TAG}.so" if TAG else "libbdf_b200.so")
 DPS = [8, 16, 24, 32, 40, 48, 56, 64, 72, 80, 88, 96, 104, 112, 120, 128]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -52,12 +54,14 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if ptxas_v else []
+    if TAG:
+        extra = extra + os.environ.get("BDF_EXTRA_NVCC", "").split()
     jobs = []
     for name in ("engine", "features", "predict"):
         if force or _stale(os.path.join(OBJ, f"{name}.o"), deps):
             jobs.append((os.path.join(CSRC, f"{name}.cu"), os.path.join(OBJ, f"{name}.o"), extra))
     only = os.environ.get("BDF_BUILD_DPS")  # dev builds: recompile only these padded dimensions (others keep their objects)
-    extra_defs = os.environ.get("BDF_EXTRA_NVCC", "").split()
+    extra_defs = [] if TAG else os.environ.get("BDF_EXTRA_NVCC", "").split()
     for dp in DPS:
         if only and str(dp) not in only.split(",") and os.path.exists(os.path.join(OBJ, f"row_inst_{dp}.o")):
             continue

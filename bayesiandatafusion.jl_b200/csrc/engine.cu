@@ -598,6 +598,9 @@ int bdf_create(bdf_t** out, int device, int num_latent, int rank, int world) {
     cudaMemcpy(h->ones, one.data(), sizeof(double) * h->ld, cudaMemcpyHostToDevice);
   }
   h->num_sms = prop.multiProcessorCount;
+  if ((ce = cudaMalloc((void**)&h->work_counter, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+  // the persistent warp-specialised row kernel (row_kernel_ws.cuh) is opt-in: measured slower than one CTA per row on C2 (profiles/README.md)
+  { const char* ws = getenv("BDF_ROWS_WS"); h->use_ws = ws && ws[0] == '1'; }
   cudaMemset(h->err_flag, 0, sizeof(int));
   if ((ce = cudaMalloc((void**)&h->scratch, sizeof(double) * ((size_t)4 * num_latent * num_latent + 4 * num_latent))) != cudaSuccess) return bail(ce, "cudaMalloc");
   if ((ce = cudaMalloc((void**)&h->lt, sizeof(double) * (64 * (size_t)(h->DP / 8) * (h->DP / 8 + 1) / 2 + h->DP))) != cudaSuccess) return bail(ce, "cudaMalloc");
@@ -634,7 +637,7 @@ int bdf_destroy(bdf_t* h) {
       free_work_list(mi);
       cudaFree(mi.perm); cudaFree(mi.val_adj);
     }
-  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->ones); cudaFree(h->arena); cudaFree(h->arena2);
+  cudaFree(h->ws); cudaFree(h->scratch); cudaFree(h->err_flag); cudaFree(h->lt); cudaFree(h->ones); cudaFree(h->arena); cudaFree(h->arena2); cudaFree(h->work_counter);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1104,14 +1107,36 @@ int bdf_debug_phase_clocks(bdf_t* h, int entity, double* mean_cycles /* 7 */, in
   if (e.uses.empty()) FAIL(BDF_ERR_STATE, "entity takes part in no relation");
   const int ni = e.uses.size() > 1 && e.merged_uses == e.uses.size() ? e.merged.n_items : h->rels[e.uses[0].first].modes[e.uses[0].second].n_items;
   long long* d = nullptr;
-  CU(cudaMalloc((void**)&d, sizeof(long long) * 16 * (size_t)std::max(ni, 1)));
-  CU(cudaMemsetAsync(d, 0, sizeof(long long) * 16 * (size_t)std::max(ni, 1), h->stream));
+  const size_t nd = 16 * (size_t)std::max(ni, 1000);
+  CU(cudaMalloc((void**)&d, sizeof(long long) * nd));
+  CU(cudaMemsetAsync(d, 0, sizeof(long long) * nd, h->stream));
   int rc = sample_entity(h, entity, e.mu, 0, e.Lambda, nullptr, d);
-  std::vector<long long> hbuf((size_t)16 * std::max(ni, 1));
+  std::vector<long long> hbuf(nd);
   cudaMemcpyAsync(hbuf.data(), d, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
   cudaFree(d);
   if (rc) return rc;
+  if (getenv("BDF_DEBUG_WS")) {  // persistent warp-specialised kernel: per-group busy / wait cycles, averaged over the CTAs
+    double a[5][5] = {{0}};
+    const int nb = std::min(h->num_sms, (ni + 1) / 2);
+    for (int b = 0; b < nb; b++)
+      for (int g = 0; g < 5; g++)
+        for (int k = 0; k < 5; k++) a[g][k] += (double)hbuf[((size_t)b * 5 + g) * 8 + k] / nb;
+    for (int g = 0; g < 2; g++)
+      fprintf(stderr, "  syrk group %d: total %.0f  syrk+split %.0f  wait-for-slot %.0f  park %.0f  rows parked %.0f\n", g, a[g][0], a[g][1], a[g][2], a[g][3], a[g][4]);
+    {
+      double t[5] = {0};
+      for (int b = 0; b < nb; b++)
+        for (int g = 0; g < 2; g++)
+          for (int k = 0; k < 5; k++) t[k] += (double)hbuf[((size_t)nb * 5 + (size_t)b * 2 + g) * 8 + k] / (2 * nb);
+      fprintf(stderr, "  syrk_item of warp 0, per group: prologue %.0f  wait-for-stage %.0f  group barrier %.0f  issue+meta %.0f  compute %.0f\n", t[0], t[1], t[2], t[3], t[4]);
+    }
+    for (int g = 2; g < 5; g++)
+      fprintf(stderr, "  finalise group %d: total %.0f  wait-for-row %.0f  factor+draw %.0f  rows %.0f\n", g - 2, a[g][0], a[g][1], a[g][2], a[g][4]);
+    for (int k = 0; k < 7; k++) mean_cycles[k] = 0.0;
+    if (n_items) *n_items = ni;
+    return BDF_OK;
+  }
   for (int k = 0; k < 7; k++) mean_cycles[k] = 0.0;
   int64_t cnt = 0;
   for (int i = 0; i < ni; i++) {

@@ -161,6 +161,8 @@ struct bdf_handle {
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: the opt-in is remembered per handle (a handle is bound to one
   // device), one bit per kernel family — not in a process-wide static
   uint32_t smem_optin = 0;
+  int* work_counter = nullptr;      // work queue head of the persistent row kernel
+  bool use_ws = false;              // BDF_ROWS_WS=1 in the environment at bdf_create selects the persistent warp-specialised kernel for 64 < D <= 104
   bool async_mode = false;          // bdf_set_async
   cudaStream_t side = nullptr;      // high-priority side stream of bdf_nw_sample_async (created on first use)
   cudaEvent_t ev_ready = nullptr;

@@ -1,11 +1,13 @@
 // One padded latent dimension (-DBDF_DP=...) of the row-draw and statistics kernels; build.py compiles this file
 // once per DP so the 16 instances build in parallel.
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 
 #include "../../include/bdf_b200.h"
 #include "engine.cuh"
 #include "row_kernel.cuh"
+#include "row_kernel_ws.cuh"
 #include "stats_kernel.cuh"
 
 #ifndef BDF_DP
@@ -22,8 +24,40 @@ static constexpr int kDP = BDF_DP;
 #endif
 static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : BDF_NW_BIG);
 
+// 64 < D <= 104, 2-mode relations: the persistent warp-specialised kernel (5 rows in flight per SM instead of 4, row_kernel_ws.cuh) is
+// compiled in and parity-tested, but opt-in (BDF_ROWS_WS=1 at bdf_create): on C2 it measured slower than one CTA per row
+#ifndef BDF_USE_WS
+#define BDF_USE_WS 1
+#endif
+static constexpr bool kWS = BDF_USE_WS && kDP > 64 && kDP <= 104;  // three 8·tri(DP/8)·64-byte tile slots + two gather rings must fit 227 KB
+
+static int launch_rows_ws(bdf_t* h, const RowParams& p0, int n_items) {
+  if constexpr (kWS) {
+    using W = RowKernelWS<kDP, false>;
+    static_assert(W::SMEM_BYTES <= 227 * 1024, "shared memory of the persistent kernel");
+    if (!(h->smem_optin & BDF_OPTIN_ROWS_WS)) {
+      CU(cudaFuncSetAttribute(row_kernel_ws<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES));
+      h->smem_optin |= BDF_OPTIN_ROWS_WS;
+    }
+    if (n_items > 0) {
+      RowParams p = p0;
+      p.work_counter = h->work_counter;
+      p.n_items = n_items;
+      CU(cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+      const int grid = std::min(h->num_sms, (n_items + W::NSG - 1) / W::NSG);
+      row_kernel_ws<W><<<grid, W::NTHR, W::SMEM_BYTES, h->stream>>>(p);
+      h->launches++;
+      CU(cudaGetLastError());
+    }
+  }
+  return BDF_OK;
+}
+
 template <bool TENSOR>
 static int launch_rows_t(bdf_t* h, const RowParams& p, int n_items) {
+  if constexpr (kWS && !TENSOR) {
+    if (h->use_ws) return launch_rows_ws(h, p, n_items);
+  }
   using K = RowKernel<kDP, kNW, TENSOR>;
   const uint32_t bit = TENSOR ? BDF_OPTIN_ROWS_TENSOR : BDF_OPTIN_ROWS;
   if (!(h->smem_optin & bit)) {

@@ -102,6 +102,7 @@ struct RowParams {
   int entity;
   int* err_flag;
   int n_items;
+  int* work_counter;  // work queue head of the persistent warp-specialised kernel (row_kernel_ws.cuh), zeroed before each launch
 #ifdef BDF_DEBUG  // profiling builds only (tools/phase_probe*.py): the release library carries neither the fields nor the code
   int flags;       // bit 0 = return after the syrk, bit 1 = no DMMAs, bit 2 = no gather (timing experiments only; results invalid)
   long long* dbg;  // optional per-item phase clocks [n_items][8] (bdf_debug_phase_clocks), else nullptr
@@ -126,6 +127,12 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -203,7 +210,25 @@ __device__ __forceinline__ void tri_coords(int t, int& I, int& J) {
 }
 
 
-template <int DP_, int NW_, bool TENSOR_>
+// group-wide synchronisation of the code below: the whole CTA (one row per CTA) or one 4-warp group of the warp-specialised
+// persistent kernel (row_kernel_ws.cuh), which uses a named barrier per group
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct GroupSync {
+  int id, nthreads;
+  __device__ __forceinline__ void operator()() const { named_bar(id, nthreads); }
+};
+
+// one work item, as every thread of its group sees it
+struct RowCtx {
+  int item, lrow, len, split;
+  int64_t obeg, slot;
+  const RelTab* rt;
+  double alpha_f;  // a row fed by one work item scales its Gram matrix by α when parking it; the partials of a split row are parked already scaled
+};
+
+template <int DP_, int NW_, bool TENSOR_, int KS_ = 0, int NBUF_ = 0>
 struct RowKernel {
   static constexpr int DP = DP_;
   static constexpr int NW = NW_;
@@ -218,17 +243,20 @@ struct RowKernel {
   static constexpr int PST = NW * TPW * 64 + DP;  // doubles per parked partial
   // gather ring of the row kernel
   static constexpr int GP = NW == 8 ? 1 : (NW == 4 ? 2 : 8);  // passes per stage
-  static constexpr int KS = OPP * GP;                          // observations per stage (16)
-  static constexpr int NBUF = NW == 1 ? BDF_NBUF1 : 3;
+  static constexpr int KS = KS_ > 0 ? KS_ : OPP * GP;         // observations per stage (16)
+  static constexpr int NBUF = NBUF_ > 0 ? NBUF_ : (NW == 1 ? BDF_NBUF1 : 3);
+  static constexpr int PF = NBUF - 1;                          // stages in flight ahead of the one being consumed
   static constexpr int STG = KS * S * (TENSOR ? 2 : 1) + KS;   // doubles per stage: tile(s) + residuals
   static constexpr int PSZ = 64 * C::NT;  // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
   static constexpr int REGSZ = PSZ > NBUF * STG ? PSZ : NBUF * STG;  // the tiles alias the (dead) stage ring
-  static constexpr int SMEM_DOUBLES = REGSZ + NB * 64 + 4 * DP + 8 + 4;  // … + ts[8] + ring mbarriers
+  static constexpr int META_D = 4 * KS;  // stage metadata, double-buffered: partner slots (2 × KS × 2 ints) and values (2 × KS doubles)
+  static constexpr int SMEM_DOUBLES = REGSZ + 4 * DP + 8 + 4 + META_D;  // … rhs, Λμ, y, x, ts[8], ring mbarriers, stage metadata
   static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
   // register-staged loader of the statistics kernel (stats_kernel.cuh)
   static constexpr int SPASSES = NW == 8 ? 2 : (NW == 4 ? 4 : 8);
   static constexpr int SKS = OPP * SPASSES;
   static constexpr int SBUFSZ = 2 * SKS * S + 2 * SKS;
+  static_assert(KS % NW == 0 && KS % 4 == 0 && KS / NW <= 32, "a stage is issued KS/NW rows per warp and consumed in k-steps of 4");
 
   struct Pre {
     double2 a[SPASSES][JP];
@@ -302,98 +330,111 @@ struct RowKernel {
     });
   }
 
-  // ---- the kernel body -------------------------------------------------------------------------------------
-  static __device__ void run(const RowParams& p, double* smem) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = p.D;
-    const bool aug = use_aug(D);
-    const int item = blockIdx.x;
-    const int lrow = p.item_row[item];
-    const int64_t obeg = p.item_beg[item];
-    const int len = p.item_len[item];
-    const int64_t oend = obeg + len;
-    const int split = p.item_split[item];
-    const int64_t slot = p.slot_base + lrow;
-    const RelTab& rt = p.rt[p.item_rel ? p.item_rel[item] : 0];
-    // a row fed by one work item scales its Gram matrix by α when parking it; the partials of a row split over several items
-    // (chunks of a long row, or one relation each) are parked already scaled by their own α and just add up
-    const double alpha_f = split < 0 ? rt.alpha : 1.0;
-
-    double* ring = smem;                    // [NBUF][STG]: tile (KS×S), [second tile], residuals (KS)
-    double* Tl = smem;                      // Λ* / factor tiles, alias the ring after the main loop
-    double* WvT = smem + REGSZ;             // inverse diagonal blocks W_pp⁻¹ in the tile layout (tile_el(row, col))
-    double* rhs = WvT + NB * 64;            // [DP]
-    double* lmu = rhs + DP;                 // Λ·μ [DP]
-    double* ys = lmu + DP;                  // W⁻¹·rhs (+ z) [DP]
-    double* xs = ys + DP;                   // the draw [DP]
-    double* ts = xs + DP;                   // [8]
+  static __device__ __forceinline__ RowCtx make_ctx(const RowParams& p, int item) {
+    RowCtx c;
+    c.item = item;
+    c.lrow = p.item_row[item];
+    c.obeg = p.item_beg[item];
+    c.len = p.item_len[item];
+    c.split = p.item_split[item];
+    c.slot = p.slot_base + c.lrow;
+    c.rt = &p.rt[p.item_rel ? p.item_rel[item] : 0];
+    c.alpha_f = c.split < 0 ? c.rt->alpha : 1.0;
+    return c;
+  }
 
 #ifdef BDF_DEBUG
 #define BDF_STAMP(k)                                                   \
-  if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + (k)] = clock64()
+  if (p.dbg && tid == 0) p.dbg[(size_t)c.item * 8 + (k)] = clock64()
 #else
 #define BDF_STAMP(k)
 #endif
-    BDF_STAMP(0);
-    double acc[TPW][2];
-#pragma unroll
-    for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
-    double bsum = 0.0;  // Σ v_tid · r  (used when !aug)
 
-    // ---- gather ring -----------------------------------------------------------------------------------------
-    const int nst = (len + KS - 1) / KS;
-    const int npc = (D + 1) >> 1;  // 16-byte pieces that carry latent columns; columns ≥ 2·npc are zeroed once
-    {
-      const int c0 = 2 * npc;
-      if (c0 < DP)
-        for (int e = tid; e < NBUF * (TENSOR ? 2 : 1) * KS * (DP - c0); e += NTHR) {
-          const int row = e / (DP - c0), col = c0 + e % (DP - c0);
-          const int b = row / ((TENSOR ? 2 : 1) * KS), rr = row % ((TENSOR ? 2 : 1) * KS);
-          ring[b * STG + rr * S + col] = (TENSOR && rr >= KS && col == D) ? 1.0 : 0.0;  // second partner's aug column = 1
-        }
-    }
-    // Gather by TMA: lane k < KS of warp 0 owns observation k of a stage and moves its whole partner row (npc·16 bytes)
-    // with ONE 1-D bulk copy (cp.async.bulk → UBLKCP) that signals the stage's mbarrier by byte count; the other
-    // warps issue nothing. Partner slots / values are fetched one stage ahead of their use.
-    uint64_t* fullb = reinterpret_cast<uint64_t*>(ts + 8);
+  // the stage ring's padding columns (≥ 2·ceil(D/2)) are zeroed once: the bulk copies never touch them
+  static __device__ __forceinline__ void ring_init(const RowParams& p, double* ring, uint64_t* fullb, int tid) {
+    const int D = p.D;
+    const int c0 = 2 * ((D + 1) >> 1);
+    if (c0 < DP)
+      for (int e = tid; e < NBUF * (TENSOR ? 2 : 1) * KS * (DP - c0); e += NTHR) {
+        const int row = e / (DP - c0), col = c0 + e % (DP - c0);
+        const int b = row / ((TENSOR ? 2 : 1) * KS), rr = row % ((TENSOR ? 2 : 1) * KS);
+        ring[b * STG + rr * S + col] = (TENSOR && rr >= KS && col == D) ? 1.0 : 0.0;  // second partner's aug column = 1
+      }
     if (tid == 0) {
 #pragma unroll
       for (int b = 0; b < NBUF; b++) mbar_init(fullb + b, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+  }
+
+  // ---- (1) gather + syrk of one work item ------------------------------------------------------------------------------------
+  // `ring` / `fullb`: the group's stage ring and its mbarriers (ring_init + a group sync done by the caller); `gs`: stages consumed on this
+  // ring so far (the barriers' phases run on across the items of a persistent group); lmu[DP] ← Λ·μ of the row, zs[DP] ← its standard
+  // normals. Ends with a group sync: the ring is dead (and free for the next item) when it returns.
+  template <class Sync>
+  static __device__ __forceinline__ void syrk_item(const RowParams& p, const RowCtx& c, double* ring, uint64_t* fullb, double* metab, uint32_t& gs, double* lmu,
+                                                   double* zs, double (&acc)[TPW][2], double& bsum, int tid, Sync sync, long long* tprof = nullptr) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int D = p.D;
+    const bool aug = use_aug(D);
+    const RelTab& rt = *c.rt;
+#ifdef BDF_DEBUG
+    long long tp0 = tprof ? clock64() : 0;
+#define BDF_TP(k) if (tprof) { const long long t1 = clock64(); tprof[k] += t1 - tp0; tp0 = t1; }
+#else
+#define BDF_TP(k)
+#endif
+    const int len = c.len;
+    const int64_t obeg = c.obeg, oend = obeg + len;
+#pragma unroll
+    for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
+    bsum = 0.0;  // Σ v_tid · r  (used when !aug)
+
+    const int nst = (len + KS - 1) / KS;
+    const int npc = (D + 1) >> 1;  // 16-byte pieces that carry latent columns
+    // Gather by TMA: one 1-D bulk copy (cp.async.bulk → UBLKCP) moves one whole partner row (npc·16 bytes) and signals the stage's
+    // mbarrier by byte count. The partner slot and the value of an observation are fetched one stage ahead of their use with cp.async
+    // (LDGSTS) into a small double-buffered shared-memory table — not into registers: next to the 92 accumulator registers the
+    // compiler spilled them, and the spill store made the warp wait out the HBM latency of the CSR stream on every stage.
     const uint32_t rowbytes = (uint32_t)npc * 16u;
-    int c0n = 0, c1n = 0;
-    double rvn = 0.0;
     // each warp issues its share of a stage (KS/NW rows): UBLKCP is a per-thread (uniform-datapath) instruction, so 16 copies
     // from one warp serialise for ~1000 cycles per stage; spread over the warps they go out in parallel
     constexpr int KQ = KS / NW;
     const bool gl = lane < KQ;
     const int gk = warp * KQ + lane;  // this lane's observation within a stage (valid when gl)
+    int* mcol = reinterpret_cast<int*>(metab);  // [2][2][KS]
+    double* mval = metab + 2 * KS;              // [2][KS]
     auto load_meta = [&](int s) {
       if (gl) {
         int64_t o = obeg + (int64_t)s * KS + gk;
         if (o >= oend) o = oend - 1;
-        c0n = __ldg(rt.col0 + o);
-        if (TENSOR) c1n = rt.col1 ? __ldg(rt.col1 + o) : 0;
-        rvn = __ldg(rt.val + o);
+        const int mb = (int)((gs + (uint32_t)s) & 1u);
+        cp_async4(mcol + (mb * 2) * KS + gk, rt.col0 + o);
+        if (TENSOR && rt.col1) cp_async4(mcol + (mb * 2 + 1) * KS + gk, rt.col1 + o);
+        cp_async8(mval + mb * KS + gk, rt.val + o);
       }
+      cp_async_commit();
     };
     auto issue = [&](int s) {
       if (gl) {
-        const int b = s % NBUF;
+        const int b = (int)((gs + (uint32_t)s) % NBUF);
         double* st = ring + b * STG;
         int nvalid = len - s * KS;
         if (nvalid > KS) nvalid = KS;
         const bool ok = gk < nvalid;
         if (tid == 0) mbar_arrive_expect_tx(fullb + b, (uint32_t)nvalid * rowbytes * (TENSOR ? 2u : 1u));
+        const int mb = (int)((gs + (uint32_t)s) & 1u);
+        const int c0n = mcol[(mb * 2) * KS + gk];
+        const int c1n = (TENSOR && rt.col1) ? mcol[(mb * 2 + 1) * KS + gk] : 0;
+        const double rvn = mval[mb * KS + gk];
         if (ok) {
           bulk_copy_g2s(st + gk * S, rt.P0 + (size_t)c0n * p.ld, rowbytes, fullb + b);
           if (TENSOR) bulk_copy_g2s(st + (KS + gk) * S, rt.P1 + (size_t)c1n * p.ld, rowbytes, fullb + b);
         } else if (gk < ((nvalid + 3) & ~3)) {
           // rows of the last, partly filled k-step: zero them (only the final stage of an item ever takes this path)
-          for (int c = 0; c < 2 * npc; c += 2) {
-            *reinterpret_cast<double2*>(st + gk * S + c) = make_double2(0.0, 0.0);
-            if (TENSOR) *reinterpret_cast<double2*>(st + (KS + gk) * S + c) = make_double2(0.0, 0.0);
+          for (int cc = 0; cc < 2 * npc; cc += 2) {
+            *reinterpret_cast<double2*>(st + gk * S + cc) = make_double2(0.0, 0.0);
+            if (TENSOR) *reinterpret_cast<double2*>(st + (KS + gk) * S + cc) = make_double2(0.0, 0.0);
           }
         }
         const double r = ok ? rvn - rt.mean : 0.0;
@@ -401,19 +442,26 @@ struct RowKernel {
         if (aug) st[gk * S + D] = r;
       }
     };
-    __syncthreads();  // ring zero-fill and barrier init visible before any stage is issued or consumed
 #ifdef BDF_DEBUG
     const bool dbg_nogather = p.flags & 4, dbg_nocompute = p.flags & 2;  // timing experiments only (results invalid)
 #else
     constexpr bool dbg_nogather = false, dbg_nocompute = false;
 #endif
-    if (nst > 0 && !dbg_nogather) { load_meta(0); issue(0); }
-    if (nst > 1 && !dbg_nogather) { load_meta(1); issue(1); }
-    if (nst > 2) load_meta(2);
+    static_assert(PF <= 2, "the metadata table is double-buffered: at most one stage's metadata may be in flight beside the one in use");
+    if (nst > 0) {  // the only exposed latency of an item: the metadata of its first stage(s)
+      load_meta(0);
+      if (PF > 1 && nst > 1) load_meta(1);
+      cp_async_wait<0>();
+      if (!dbg_nogather) {
+        issue(0);
+        if (PF > 1 && nst > 1) issue(1);
+      }
+      if (PF < nst) load_meta(PF);
+    }
     // ---- everything below runs under the shadow of the first gathers ---------------------------------------------------
     // Λ rides in the accumulators from the start (as Λ/α, on the row's first chunk), so that parking the tiles after the
     // syrk yields Λ* = α·(Λ/α + G) in one pass; the loads are L2 hits hidden under the first gather.
-    if (split < 0 || p.item_chunk[item] == 0) {
+    if (c.split < 0 || p.item_chunk[c.item] == 0) {
       const double ia = 1.0 / rt.alpha;
       warp_dispatch(warp, [&](auto w) {
         constexpr int W = decltype(w)::value;
@@ -435,31 +483,38 @@ struct RowKernel {
       if (p.lmu) {
         s = __ldg(p.lmu + tid);
       } else if (tid < D) {
-        const double* mu = p.mu + slot * p.mu_ld;
+        const double* mu = p.mu + c.slot * p.mu_ld;
         for (int i = 0; i < D; i++) s = fma(__ldg(p.Lambda + tid + (size_t)i * D), __ldg(mu + i), s);
       }
       lmu[tid] = s;
     }
-
     // The row's standard normals (injected, or Philox + Box–Muller in double: a few hundred instructions each) are
-    // produced here by DP threads in parallel, under the shadow of the first gather, and parked in xs[] until the
-    // substitution needs them — not serially by warp 0 at the end of the row.
+    // produced here by DP threads in parallel, under the shadow of the first gather, and parked until the
+    // substitution needs them — not serially by one warp at the end of the row.
     if (tid < DP) {
       double z = 0.0;
       if (tid < D) {
-        const int64_t grow0 = p.row_of_slot ? (int64_t)p.row_of_slot[slot] : (int64_t)lrow * p.world + p.rank;
-        z = p.Z ? __ldg(p.Z + (size_t)slot * p.ld + tid) : philox_normal(p.seed, p.sweep, philox_stream(PHILOX_ROW, (uint32_t)p.entity), grow0, tid);
+        const int64_t grow0 = p.row_of_slot ? (int64_t)p.row_of_slot[c.slot] : (int64_t)c.lrow * p.world + p.rank;
+        z = p.Z ? __ldg(p.Z + (size_t)c.slot * p.ld + tid) : philox_normal(p.seed, p.sweep, philox_stream(PHILOX_ROW, (uint32_t)p.entity), grow0, tid);
       }
-      xs[tid] = z;
+      zs[tid] = z;
     }
 
     BDF_STAMP(1);
+    BDF_TP(0)
     for (int s = 0; s < nst; s++) {
-      if (!dbg_nogather) mbar_wait(fullb + (s % NBUF), (s / NBUF) & 1);  // the rows of stage s have landed
-      __syncthreads();                                // everyone is done with stage s-1: its buffer may be refilled
-      if (s + 2 < nst && !dbg_nogather) issue(s + 2);
-      if (s + 3 < nst) load_meta(s + 3);
-      const double* buf = ring + (s % NBUF) * STG;
+      const uint32_t g = gs + (uint32_t)s;
+      if (!dbg_nogather) mbar_wait(fullb + (g % NBUF), (g / NBUF) & 1);  // the rows of stage s have landed
+      BDF_TP(1)
+      sync();                                          // everyone is done with stage s-1: its buffer may be refilled
+      BDF_TP(2)
+      if (s + PF < nst) {
+        cp_async_wait<0>();  // this thread's metadata of stage s+PF (requested a stage ago)
+        if (!dbg_nogather) issue(s + PF);
+      }
+      if (s + PF + 1 < nst) load_meta(s + PF + 1);
+      BDF_TP(3)
+      const double* buf = ring + (g % NBUF) * STG;
       const double* rs = buf + (TENSOR ? 2 : 1) * KS * S;
       int rem = len - s * KS;
       if (rem > KS) rem = KS;
@@ -472,123 +527,136 @@ struct RowKernel {
           bsum = fma(v, rs[k], bsum);
         }
       }
+      BDF_TP(4)
     }
-    __syncthreads();  // the ring is dead from here on
-
+    gs += (uint32_t)nst;
+    sync();  // the ring is dead from here on
+    BDF_TP(2)
     BDF_STAMP(2);
-    // ---- split rows: park the partial; the last item of a GROUP of consecutive chunks adds the group's partials in chunk order, and
-    //      (rows with many chunks) parks the group sum, the last group then adds the group sums in group order. Two levels keep the
-    //      serial part short — a row with 2M observations has hundreds of 46 KB partials — and the order fixed (deterministic). ------
-    if (split >= 0) {
-      const int nch = p.split_nchunks[split];
-      const int G = p.split_gsize[split];  // chunks per group
-      const int ng = (nch + G - 1) / G;
-      const int c = p.item_chunk[item], g = c / G;
-      const int gsz = (g == ng - 1) ? nch - g * G : G;
-      const int64_t gc = p.split_gcoff[split] + g;  // this group's counter / partial slot
-      __shared__ int s_last;
-      auto park = [&](double* part, double sc) {
+#undef BDF_TP
+  }
+
+  // ---- (2) split rows: park the partial; the last item of a GROUP of consecutive chunks adds the group's partials in chunk order, and
+  //      (rows with many chunks) parks the group sum, the last group then adds the group sums in group order. Two levels keep the
+  //      serial part short — a row with 2M observations has hundreds of 46 KB partials — and the order fixed (deterministic).
+  //      Returns true for the item that ends up with the complete row in its accumulators. ------------------------------------------
+  template <class Sync>
+  static __device__ __forceinline__ bool split_reduce(const RowParams& p, const RowCtx& c, double (&acc)[TPW][2], double& bsum, int tid,
+                                                      volatile int* s_last, Sync sync) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int split = c.split;
+    const int nch = p.split_nchunks[split];
+    const int G = p.split_gsize[split];  // chunks per group
+    const int ng = (nch + G - 1) / G;
+    const int ch = p.item_chunk[c.item], g = ch / G;
+    const int gsz = (g == ng - 1) ? nch - g * G : G;
+    const int64_t gc = p.split_gcoff[split] + g;  // this group's counter / partial slot
+    auto park = [&](double* part, double sc) {
 #pragma unroll
-        for (int t = 0; t < TPW; t++)
-          *reinterpret_cast<double2*>(part + ((size_t)(warp * TPW + t) * 32 + lane) * 2) = make_double2(sc * acc[t][0], sc * acc[t][1]);
-        if (tid < DP) part[NW * TPW * 64 + tid] = sc * bsum;
-        __threadfence();
-        __syncthreads();
-      };
-      auto arrive = [&](int* counter, int expect) {  // true for the last arriver (which also resets the counter)
-        if (tid == 0) {
-          const int old = atomicAdd(counter, 1);
-          s_last = (old == expect - 1);
-          if (s_last) *counter = 0;
-        }
-        __syncthreads();
-        const bool last = s_last;
-        __syncthreads();
-        if (last) __threadfence();
-        return last;
-      };
-      auto add_up = [&](const double* base, int n) {
-#pragma unroll
-        for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
-        bsum = 0.0;
-        for (int k = 0; k < n; k++) {
-          const double* pc = base + (size_t)k * PST;
-#pragma unroll
-          for (int t = 0; t < TPW; t++) {
-            const double2 v = __ldcg(reinterpret_cast<const double2*>(pc + ((size_t)(warp * TPW + t) * 32 + lane) * 2));
-            acc[t][0] += v.x;
-            acc[t][1] += v.y;
-          }
-          if (tid < DP) bsum += __ldcg(pc + NW * TPW * 64 + tid);
-        }
-      };
-      park(p.ws + (size_t)(p.split_wsoff[split] + c) * PST, rt.alpha);
-      if (!arrive(p.group_counter + gc, gsz)) return;
-      add_up(p.ws + (size_t)(p.split_wsoff[split] + (int64_t)g * G) * PST, gsz);
-      if (ng > 1) {
-        park(p.ws + (size_t)(p.gslot_base + gc) * PST, 1.0);
-        if (!arrive(p.split_counter + split, ng)) return;
-        add_up(p.ws + (size_t)(p.gslot_base + p.split_gcoff[split]) * PST, ng);
+      for (int t = 0; t < TPW; t++)
+        *reinterpret_cast<double2*>(part + ((size_t)(warp * TPW + t) * 32 + lane) * 2) = make_double2(sc * acc[t][0], sc * acc[t][1]);
+      if (tid < DP) part[NW * TPW * 64 + tid] = sc * bsum;
+      __threadfence();
+      sync();
+    };
+    auto arrive = [&](int* counter, int expect) {  // true for the last arriver (which also resets the counter)
+      if (tid == 0) {
+        const int old = atomicAdd(counter, 1);
+        const int last = (old == expect - 1);
+        *s_last = last;
+        if (last) *counter = 0;
       }
+      sync();
+      const bool last = *s_last;
+      sync();
+      if (last) __threadfence();
+      return last;
+    };
+    auto add_up = [&](const double* base, int n) {
+#pragma unroll
+      for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
+      bsum = 0.0;
+      for (int k = 0; k < n; k++) {
+        const double* pc = base + (size_t)k * PST;
+#pragma unroll
+        for (int t = 0; t < TPW; t++) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(pc + ((size_t)(warp * TPW + t) * 32 + lane) * 2));
+          acc[t][0] += v.x;
+          acc[t][1] += v.y;
+        }
+        if (tid < DP) bsum += __ldcg(pc + NW * TPW * 64 + tid);
+      }
+    };
+    park(p.ws + (size_t)(p.split_wsoff[split] + ch) * PST, c.rt->alpha);
+    if (!arrive(p.group_counter + gc, gsz)) return false;
+    add_up(p.ws + (size_t)(p.split_wsoff[split] + (int64_t)g * G) * PST, gsz);
+    if (ng > 1) {
+      park(p.ws + (size_t)(p.gslot_base + gc) * PST, 1.0);
+      if (!arrive(p.split_counter + split, ng)) return false;
+      add_up(p.ws + (size_t)(p.gslot_base + p.split_gcoff[split]) * PST, ng);
     }
+    return true;
+  }
 
-    BDF_STAMP(3);
-#ifdef BDF_DEBUG
-    if (p.flags & 1) {
-      if (tid == 0 && acc[0][0] == 1.2345) p.Uout[0] = acc[0][1];
-      if (p.dbg && tid == 0) p.dbg[(size_t)item * 8 + 4] = p.dbg[(size_t)item * 8 + 5] = p.dbg[(size_t)item * 8 + 6] = clock64();
-      return;
-    }
-#endif
-    // ---- park Λ* = α·acc in shared memory (tile t = tri(I)+J is a row-major 8×8 block of 64 doubles), identity on the padding;
-    //      the augmented row (i == D) carries Σ v·r and becomes rhs = Λμ + α·Σv·r ---------------------------------------------
-    {
-      const double alpha = alpha_f;
-      warp_dispatch(warp, [&](auto w) {
-        constexpr int W = decltype(w)::value;
-        static_for<C::ntiles(W)>([&](auto t) {
-          constexpr int T = decltype(t)::value;
-          using ti = TI<C, W, T>;
-          double2 v = make_double2(alpha * acc[T][0], alpha * acc[T][1]);
-          if constexpr (ti::I == NB - 1) {  // only the last block row / column can touch the padding
-            const int i = 8 * ti::I + (lane >> 2), j = 8 * ti::J + 2 * (lane & 3);
-            if (aug && i == D) {
-              if (j < D) rhs[j] = fma(alpha, acc[T][0], lmu[j]);
-              if (j + 1 < D) rhs[j + 1] = fma(alpha, acc[T][1], lmu[j + 1]);
-            }
-            if (i >= D || j >= D) v.x = (i == j) ? 1.0 : 0.0;
-            if (i >= D || j + 1 >= D) v.y = (i == j + 1) ? 1.0 : 0.0;
+  // ---- (3) park Λ* = α·acc in shared memory (tile t = tri(I)+J, 64 doubles in the tile layout above), identity on the padding;
+  //      the augmented row (i == D) carries Σ v·r and becomes rhs = Λμ + α·Σv·r. No synchronisation inside. ---------------------------
+  static __device__ __forceinline__ void park_tiles(const RowParams& p, const RowCtx& c, double (&acc)[TPW][2], double bsum, const double* lmu,
+                                                    double* Tl, double* rhs, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int D = p.D;
+    const bool aug = use_aug(D);
+    const double alpha = c.alpha_f;
+    warp_dispatch(warp, [&](auto w) {
+      constexpr int W = decltype(w)::value;
+      static_for<C::ntiles(W)>([&](auto t) {
+        constexpr int T = decltype(t)::value;
+        using ti = TI<C, W, T>;
+        double2 v = make_double2(alpha * acc[T][0], alpha * acc[T][1]);
+        if constexpr (ti::I == NB - 1) {  // only the last block row / column can touch the padding
+          const int i = 8 * ti::I + (lane >> 2), j = 8 * ti::J + 2 * (lane & 3);
+          if (aug && i == D) {
+            if (j < D) rhs[j] = fma(alpha, acc[T][0], lmu[j]);
+            if (j + 1 < D) rhs[j + 1] = fma(alpha, acc[T][1], lmu[j + 1]);
           }
-          *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + tile_acc_off(lane)) = v;
-        });
+          if (i >= D || j >= D) v.x = (i == j) ? 1.0 : 0.0;
+          if (i >= D || j + 1 >= D) v.y = (i == j + 1) ? 1.0 : 0.0;
+        }
+        *reinterpret_cast<double2*>(Tl + 64 * (tri(ti::I) + ti::J) + tile_acc_off(lane)) = v;
       });
-    }
-    if (!aug && tid < D) rhs[tid] = fma(alpha_f, bsum, lmu[tid]);
+    });
+    if (!aug && tid < D) rhs[tid] = fma(alpha, bsum, lmu[tid]);
     if (tid >= D && tid < DP) rhs[tid] = 0.0;
-    __syncthreads();
-    BDF_STAMP(4);
+  }
 
-    // ---- blocked UL factorisation Λ* = W·Wᵀ (W upper), block rows pb = NB-1 … 0, on the shared-memory tiles --------
-    // Per panel: (b) the panel tiles are scaled, R_pJ = W_pp⁻¹·A_pJ, by one DMMA pair each; (c) the tiles above the
-    // panel get A_IJ −= R_pIᵀ·R_pJ, again DMMA, one block row per warp at a time; warp 0 takes the next diagonal tile
-    // first and factors it while the other warps finish the trailing update (look-ahead).
-    // The serial roles (diagonal blocks, substitutions) rotate over the warps from item to item: warp w of every co-resident
-    // CTA sits on the same SM sub-partition, so a fixed "warp 0" would pile every row's dependent chain onto one scheduler.
+  // ---- (4) blocked UL factorisation Λ* = W·Wᵀ (W upper), block rows pb = NB-1 … 0, on the shared-memory tiles; y = W⁻¹·rhs rides along;
+  //      then x = W⁻ᵀ(y + z) by forward substitution and the store of the draw (into every peer replica too). xs holds z on entry. -------
+  // Per panel: (b) the panel tiles are scaled, R_pJ = W_pp⁻¹·A_pJ, by one DMMA pair each; (c) the tiles above the
+  // panel get A_IJ −= R_pIᵀ·R_pJ, again DMMA, one block row per warp at a time; one warp takes the next diagonal tile
+  // first and factors it while the other warps finish the trailing update (look-ahead). W_pp⁻¹ replaces the diagonal tile (p, p),
+  // which nothing reads once it is factored.
+  // The serial roles (diagonal blocks, substitutions) rotate over the warps from row to row (`rot`): warp w of every co-resident
+  // group sits on the same SM sub-partition, so a fixed "warp 0" would pile every row's dependent chain onto one scheduler.
+  template <class Sync>
+  static __device__ __forceinline__ void factor_and_draw(const RowParams& p, const RowCtx& c, double* Tl, double* rhs, double* ys, double* xs,
+                                                         double* ts, int rot, int tid, Sync sync) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int D = p.D;
 #if BDF_VWARP
-    const int vw = (warp - item) & (NW - 1);
+    const int vw = (warp - rot) & (NW - 1);
 #else
     const int vw = warp;
 #endif
     bool bad = false;
     const int fo = tile_frag_off(lane);  // operand-fragment offset in a tile: A[m][k] = B[k][m] = tile(k, m)
     const int ao = tile_acc_off(lane);   // accumulator-layout offset (double2)
+    auto Wv = [&](int pb) { return Tl + 64 * (tri(pb) + pb); };  // W_pp⁻¹, in the tile layout, in place of the diagonal tile
     auto factor_diag = [&](int pb) {
       // A_pp = W·Wᵀ by elimination from the last column to the first, in the DMMA accumulator layout (lane = 4·row+q
-      // holds columns 2q, 2q+1); an identity block carried along ends up as W⁻¹, stored transposed in WvT[pb].
+      // holds columns 2q, 2q+1); an identity block carried along ends up as W⁻¹.
       // The next pivot is formed from pre-update values as soon as the current scale is known, so its rsqrt overlaps
       // the rank-1 update instead of waiting for it.
       const int r = lane >> 2, q = lane & 3;
-      const double2 av = *reinterpret_cast<const double2*>(Tl + 64 * (tri(pb) + pb) + ao);
+      const double2 av = *reinterpret_cast<const double2*>(Wv(pb) + ao);
       double a0 = av.x, a1 = av.y;
       double e0 = (2 * q == r) ? 1.0 : 0.0, e1 = (2 * q + 1 == r) ? 1.0 : 0.0;
       double piv = __shfl_sync(0xffffffffu, a1, 4 * 7 + 3);  // a_77
@@ -624,7 +692,7 @@ struct RowKernel {
           e1 = ej1;
         }
       }
-      *reinterpret_cast<double2*>(WvT + pb * 64 + ao) = make_double2(e0, e1);  // W_pp⁻¹ in the tile layout: element (row, col) at tile_el(row, col)
+      *reinterpret_cast<double2*>(Wv(pb) + ao) = make_double2(e0, e1);  // element (row, col) of W_pp⁻¹ at tile_el(row, col)
     };
     // trailing update of block row I above panel pb: tiles (I, J), J = j0 … I
     auto update_row = [&](int pb, int I, int j0, int j1) {
@@ -654,29 +722,30 @@ struct RowKernel {
           if (J + u <= j1) *reinterpret_cast<double2*>(trow + 64 * (J + u)) = make_double2(c2[u][0], c2[u][1]);
       }
     };
-    constexpr int BS_SWITCH = NW == 4 ? BDF_BS_SWITCH : 1000;  // panels at or above this: backsub_step rides on warp 0 (off by default)
+    constexpr int BS_SWITCH = NW == 4 ? BDF_BS_SWITCH : 1000;  // panels at or above this: backsub_step rides on the chain warp (off by default)
     // one block of the substitution y = W⁻¹·rhs, runnable as soon as block row J is final: y_J = W_JJ⁻¹·rhs_J, then
     // rhs[c] −= Σ_k R_J[k][c]·y_J[k] for c < 8J. One warp; rides along with the trailing update.
     auto backsub_step = [&](int J, bool update) {
       const int r8 = lane & 7;
+      const double* wv = Wv(J);
       double y0 = 0.0, y1 = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
-        y0 = fma(WvT[J * 64 + tile_el(r8, k)], rhs[8 * J + k], y0);
-        y1 = fma(WvT[J * 64 + tile_el(r8, k + 1)], rhs[8 * J + k + 1], y1);
+        y0 = fma(wv[tile_el(r8, k)], rhs[8 * J + k], y0);
+        y1 = fma(wv[tile_el(r8, k + 1)], rhs[8 * J + k + 1], y1);
       }
       if (lane < 8) ys[8 * J + r8] = y0 + y1;
       __syncwarp();
       if (update) {
-        for (int c = lane; c < 8 * J; c += 32) {
-          const double* tp = Tl + 64 * (tri(J) + (c >> 3));  // R_J[k][c] = tile(J, c/8)(k, c%8)
-          double s0 = rhs[c], s1 = 0.0;
+        for (int cc = lane; cc < 8 * J; cc += 32) {
+          const double* tp = Tl + 64 * (tri(J) + (cc >> 3));  // R_J[k][c] = tile(J, c/8)(k, c%8)
+          double s0 = rhs[cc], s1 = 0.0;
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
-            s0 = fma(-tp[tile_el(k, c & 7)], ys[8 * J + k], s0);
-            s1 = fma(-tp[tile_el(k + 1, c & 7)], ys[8 * J + k + 1], s1);
+            s0 = fma(-tp[tile_el(k, cc & 7)], ys[8 * J + k], s0);
+            s1 = fma(-tp[tile_el(k + 1, cc & 7)], ys[8 * J + k + 1], s1);
           }
-          rhs[c] = s0 + s1;
+          rhs[cc] = s0 + s1;
         }
         __syncwarp();
       }
@@ -691,14 +760,14 @@ struct RowKernel {
 #define BDF_LAP0()
 #endif
     if (vw == 0) factor_diag(NB - 1);
-    __syncthreads();
+    sync();
     for (int pb = NB - 1; pb > 0; pb--) {
       BDF_LAP0();
       // (b) scale the panel tiles (pb, J < pb) in place
       {
         // A operand = W_pp⁻¹[m][k], m = lane/4, k = lane%4 (+4): stored untransposed, so its fragment is read along a tile row
         const int wo = tile_el(lane >> 2, lane & 3);
-        const double wa0 = WvT[pb * 64 + wo], wa1 = WvT[pb * 64 + (wo ^ 4)];
+        const double wa0 = Wv(pb)[wo], wa1 = Wv(pb)[wo ^ 4];
         for (int J = vw; J < pb; J += NW) {
           double* tp = Tl + 64 * (tri(pb) + J);
           const double b0 = tp[fo], b1 = tp[32 + fo];
@@ -709,7 +778,7 @@ struct RowKernel {
         }
       }
       BDF_LAP(d_b)
-      __syncthreads();
+      sync();
       BDF_LAP(d_w1)
       // (c) trailing update of block rows I < pb; rows are dealt to warps 1…NW-1 in a snake so the triangle balances
       if (NW == 1) {
@@ -729,30 +798,29 @@ struct RowKernel {
           const int I = pb - 1 - n;
           const int ph = n % (2 * NWC);
           const int wo = 1 + (ph < NWC ? ph : 2 * NWC - 1 - ph);
-          if (wo == vw) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to warp 0
+          if (wo == vw) update_row(pb, I, 0, n == 0 ? I - 1 : I);  // (pb-1, pb-1) belongs to the chain warp
         }
       }
       BDF_LAP(d_c)
-      __syncthreads();
+      sync();
       BDF_LAP(d_w2)
     }
 #ifdef BDF_DEBUG
     if (p.dbg && lane == 0 && vw < 2) {
-      long long* o = p.dbg + (size_t)gridDim.x * 8 + ((size_t)item * 2 + vw) * 4;
+      long long* o = p.dbg + (size_t)gridDim.x * 8 + ((size_t)c.item * 2 + vw) * 4;
       o[0] = d_b; o[1] = d_w1; o[2] = d_c; o[3] = d_w2;
     }
 #endif
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
     BDF_STAMP(5);
 
-    // ---- one warp: last block of y = W⁻¹·rhs, then x = W⁻ᵀ(y + z) by forward substitution over the block rows (a CTA-wide
+    // ---- one warp: last block of y = W⁻¹·rhs, then x = W⁻ᵀ(y + z) by forward substitution over the block rows (a group-wide
     //      version with one barrier per block was measured slower under load: the idle warps' issue slots go to co-resident rows)
     if (vw == 0) {
       {
       const int r8 = lane & 7;
-      const int64_t grow = (int64_t)lrow * p.world + p.rank;  // global 0-based row id
       backsub_step(0, false);
-      for (int c = lane; c < DP; c += 32) ys[c] += xs[c];  // v = y + z (z parked in xs at kernel start)
+      for (int cc = lane; cc < DP; cc += 32) ys[cc] += xs[cc];  // v = y + z (z parked in xs)
       __syncwarp();
       // forward substitution R·x = v (R = Wᵀ, lower, block rows in the tiles): column-oriented — lane owns rows
       // lane, lane+32, … of v in registers; once x_J is known every lane subtracts R[i][8J..8J+7]·x_J from its rows.
@@ -772,11 +840,12 @@ struct RowKernel {
             if ((lane >> 3) == ((8 * J) & 31) >> 3) ts[lane & 7] = mine;
           }
           __syncwarp();
+          const double* wv = Wv(J);
           double x0 = 0.0, x1 = 0.0;
 #pragma unroll
           for (int kk = 0; kk < 8; kk += 2) {
-            x0 = fma(WvT[J * 64 + tile_el(kk, r8)], ts[kk], x0);
-            x1 = fma(WvT[J * 64 + tile_el(kk + 1, r8)], ts[kk + 1], x1);
+            x0 = fma(wv[tile_el(kk, r8)], ts[kk], x0);
+            x1 = fma(wv[tile_el(kk + 1, r8)], ts[kk + 1], x1);
           }
           const double xj = x0 + x1;  // lane r8 (replicated over the 4 lane groups) holds x[8J + r8]
           if (lane < 8) xs[8 * J + r8] = xj;
@@ -804,23 +873,59 @@ struct RowKernel {
       }
       }
       __syncwarp();
-      double* out = p.Uout + (size_t)slot * p.ld;
+      double* out = p.Uout + (size_t)c.slot * p.ld;
       for (int j = lane; j < p.ld; j += 32) out[j] = j < D ? xs[j] : 0.0;
       // fused all-gather: the drawn row goes straight into every peer's replica over NVLink (no collective afterwards)
 #pragma unroll 1
       for (int r = 0; r < 8 && p.peer_out[r]; r++) {
-        double* po = p.peer_out[r] + (size_t)slot * p.ld;
+        double* po = p.peer_out[r] + (size_t)c.slot * p.ld;
         for (int j = lane; j < p.ld; j += 32) po[j] = j < D ? xs[j] : 0.0;
       }
       __syncwarp();
 #ifdef BDF_DEBUG
-      if (p.dbg && lane == 0) p.dbg[(size_t)item * 8 + 6] = clock64();
+      if (p.dbg && lane == 0) p.dbg[(size_t)c.item * 8 + 6] = clock64();
 #endif
     }
-  }
-#undef BDF_STAMP
 #undef BDF_LAP
 #undef BDF_LAP0
+  }
+
+  // ---- the kernel body: one CTA per work item --------------------------------------------------------------------------------
+  static __device__ void run(const RowParams& p, double* smem) {
+    const int tid = threadIdx.x;
+    const RowCtx c = make_ctx(p, blockIdx.x);
+    double* ring = smem;                    // [NBUF][STG]: tile (KS×S), [second tile], residuals (KS)
+    double* Tl = smem;                      // Λ* / factor tiles, alias the ring after the main loop
+    double* rhs = smem + REGSZ;             // [DP]
+    double* lmu = rhs + DP;                 // Λ·μ [DP]
+    double* ys = lmu + DP;                  // W⁻¹·rhs (+ z) [DP]
+    double* xs = ys + DP;                   // z, then the draw [DP]
+    double* ts = xs + DP;                   // [8]
+    uint64_t* fullb = reinterpret_cast<uint64_t*>(ts + 8);
+    double* metab = ts + 8 + 4;
+    __shared__ int s_last;
+    BDF_STAMP(0);
+    double acc[TPW][2];
+    double bsum;
+    uint32_t gs = 0;
+    ring_init(p, ring, fullb, tid);
+    __syncthreads();  // ring zero-fill and barrier init visible before any stage is issued or consumed
+    syrk_item(p, c, ring, fullb, metab, gs, lmu, xs, acc, bsum, tid, CtaSync{});
+    if (c.split >= 0 && !split_reduce(p, c, acc, bsum, tid, &s_last, CtaSync{})) return;
+    BDF_STAMP(3);
+#ifdef BDF_DEBUG
+    if (p.flags & 1) {
+      if (tid == 0 && acc[0][0] == 1.2345) p.Uout[0] = acc[0][1];
+      if (p.dbg && tid == 0) p.dbg[(size_t)c.item * 8 + 4] = p.dbg[(size_t)c.item * 8 + 5] = p.dbg[(size_t)c.item * 8 + 6] = clock64();
+      return;
+    }
+#endif
+    park_tiles(p, c, acc, bsum, lmu, Tl, rhs, tid);
+    __syncthreads();
+    BDF_STAMP(4);
+    factor_and_draw(p, c, Tl, rhs, ys, xs, ts, c.item, tid, CtaSync{});
+  }
+#undef BDF_STAMP
 };
 
 #ifndef BDF_MINB

@@ -288,3 +288,13 @@ def test_three_emulated_ranks_with_shard_maps(partition):
         assert rel_err(got, Uo[mode]) <= TOL
     for eng, _, _ in engs:
         eng.close()
+
+
+def test_warp_specialised_persistent_row_kernel_matches_oracle(monkeypatch):
+    """row_kernel_ws.cuh (opt-in, BDF_ROWS_WS=1): two syrk groups feeding three finalise groups per SM through shared-memory tile
+    slots. Same arithmetic as the one-CTA-per-row kernel, so the same 1e-10 against the oracle — plain rows, empty rows, duplicates,
+    a heavy row that is split into chunks (partials parked in global memory, two-level reduction), per-row mean matrix."""
+    monkeypatch.setenv("BDF_ROWS_WS", "1")
+    for D in (72, 100, 104):
+        check_half_sweeps([700, 60], 40000, D, seed=300 + D, heavy=(1, 7, 21000))
+    check_half_sweeps([300, 40], 9000, 100, seed=77, mu_matrix=True)
