@@ -34,7 +34,7 @@ static constexpr bool kWS = BDF_USE_WS && kDP > 64 && kDP <= 104;  // three 8·t
 static int launch_rows_ws(bdf_t* h, const RowParams& p0, int n_items) {
   if constexpr (kWS) {
     using W = RowKernelWS<kDP, false>;
-    static_assert(W::SMEM_BYTES <= 227 * 1024, "shared memory of the persistent kernel");
+    static_assert(!kWS || W::SMEM_BYTES <= 227 * 1024, "shared memory of the persistent kernel");
     if (!(h->smem_optin & BDF_OPTIN_ROWS_WS)) {
       CU(cudaFuncSetAttribute(row_kernel_ws<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES));
       h->smem_optin |= BDF_OPTIN_ROWS_WS;
