@@ -133,8 +133,8 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
     from identical inputs; rank 0 owns the printing, the dumps and the result."""
     rel = data.relations[0]  # predictions / RMSE are reported for the first relation, as in src/macau.jl:142-143
     lead = comm is None or comm.rank == 0
-    verbose = verbose and lead
-    if verbose:
+    say = verbose and lead  # `verbose` itself is the same on every rank: it also decides a collective (the ROC gather) below
+    if say:
         print("Model setup")
     if reset_model:
         data.reset(num_latent, lambda_beta=lambda_beta, compute_ff_size=compute_ff_size)
@@ -166,7 +166,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
     if comm is not None:
         comm.connect(eng, ents)  # peer mappings for the fused all-gather of the drawn rows
 
-    if verbose:
+    if say:
         print("Sampling")
     ntest = rel.numTest()
     dev_test = ntest > 0 and hasattr(eng, "predict_accumulate")
@@ -231,12 +231,14 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 if comm is None:
                     N, NU, NS = eng.nw_stats_uhat(e)
                 else:
-                    N = comm.nw_stats(eng, e, uhat=True)
+                    comm.nw_stats(eng, e, uhat=True)
+                    N = float(en.count)
                 if full_lambda_u:
                     nu = nu + mj.beta.shape[0]
                     Tinv = Tinv + eng.beta_gram(e) * en.lambda_beta
             elif comm is not None:
-                N = comm.nw_stats(eng, e, uhat=False)   # device statistics, all-reduced over the ranks
+                comm.nw_stats(eng, e, uhat=False)       # device statistics, all-reduced over the ranks
+                N = float(en.count)
             elif need_N or not hasattr(eng, "step_nw_stats"):
                 N, NU, NS = eng.nw_stats(e)
             else:
@@ -290,7 +292,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                             write_binary_matrix(f"{output}-{en.name}-{nstr}{tag}.binary", X32)
                         else:
                             np.savetxt(f"{output}-{en.name}-{nstr}{tag}.csv", X32, delimiter=",", fmt="%.9g")
-            if rmse_train:
+            if rmse_train and lead:
                 # train_rat = pred(rel) averaged over the posterior samples like probe_rat_all — src/macau.jl:164-178
                 train_rat = eng.predict(r_id, rel.data.ids, rel.F if rel.hasFeatures() else None)
                 if train_counter == 0:
@@ -302,7 +304,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 if rel.hasFeatures():
                     raise ValueError("Prediction of all elements is not possible when Relation has features.")  # src/sampling.jl:93-95
                 yhat_full += eng.predict_all(r_id, tuple(rel.data.dims))  # pred_all — src/macau.jl:145-146
-            if i == burnin + 1 and verbose:
+            if i == burnin + 1 and say:
                 print("--------- Burn-in complete, averaging posterior samples ----------")
             if callable(f) and lead:
                 if stale:
@@ -311,11 +313,10 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 f_output.append(f(data))
         time1 = time.time()
         if ntest and (verbose or i == burnin + psamples):
-            if comm is None or verbose or i == burnin + psamples:
-                pa, _ = test_predictions()
-                if lead:
-                    roc_avg = AUC_ROC(rel.test_label, -pa)   # src/macau.jl:198, src/ROC.jl
-        if verbose:
+            pa, _ = test_predictions()                   # every rank takes part in the gather
+            if lead:
+                roc_avg = AUC_ROC(rel.test_label, -pa)   # src/macau.jl:198, src/ROC.jl
+        if say:
             print(f"{i:3d}: ROC={roc_avg:6.4f} RMSE={rmse_avg:6.4f} | " +
                   " ".join(f"{en.name[:3]}[mu:{np.linalg.norm(en.model.mu):6.2f}]" for en in data.entities) + " | " +
                   " ".join(f"{r.name[:4]}[a={r.model.alpha:2.1f}]" for r in data.relations) + f" [{time1 - time0:1.1f}s]")
