@@ -61,6 +61,8 @@ SIGNATURES = {
     "bdf_synchronize": (C.c_int, [H]),
     "bdf_launch_count": (C.c_int64, [H]),
     "bdf_predict": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp]),
+    "bdf_ipc_export_beta": (C.c_int, [H, C.c_int, C.c_char_p]),
+    "bdf_ipc_import_beta": (C.c_int, [H, C.c_int, C.c_int, C.c_char_p]),
     "bdf_set_test": (C.c_int, [H, C.c_int, C.c_int64, c_i64p, c_dp, c_dp, C.c_double]),
     "bdf_test_reset": (C.c_int, [H, C.c_int]),
     "bdf_predict_accumulate": (C.c_int, [H, C.c_int, C.c_int, C.c_double, C.c_double, c_dp]),
@@ -82,6 +84,7 @@ SIGNATURES = {
     "bdf_beta_gram": (C.c_int, [H, C.c_int, c_dp]),
     "bdf_sample_beta": (C.c_int, [H, C.c_int, c_dp, c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "bdf_debug_ata_time": (C.c_int, [H, C.c_int, C.c_int, c_dp]),
+    "bdf_debug_ata_time_window": (C.c_int, [H, C.c_int, C.c_int, C.c_int, c_dp]),
     "bdf_sample_lambda_beta": (C.c_int, [H, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, c_dp, c_dp]),
 }
 

@@ -618,6 +618,7 @@ int bdf_destroy(bdf_t* h) {
   bdf_dense_teardown(h);
   for (auto& e : h->ents) {
     for (int r = 0; r < 8; r++) if (e.peerU[r]) cudaIpcCloseMemHandle(e.peerU[r]);
+    for (int r = 0; r < 8; r++) if (e.peer_beta[r]) cudaIpcCloseMemHandle(e.peer_beta[r]);
     cudaFree(e.slot_of_row); cudaFree(e.row_of_slot);
     cudaFree(e.inj); if (e.pinned) cudaFreeHost(e.pinned); if (e.ev_done) cudaEventDestroy(e.ev_done);
     cudaFree(e.U); cudaFree(e.mu); cudaFree(e.Lambda); cudaFree(e.mu_rows); cudaFree(e.Z); cudaFree(e.stats); cudaFree(e.hyper);

@@ -100,6 +100,7 @@ struct EntityS {
   double* FF = nullptr;         // full(FᵀF), numF × numF column-major (src/RelationData.jl:337-339), when the direct solve is in use
   bool use_ff = false;
   double* beta = nullptr;       // numF × ld
+  double* peer_beta[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // IPC-mapped beta replicas of the other ranks
   double* uhat = nullptr;       // slots × ld, (F·beta)
   double* cgbuf = nullptr;      // CG work vectors
   double* btb = nullptr;        // [numF, colsum(D), betaᵀbeta(D×D)] in the stats layout

@@ -107,6 +107,55 @@ __global__ void __launch_bounds__(256) spbin_gather_kernel(const SpItem* __restr
   }
 }
 
+// The same product for a NARROW column window (pitch ≤ 16 doubles: the rank's share of the right-hand sides in a column-split CG). With one
+// index per warp step only `ld` of the 32 lanes would load — the kernel is bound by L2 requests per second, so half the bytes would cost the
+// same time. Here the warp handles 32/LPR indices per step, LPR lanes (= one 8·LPR-byte segment) per gathered row, so a load instruction
+// still moves 256 bytes; the 32/LPR interleaved partial sums are combined by a shuffle tree at the end (deterministic; not the strictly
+// sequential order of the full-width kernel, which stays the one behind bdf_spmm and every single-GPU product).
+template <int LPR, bool VAL>
+__global__ void __launch_bounds__(256) spbin_gather_narrow_kernel(const SpItem* __restrict__ items, int n_items, const int32_t* __restrict__ idx,
+                                                                  const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                                                                  double* __restrict__ part, int ld, double lam, const double* __restrict__ P) {
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, g = lane / LPR, c = lane % LPR;
+  const bool col_ok = c < ld;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int it = warp0; it < n_items; it += nwarps) {
+    const SpItem w = items[it];
+    double acc = 0.0;
+    for (int64_t o = w.beg; o < w.end; o += 32) {
+      const int n = (int)min((int64_t)32, w.end - o);
+      const int mine = lane < n ? __ldg(idx + o + lane) : 0;
+      const double myval = (VAL && lane < n) ? __ldg(vals + o + lane) : 0.0;
+      for (int j0 = 0; j0 < n; j0 += 4 * G) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u * G + g;
+          const int ci = __shfl_sync(0xffffffffu, mine, j & 31);
+          const double a = VAL ? __shfl_sync(0xffffffffu, myval, j & 31) : 1.0;
+          const double x = (j < n && col_ok) ? __ldg(X + (size_t)ci * ld + c) : 0.0;
+          v[u] = VAL ? __dmul_rn(a, x) : x;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc = __dadd_rn(acc, v[u]);
+      }
+    }
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (g == 0 && col_ok) {
+      if (w.slot < 0) {
+        double sres = acc;
+        if (P) sres += lam * P[(size_t)w.row * ld + c];
+        Y[(size_t)w.row * ld + c] = sres;
+      } else {
+        part[(size_t)w.slot * ld + c] = acc;
+      }
+    }
+  }
+}
+
 // rows that were split: Y[row,:] = Σ_chunks partial (chunk order) (+ lam·P[row,:])
 struct SpLong {
   int32_t row, nchunks;
@@ -235,6 +284,32 @@ __global__ void to_colmajor_kernel(const double* __restrict__ rm, int64_t rows, 
     const int64_t r = e % rows;
     const int d = (int)(e / rows);
     cm[e] = rm[(size_t)r * ld + d];
+  }
+}
+
+// column window [c0, c0+nc) of a (rows × ld) matrix → packed (rows × ldw) buffer, zero padding
+__global__ void window_extract_kernel(const double* __restrict__ A, int64_t rows, int ld, int c0, int nc, int ldw, double* __restrict__ W) {
+  const int64_t n = rows * ldw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / ldw;
+    const int c = (int)(e % ldw);
+    W[e] = c < nc ? A[(size_t)r * ld + c0 + c] : 0.0;
+  }
+}
+// … and back: the solved window goes into columns [c0, c0+nc) of this rank's beta AND of every peer's replica (IPC-mapped peer memory, plain
+// NVLink stores) — the all-gather of the beta columns of solve_cg2's column split (src/parallel_matrix.jl:488-507) without a collective
+struct PeerPtrs { double* p[8]; };
+__global__ void window_scatter_kernel(const double* __restrict__ W, int64_t rows, int ld, int c0, int nc, int ldw, double* __restrict__ A, PeerPtrs peers) {
+  const int64_t n = rows * nc;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / nc;
+    const int c = (int)(e % nc);
+    const double v = W[(size_t)r * ldw + c];
+    const size_t o = (size_t)r * ld + c0 + c;
+    A[o] = v;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (peers.p[q]) peers.p[q][o] = v;
   }
 }
 
@@ -485,20 +560,40 @@ int need_features(bdf_t* h, int entity) {
   return BDF_OK;
 }
 
-int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr) {
-  if (e.f_dense) return dense_mm(h, e, transpose, X, Y, lam, P);
+// `ldx` = pitch of X / Y / P in doubles (0 = the handle's): a column window of the right-hand sides (the rank's share of a sharded CG,
+// src/parallel_matrix.jl:488-507) is a packed buffer with a smaller pitch, so a gathered row is only as wide as the window
+int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr, int ldx = 0) {
+  const int ld = ldx > 0 ? ldx : h->ld;
+  if (e.f_dense) {
+    if (ld != h->ld) FAIL(BDF_ERR_STATE, "column windows are not used with dense feature matrices");
+    return dense_mm(h, e, transpose, X, Y, lam, P);
+  }
   const int o = transpose ? 1 : 0;
   const SpItem* items = reinterpret_cast<const SpItem*>(e.sp_items[o]);
   const int ni = e.sp_nitems[o];
   int64_t g = ((int64_t)ni * 32 + 255) / 256;
   g = std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 8);
   const int32_t* idx = transpose ? e.f_rowind : e.f_colind;
-  const int nc = (h->ld + 31) / 32;
+  const int nc = (ld + 31) / 32;
   double* part = reinterpret_cast<double*>(e.sp_part);
   const double* vals = transpose ? e.f_val_csc : e.f_val_csr;
+  if (ld <= 16 && ld < h->ld) {  // a column window of a sharded solve (never the full-width products)
+#define SPN(LPR_)                                                                                                                             \
+  if (vals) spbin_gather_narrow_kernel<LPR_, true><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, vals, X, Y, part, ld, lam, P);            \
+  else spbin_gather_narrow_kernel<LPR_, false><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, nullptr, X, Y, part, ld, lam, P);
+    if (ld <= 4) { SPN(4) } else if (ld <= 8) { SPN(8) } else { SPN(16) }
+#undef SPN
+    h->launches++;
+    if (e.sp_nlong[o] > 0) {
+      spbin_reduce_kernel<<<std::min(e.sp_nlong[o], 148 * 4), 128, 0, h->stream>>>(reinterpret_cast<const SpLong*>(e.sp_long[o]), e.sp_nlong[o], part, Y, ld, lam, P);
+      h->launches++;
+    }
+    CU(cudaGetLastError());
+    return BDF_OK;
+  }
 #define SPL(NC_)                                                                                                                   \
-  if (vals) spbin_gather_kernel<NC_, true><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, vals, X, Y, part, h->ld, lam, P);         \
-  else spbin_gather_kernel<NC_, false><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, nullptr, X, Y, part, h->ld, lam, P);
+  if (vals) spbin_gather_kernel<NC_, true><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, vals, X, Y, part, ld, lam, P);         \
+  else spbin_gather_kernel<NC_, false><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, nullptr, X, Y, part, ld, lam, P);
   switch (nc) {
     case 1: SPL(1) break;
     case 2: SPL(2) break;
@@ -508,7 +603,7 @@ int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y,
 #undef SPL
   h->launches++;
   if (e.sp_nlong[o] > 0) {
-    spbin_reduce_kernel<<<std::min(e.sp_nlong[o], 148 * 4), 128, 0, h->stream>>>(reinterpret_cast<const SpLong*>(e.sp_long[o]), e.sp_nlong[o], part, Y, h->ld, lam, P);
+    spbin_reduce_kernel<<<std::min(e.sp_nlong[o], 148 * 4), 128, 0, h->stream>>>(reinterpret_cast<const SpLong*>(e.sp_long[o]), e.sp_nlong[o], part, Y, ld, lam, P);
     h->launches++;
   }
   CU(cudaGetLastError());
@@ -549,16 +644,17 @@ int build_sp_items(bdf_t* h, EntityS& e, int o, const int64_t* d_ptr, int64_t nr
 }
 
 // batched CG on (FᵀF + λI)X = B, all D columns at once; B, X device row-major (numF × ld). Returns per-column iteration counts.
-int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda, double tol, int64_t maxiter, int* iters_host) {
-  const int D = h->D, ld = h->ld;
+// Dc / ldc: the number of right-hand sides in B / X and their pitch (0 = all num_latent columns at the handle's pitch)
+int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda, double tol, int64_t maxiter, int* iters_host, int Dc = 0, int ldc = 0) {
+  const int D = Dc > 0 ? Dc : h->D, ld = ldc > 0 ? ldc : h->ld;
   const int64_t n = e.numF, m = e.N;
   const size_t vn = (size_t)n * ld, vm = (size_t)m * ld;
   const int NBLK = 296;
-  if (!e.cgbuf) {
-    int rc = dalloc(h, &e.cgbuf, 3 * vn + vm + (size_t)NBLK * 128 + 4 * 128 + 4 * 128);
+  if (!e.cgbuf) {  // sized for the full width; a column window uses a prefix of each vector
+    int rc = dalloc(h, &e.cgbuf, 3 * (size_t)n * h->ld + (size_t)m * h->ld + (size_t)NBLK * 128 + 4 * 128 + 4 * 128);
     if (rc) return rc;
   }
-  double* R = e.cgbuf; double* P = R + vn; double* Z = P + vn; double* T = Z + vn; double* part = T + vm;
+  double* R = e.cgbuf; double* P = R + (size_t)n * h->ld; double* Z = P + (size_t)n * h->ld; double* T = Z + (size_t)n * h->ld; double* part = T + (size_t)m * h->ld;
   CGState st;
   st.bknum = part + (size_t)NBLK * 128; st.bkden = st.bknum + 128; st.coef = st.bkden + 128; st.tolv = st.coef + 128;
   st.active = reinterpret_cast<int*>(st.tolv + 128); st.iters = st.active + 128; st.nactive = st.iters + 128;
@@ -575,20 +671,58 @@ int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda
   cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 2, 0, st);                // tol ← tol·‖b‖
   h->launches += 2;
   int nact = D;
-  for (int64_t iter = 1; iter <= maxiter && nact > 0; iter++) {
+  // one CG iteration (src/parallel_cg.jl:73-92); `iter` only matters as iter == 1 (p = r) versus iter > 1
+  auto body = [&](int64_t iter) -> int {
     coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(R, R, n, ld, D, part);
-    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 0, (int)iter, st);
-    cg_update_p_kernel<<<grid_for(vn), 256, 0, h->stream>>>(P, R, n, ld, D, st.coef, st.active, (int)iter);
-    spmm(h, e, false, P, T);                      // T = F·P
-    spmm(h, e, true, T, Z, lambda, P);            // Z = Fᵀ·T + λ·P
+    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 0, (int)std::min<int64_t>(iter, 2), st);
+    cg_update_p_kernel<<<grid_for(vn), 256, 0, h->stream>>>(P, R, n, ld, D, st.coef, st.active, (int)std::min<int64_t>(iter, 2));
+    int rc = spmm(h, e, false, P, T, 0.0, nullptr, ld);    // T = F·P
+    if (!rc) rc = spmm(h, e, true, T, Z, lambda, P, ld);   // Z = Fᵀ·T + λ·P
     coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(Z, P, n, ld, D, part);
-    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 1, (int)iter, st);
+    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 1, (int)std::min<int64_t>(iter, 2), st);
     cg_update_xr_kernel<<<grid_for(vn), 256, 0, h->stream>>>(X, R, P, Z, n, ld, D, st.coef, st.active);
     h->launches += 6;
-    if ((iter & 3) == 0 || iter == maxiter) {  // the all-converged test costs a sync; take it every 4th iteration
-      CU(cudaMemcpyAsync(&nact, st.nactive, 4, cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
+    return rc;
+  };
+  auto check = [&]() -> int {  // the all-converged test costs a drain of the stream
+    CU(cudaMemcpyAsync(&nact, st.nactive, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BDF_OK;
+  };
+  int64_t iter = 1;
+  int rcb;
+  if (maxiter >= 1) { if ((rcb = body(1))) return rcb; iter = 2; }
+  // The iteration is launch-bound (ten short kernels, ≈1000 iterations per draw): iterations 2… are captured ONCE into a CUDA graph of KB
+  // iterations and replayed; converged columns are masked on the device, so the few iterations that run past convergence inside a
+  // replay change nothing (neither the solution nor the per-column iteration counts).
+  constexpr int KB = 8;
+  if (maxiter - iter + 1 >= 2 * KB) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const int64_t l0 = h->launches;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rcc = BDF_OK;
+    for (int k = 0; k < KB && !rcc; k++) rcc = body(2);
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    const int64_t per_replay = h->launches - l0;
+    h->launches = l0;
+    if (rcc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (rcc) return rcc; FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce)); }
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) { cudaGraphDestroy(graph); FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce)); }
+    while (nact > 0 && maxiter - iter + 1 >= KB) {
+      ce = cudaGraphLaunch(exec, h->stream);
+      if (ce != cudaSuccess) break;
+      h->launches += per_replay;
+      iter += KB;
+      if ((rcb = check())) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); return rcb; }
     }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  for (; iter <= maxiter && nact > 0; iter++) {
+    if ((rcb = body(iter))) return rcb;
+    if ((iter & 3) == 0 || iter == maxiter) { if ((rcb = check())) return rcb; }
   }
   CU(cudaGetLastError());
   if (iters_host) {
@@ -623,6 +757,7 @@ int download_colmajor(bdf_t* h, const double* dev_rm, int64_t rows, int ncol, do
 
 // =====================================================================================================================
 static void free_feature_state(EntityS& e) {
+  for (int r = 0; r < 8; r++) if (e.peer_beta[r]) { cudaIpcCloseMemHandle(e.peer_beta[r]); e.peer_beta[r] = nullptr; }
   cudaFree(e.f_rowptr); cudaFree(e.f_colind); cudaFree(e.f_colptr); cudaFree(e.f_rowind); cudaFree(e.beta); cudaFree(e.uhat); cudaFree(e.cgbuf); cudaFree(e.btb);
   cudaFree(e.f_val_csr); cudaFree(e.f_val_csc); cudaFree(e.f_dense); cudaFree(e.FF);
   e.f_rowptr = e.f_colptr = nullptr; e.f_colind = e.f_rowind = nullptr; e.beta = e.uhat = e.cgbuf = e.btb = nullptr; e.f_val_csr = e.f_val_csc = nullptr;
@@ -1239,7 +1374,12 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   CU(cudaMemcpyAsync(e.Lambda, Lambda, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
   // temporaries from the handle's grow-only arena (no per-call cudaMalloc/cudaFree)
   const size_t nT = (size_t)e.N * ld, nR = (size_t)e.numF * ld;
-  if ((rc = bdf_ensure_arena(h, sizeof(double) * (dd + 2 * nT + 2 * nR + 64)))) return rc;
+  // column-split solve over the ranks (the reference's own strategy, solve_cg2): needs every peer's beta mapped (bdf_ipc_import_beta)
+  int npeer = 0;
+  for (int r = 0; r < 8; r++) npeer += e.peer_beta[r] != nullptr;
+  const bool sharded = h->world > 1 && npeer == h->world - 1 && !e.use_ff && !e.f_dense;
+  if (sharded && (beta_out || rhs_out)) FAIL(BDF_ERR_INVALID, "column-split beta solve: fetch beta with bdf_get_beta once the ranks have synchronised (beta_out / rhs_out must be NULL)");
+  if ((rc = bdf_ensure_arena(h, sizeof(double) * (dd + 2 * nT + 4 * nR + 64)))) return rc;
   double* Cm = reinterpret_cast<double*>(h->arena);
   double* T = Cm + ((dd + 31) / 32) * 32;
   double* rhs = T + nT;
@@ -1265,6 +1405,25 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   if (e.use_ff) {  // use_ff: solve_full(entity.FF, Ft_y, lambda_beta), src/sampling.jl:303-304
     rc = solve_full_dev(h, e, rhs, e.beta, lambda_beta);
     if (iters_out) for (int d = 0; d < D; d++) iters_out[d] = 0;
+  } else if (sharded) {
+    const int c0 = (int)((int64_t)D * h->rank / h->world), c1 = (int)((int64_t)D * (h->rank + 1) / h->world);
+    const int Dw = c1 - c0, ldw = (std::max(Dw, 1) + 3) / 4 * 4;
+    if (iters_out) for (int d = 0; d < D; d++) iters_out[d] = 0;  // the other ranks' columns: the caller adds the vectors up
+    if (Dw > 0) {
+      double* Bw = rhs + nR + nT + nR;  // behind the E1 / E2 staging areas
+      double* Xw = Bw + nR;
+      window_extract_kernel<<<grid_for((int64_t)e.numF * ldw), 256, 0, h->stream>>>(rhs, e.numF, ld, c0, Dw, ldw, Bw);
+      h->launches++;
+      std::vector<int> itw(D, 0);
+      rc = cg_solve_dev(h, e, Bw, Xw, lambda_beta, tol, e.numF, itw.data(), Dw, ldw);
+      if (!rc) {
+        PeerPtrs pp;
+        for (int r = 0; r < 8; r++) pp.p[r] = e.peer_beta[r];
+        window_scatter_kernel<<<grid_for((int64_t)e.numF * Dw), 256, 0, h->stream>>>(Xw, e.numF, ld, c0, Dw, ldw, e.beta, pp);
+        h->launches++;
+        if (iters_out) for (int d = 0; d < Dw; d++) iters_out[c0 + d] = itw[d];
+      }
+    }
   } else {
     rc = cg_solve_dev(h, e, rhs, e.beta, lambda_beta, tol, e.numF, iters_out);
   }
@@ -1275,9 +1434,38 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   return rc;
 }
 
+/* CUDA IPC handle of this rank's beta buffer / mapping of a peer's: with every peer mapped, bdf_sample_beta solves only this rank's share of
+ * the num_latent right-hand sides and stores the solved columns into all replicas (see window_scatter_kernel). */
+int bdf_ipc_export_beta(bdf_t* h, int entity, unsigned char* handle64) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!handle64) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  CU(cudaIpcGetMemHandle(&mh, h->ents[entity].beta));
+  memcpy(handle64, &mh, 64);
+  return BDF_OK;
+}
+int bdf_ipc_import_beta(bdf_t* h, int entity, int peer_rank, const unsigned char* handle64) {
+  CHECK_H(); CHECK_ENT(entity);
+  int rc = need_features(h, entity);
+  if (rc) return rc;
+  if (!handle64 || peer_rank < 0 || peer_rank >= h->world || peer_rank >= 8 || peer_rank == h->rank) FAIL(BDF_ERR_INVALID, "bad peer rank (up to 8 ranks)");
+  CU(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  void* ptr = nullptr;
+  CU(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->ents[entity].peer_beta[peer_rank] = (double*)ptr;
+  return BDF_OK;
+}
+
 /* Profiling hook: `reps` device-resident applications of (FᵀF + λI) to the current beta (D columns at once), CUDA-event
  * timed on the handle's stream; returns the mean milliseconds per application (two sparse-binary products). */
-int bdf_debug_ata_time(bdf_t* h, int entity, int reps, double* ms_per_apply) {
+int bdf_debug_ata_time_window(bdf_t* h, int entity, int reps, int ncols, double* ms_per_apply);
+int bdf_debug_ata_time(bdf_t* h, int entity, int reps, double* ms_per_apply) { return bdf_debug_ata_time_window(h, entity, reps, 0, ms_per_apply); }
+int bdf_debug_ata_time_window(bdf_t* h, int entity, int reps, int ncols, double* ms_per_apply) {
   CHECK_H(); CHECK_ENT(entity);
   int rc = need_features(h, entity);
   if (rc) return rc;
@@ -1287,9 +1475,10 @@ int bdf_debug_ata_time(bdf_t* h, int entity, int reps, double* ms_per_apply) {
   if ((rc = dalloc(h, &T, (size_t)e.N * h->ld)) || (rc = dalloc(h, &Z, (size_t)e.numF * h->ld))) { cudaFree(T); return rc; }
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
-  spmm(h, e, false, e.beta, T); spmm(h, e, true, T, Z, 1.0, e.beta);
+  const int ldw = ncols > 0 && ncols < h->D ? (ncols + 3) / 4 * 4 : 0;  // a packed column window like a rank's share of a column-split CG
+  spmm(h, e, false, e.beta, T, 0.0, nullptr, ldw); spmm(h, e, true, T, Z, 1.0, e.beta, ldw);
   cudaEventRecord(a, h->stream);
-  for (int i = 0; i < reps; i++) { spmm(h, e, false, e.beta, T); spmm(h, e, true, T, Z, 1.0, e.beta); }
+  for (int i = 0; i < reps; i++) { spmm(h, e, false, e.beta, T, 0.0, nullptr, ldw); spmm(h, e, true, T, Z, 1.0, e.beta, ldw); }
   cudaEventRecord(b, h->stream);
   cudaEventSynchronize(b);
   float ms = 0.f;

@@ -129,6 +129,14 @@ class Engine:
     def ipc_import(self, entity: int, peer_rank: int, handle: bytes):
         self._ck(self.lib.bdf_ipc_import(self.h, entity, peer_rank, handle))
 
+    def ipc_export_beta(self, entity: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.bdf_ipc_export_beta(self.h, entity, buf))
+        return buf.raw
+
+    def ipc_import_beta(self, entity: int, peer_rank: int, handle: bytes):
+        self._ck(self.lib.bdf_ipc_import_beta(self.h, entity, peer_rank, handle))
+
     def stats_dev(self, entity: int):
         p = C.c_void_p()
         n = C.c_int64()
@@ -349,9 +357,12 @@ class Engine:
         self._ck(self.lib.bdf_beta_gram(self.h, entity, _dp(B)))
         return B
 
-    def sample_beta(self, entity: int, mu, Lambda, lambda_beta: float, tol: float = float("nan"), E1=None, E2=None, want_rhs: bool = False):
+    def sample_beta(self, entity: int, mu, Lambda, lambda_beta: float, tol: float = float("nan"), E1=None, E2=None, want_rhs: bool = False,
+                    want_beta: bool = True):
+        """want_beta=False leaves beta on the device (required by the column-split solve of a multi-GPU run, whose columns land in this
+        rank's replica only once the ranks have synchronised); returns (None, iters) then."""
         n = self.numF[entity]
-        beta = np.zeros((n, self.D), order="F")
+        beta = np.zeros((n, self.D), order="F") if want_beta else None
         rhs = np.zeros((n, self.D), order="F") if want_rhs else None
         iters = np.zeros(self.D, dtype=np.int32)
         e1 = _f64(E1) if E1 is not None else None
@@ -367,9 +378,9 @@ class Engine:
                                                  C.cast(C.byref(out), _lib.c_dp), C.cast(C.byref(shape), _lib.c_dp)))
         return out.value, shape.value
 
-    def debug_ata_time(self, entity: int, reps: int = 20) -> float:
+    def debug_ata_time(self, entity: int, reps: int = 20, ncols: int = 0) -> float:
         ms = C.c_double()
-        self._ck(self.lib.bdf_debug_ata_time(self.h, entity, reps, C.cast(C.byref(ms), _lib.c_dp)))
+        self._ck(self.lib.bdf_debug_ata_time_window(self.h, entity, reps, ncols, C.cast(C.byref(ms), _lib.c_dp)))
         return ms.value
 
     def debug_phase_clocks(self, entity: int):

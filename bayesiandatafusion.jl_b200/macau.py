@@ -164,7 +164,8 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
             if en.use_FF:
                 eng.compute_ff(e)  # en.FF = full(At_mul_B(en.F, en.F)) — reset!, src/RelationData.jl:337-339
     if comm is not None:
-        comm.connect(eng, ents)  # peer mappings for the fused all-gather of the drawn rows
+        # peer mappings: drawn rows go straight into every replica; the CG of the link matrices is split by column over the ranks
+        comm.connect(eng, ents, [e for e, en in zip(ents, data.entities) if en.hasFeatures() and not en.use_FF and not isinstance(en.F, np.ndarray)])
 
     if say:
         print("Sampling")
@@ -185,6 +186,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
     f_output = []
     tol_arg = math.nan if math.isnan(tol) else float(tol)
     stale = True  # the host model lags behind the device
+    iter_seconds = []
 
     def refresh_host_model():
         for e, en in zip(ents, data.entities):
@@ -257,7 +259,9 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
         # update_beta! — src/macau.jl:138-140, src/sampling.jl:361-370
         for e, en in zip(ents, data.entities):
             if en.hasFeatures():
-                eng.sample_beta(e, en.model.mu, en.model.Lambda, en.lambda_beta, tol_arg)
+                _, iters = eng.sample_beta(e, en.model.mu, en.model.Lambda, en.lambda_beta, tol_arg, want_beta=False)  # beta stays on the device
+                if comm is not None:
+                    comm.allreduce_scalars(iters)  # orders the ranks' stores of their beta columns before anyone reads beta
                 if en.lambda_beta_sample:
                     g = float("nan")
                     if host_noise is not None:
@@ -312,6 +316,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                     stale = False
                 f_output.append(f(data))
         time1 = time.time()
+        iter_seconds.append(time1 - time0)
         if ntest and (verbose or i == burnin + psamples):
             pa, _ = test_predictions()                   # every rank takes part in the gather
             if lead:
@@ -351,4 +356,5 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
     if callable(f):
         result["f_output"] = f_output
     result["gpu_launches"] = eng.launches
+    result["seconds_per_iteration"] = float(np.mean(iter_seconds)) if iter_seconds else math.nan  # the "[%1.1fs]" of src/macau.jl:203-207
     return result

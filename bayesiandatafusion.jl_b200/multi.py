@@ -46,7 +46,7 @@ class Comm:
             deg += np.bincount(r.data.ids[:, m] - 1, minlength=en.count)
         return eng.add_entity_partitioned(en.count, balanced_partition(deg, self.world, 2.0 * self.D))
 
-    def connect(self, eng: Engine, ents):
+    def connect(self, eng: Engine, ents, beta_ents=()):
         """Bind the engine to the collectives' stream and map every peer's factor replicas (CUDA IPC) so that the row kernel's peer stores
         replace the all-gather of the drawn rows; without peer access the ranks fall back to an NCCL all-gather per half-sweep."""
         torch, dist = self.torch, self.dist
@@ -74,6 +74,18 @@ class Comm:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         self.fused = bool(flag.item())
         self.eng = eng
+        # link-matrix solves are split by right-hand-side column over the ranks (solve_cg2, src/parallel_matrix.jl:488-507) once every
+        # rank has its peers' beta buffers mapped; all ranks must agree, so the mappings are attempted only if the factor mappings worked
+        self.beta_split = False
+        if self.fused and beta_ents:
+            mine = {e: eng.ipc_export_beta(e) for e in beta_ents}
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+            for r, handles in enumerate(everyone):
+                if r != self.rank:
+                    for e in beta_ents:
+                        eng.ipc_import_beta(e, r, handles[e])
+            self.beta_split = True
 
     def nw_stats(self, eng: Engine, e: int, uhat: bool) -> None:
         """ConditionalNormalWishart's reductions over ALL rows: this rank's partial statistics on the device, then the all-reduce (which

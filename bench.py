@@ -8,18 +8,23 @@ A "step" is one Gibbs sweep = loop body of src/macau.jl:96-134 for BPMF: for eac
 statistics → (mu, Lambda) draw}. Default workload: D=100 (the configuration BASELINE.json's target is quoted on).
 
   value         device-resident sweeps/s (inputs in HBM, Philox noise, CUDA events on the engine's stream, max over ranks)
-  e2e           sweeps/s through the public host API (`macau()`-style sequence of C-ABI calls with HOST buffers: mu/Lambda
-                H2D, Normal-Wishart statistics and hyper-parameters D2H, test-set ids H2D and predictions D2H every sweep);
-                at N > 1 every rank runs that sequence on its shard (statistics all-reduced on the device in between, each
-                rank predicting 1/N of the held-out set), wall clock, max over ranks
+  e2e           sweeps/s through the public host API — the very sequence of C-ABI calls `bdf_b200.macau()` issues, with HOST buffers:
+                per entity bdf_sample_mode (mu, Lambda H2D), statistics on the device (all-reduced at N > 1), bdf_nw_sample_async
+                (hyper-priors H2D) / _fetch (mu, Lambda D2H); per sweep bdf_predict_accumulate on the held-out 1 % registered once
+                with bdf_set_test (running posterior mean, clamped RMSE on the device; 40 bytes D2H). At N > 1 every rank runs
+                that sequence on its shard and its 1/N of the held-out set. Wall clock, max over ranks
   N > 1         rows sharded over the ranks by a work-balanced map (--partition balanced, default) or the reference's
                 cyclic deal (--partition cyclic); drawn rows are stored into every peer replica by the row kernel
   roofline      the row-draw kernel: algorithmic FP64 flops per launch (SURVEY §8d formula) ÷ its CUDA-event duration,
                 against the FP64 DMMA peak measured on this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no
                 FP64 figure)
-  cpu_baseline  the restated-reference CPU oracle (oracle/, C + OpenMP, cyclic row shards like src/sampling.jl:154) timed
-                on a bounded 1/100-scale sample of the same generator, extrapolated linearly in nnz — a reported baseline
---impl reference times only that CPU arm (Julia is not installable here).
+  cpu_baseline  the restated-reference CPU oracle (oracle/, C + OpenMP, cyclic row shards like src/sampling.jl:154; its syrk is an
+                auto-vectorised rank-1 loop, not a BLAS dsyrk) timed on a bounded 1/10-scale sample of the same generator (48k users
+                x 1.78k items... both modes shrink, so the per-row degrees stay those of the full workload), extrapolated linearly
+                in nnz — a reported baseline
+  d32           (N=1 default run) the same device-resident measurement at D=32, the other half of BASELINE.json's "D=32/100":
+                sweeps/s and the row kernel against BOTH bounds (FP64 DMMA peak and HBM copy peak)
+--impl reference times only that CPU arm, with the requested --steps / --warmup (Julia is not installable here).
 """
 from __future__ import annotations
 
@@ -138,9 +143,20 @@ def cpu_sweeps(D, scale, steps, warmup, threads=None):
         sweep()
     dt = (time.perf_counter() - t0) / steps
     full = (1.0 / dt) * (nnz / NNZ)  # sweeps/s extrapolated linearly in nnz to the full workload
-    return {"value": full, "unit": "sweeps/s", "cores": threads, "kind": "port",
-            "sample": f"1/{round(1 / scale)}-scale sample of the same generator ({n1} users x {n2} items, {nnz} ratings, D={D}): "
-                      f"{dt:.3f} s/sweep measured, sweeps/s extrapolated linearly in nnz to 100M ratings"}, dt
+    return {"value": full, "unit": "sweeps/s", "cores": threads, "kind": "port", "extrapolated": True, "sample_scale": scale,
+            "sample_seconds_per_sweep": dt, "sample_sweeps_per_s": 1.0 / dt,
+            "sample": f"1/{round(1 / scale)}-scale sample of the same generator ({n1} users x {n2} items, {nnz} ratings, D={D}; per-row degrees as in "
+                      f"the full workload): {dt:.3f} s/sweep measured on {threads} threads over {steps} timed sweep(s) after {warmup} warm-up, sweeps/s "
+                      f"extrapolated linearly in nnz to 100M ratings; restated reference (C + OpenMP, rank-1 auto-vectorised syrk, explicit LU inverse "
+                      f"like Julia's inv — no BLAS)"}, dt
+
+
+def make_config(n1, n2, nnz_tr, ntest, D, world, partition):
+    """The workload description both arms print (the driver compares it)."""
+    return {"workload": f"BPMF synthetic Netflix-scale {n1}x{n2}, {nnz_tr} training ratings (+{ntest} held out), D={D}",
+            "alpha": ALPHA, "skew": 2.5, "seed": SEED, "noise": "device Philox",
+            "l2": "inputs (ratings 1.2 GB/mode + factors) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"rows sharded over {world} GPU(s) ({partition} shard map); drawn rows stored into every peer replica by the row kernel (NVLink P2P, fused all-gather) + NCCL all-reduce of NW stats per half-sweep" if world > 1 else "single GPU"}
 
 
 def run_reference(args):
@@ -148,12 +164,14 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    cb, dt = cpu_sweeps(args.latent, args.cpu_scale, steps, min(warmup, 1))
+    cb, dt = cpu_sweeps(args.latent, args.cpu_scale, steps, warmup)
     line = {
         "impl": "reference", "metric": f"Gibbs sweeps/sec (Netflix-100M, D={args.latent})", "value": cb["value"], "unit": "sweeps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1), "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BPMF synthetic Netflix-scale {N_USERS}x{N_ITEMS}, {NNZ} ratings, D={args.latent}"},
+        "config": make_config(N_USERS, N_ITEMS, NNZ - min(1_000_000, NNZ // 100), min(1_000_000, NNZ // 100), args.latent, args.gpus, args.partition),
+        "step": f"one Gibbs sweep of a bounded 1/{round(1 / args.cpu_scale)}-scale sample of the workload (ms_per_step is that sample sweep as timed; value = sweeps/s "
+                f"extrapolated linearly in nnz to the full workload, i.e. sample sweeps/s × {args.cpu_scale:g})",
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated-reference CPU path (oracle/, C+OpenMP); Julia is not installable in this image",
     }
@@ -268,98 +286,153 @@ def run_ours(args):
         "share_of_step": (t_k[e1] + t_k[e2]) / (ms / args.steps),
     }
 
-    # ---- end to end through the host-facing C ABI ("e2e") -----------------------------------------------------------
-    e2e = None
-    if world == 1:
-        hyper = {e: (np.zeros(D), 5.0 * np.eye(D)) for e in (e1, e2)}
-        mu0, WI = np.zeros(D), np.eye(D)
-        pin_ids = torch.from_numpy(np.asfortranarray(test_ids).T.copy()).pin_memory()  # (2, ntest) C-order = ntest×2 column-major
-        pin_ids_np = pin_ids.numpy().T
-        acc = np.zeros(ntest)
+    # ---- end to end through the host-facing C ABI ("e2e"): the call sequence of bdf_b200.macau() ---------------------------------
+    hyper = {e: (np.zeros(D), 5.0 * np.eye(D)) for e in (e1, e2)}
+    mu0, WI = np.zeros(D), np.eye(D)
+    my_ids = np.asfortranarray(test_ids[rank::world])
+    my_vals = np.ascontiguousarray(test_vals[rank::world])
+    eng.set_test(rel, my_ids, my_vals, None, 0.0)   # the held-out 1 % goes to the device ONCE (this rank's share)
+    eng.set_async(True)
+    clamp = (float(vals.min()), float(vals.max()))
+    sums = [0.0] * 5
 
-        def host_sweep():
-            for e in (e1, e2):
-                mu, Lam = hyper[e]
-                eng.sample_mode(e, mu, Lam, None)                 # H2D mu, Lambda; row draws on the device
-                N, NU, NS = eng.nw_stats(e)                       # D2H 1+D+D² doubles
-                hyper[e] = eng.nw_sample(e, mu0, 2.0, WI, float(D))  # H2D hyper-priors, D2H (mu, Lambda)
-            eng.advance_sweep()
-            return eng.predict(rel, pin_ids_np)                   # H2D test ids, D2H predictions
+    def host_sweep():
+        for e in (e1, e2):
+            mu, Lam = hyper[e]
+            eng.sample_mode(e, mu, Lam, None)                 # H2D mu, Lambda; this rank's row draws (+ peer stores)
+            eng.step_nw_stats(e)                              # statistics stay on the device
+            if dist is not None:
+                dist.all_reduce(ds.views[e][2])               # (1+D+D²) doubles; also orders the peer stores
+            eng.nw_sample_async(e, mu0, 2.0, WI, float(D))    # H2D hyper-priors; the draw runs beside the next entity's row kernel
+        for e in (e1, e2):
+            hyper[e] = eng.nw_sample_fetch(e)                 # D2H (mu, Lambda); the same draw on every rank
+        eng.advance_sweep()
+        return eng.predict_accumulate(rel, True, clamp)       # running posterior mean + clamped SSE on the device; 40 bytes D2H
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            host_sweep()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            acc += host_sweep()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.steps
-        rmse = float(np.sqrt(np.mean((acc / args.steps - test_vals) ** 2)))
-        h2d = 2 * (D + D * D) * 8 + 2 * (D + D * D) * 8 + ntest * 2 * 8
-        d2h = 2 * (1 + D + D * D) * 8 + 2 * (D + D * D) * 8 + ntest * 8
-        e2e = {"value": 1.0 / dt, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "test_rmse_running_mean": rmse,
-               "path": "bdf_sample_mode + bdf_nw_stats + bdf_nw_sample per entity, bdf_predict on the held-out 1% per sweep (host buffers)"}
-    else:
-        # N > 1: the same host-buffer sequence on every rank (its own rows; hyper-parameters cross the ABI as host arrays every
-        # half-sweep), the statistics all-reduced on the device in between, and each rank predicting its 1/N of the held-out set
-        hyper = {e: (np.zeros(D), 5.0 * np.eye(D)) for e in (e1, e2)}
-        mu0, WI = np.zeros(D), np.eye(D)
-        my_ids = np.asfortranarray(test_ids[rank::world])
-        pin_ids = torch.from_numpy(my_ids.T.copy()).pin_memory()
-        pin_ids_np = pin_ids.numpy().T
-        my_vals = test_vals[rank::world]
-        acc = np.zeros(my_ids.shape[0])
-
-        def host_sweep():
-            for e in (e1, e2):
-                mu, Lam = hyper[e]
-                eng.sample_mode(e, mu, Lam, None)                 # H2D mu, Lambda; this rank's row draws (+ peer stores)
-                eng.step_nw_stats(e)
-                dist.all_reduce(ds.views[e][2])                   # (1+D+D²) doubles; also orders the peer stores
-                hyper[e] = eng.nw_sample(e, mu0, 2.0, WI, float(D))  # H2D hyper-priors, D2H (mu, Lambda); same draw on every rank
-            eng.advance_sweep()
-            return eng.predict(rel, pin_ids_np)                   # H2D test ids, D2H predictions
-
-        for _ in range(max(1, min(args.warmup, 2))):
-            host_sweep()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            acc += host_sweep()
-        barrier()
-        dt = (time.perf_counter() - t0) / args.steps
-        tt = torch.tensor([dt, float(np.sum((acc / args.steps - my_vals) ** 2)), float(len(my_vals))], device="cuda", dtype=torch.float64)
-        tmax = tt.clone()
+    eng.test_reset(rel)
+    for _ in range(max(1, min(args.warmup, 2))):
+        host_sweep()
+    eng.test_reset(rel)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sums = host_sweep()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.steps
+    tt = torch.tensor([dt, sums[0], sums[3]], device="cuda", dtype=torch.float64)
+    tmax = tt.clone()
+    if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tt)
-        nt = my_ids.shape[0]
-        h2d = 2 * (D + D * D) * 8 + 2 * (D + D * D) * 8 + nt * 2 * 8
-        d2h = 2 * (D + D * D) * 8 + nt * 8
-        e2e = {"value": 1.0 / float(tmax[0].item()), "unit": "sweeps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "test_rmse_running_mean": float(np.sqrt(tt[1].item() / tt[2].item())),
-               "path": "per rank: bdf_sample_mode (host mu/Lambda) + bdf_step_nw_stats + NCCL all-reduce + bdf_nw_sample (host out) per entity, bdf_predict on "
-                       "its share of the held-out 1% per sweep; wall clock, max over ranks; bytes summed over ranks"}
+    h2d = 2 * (D + D * D) * 8 + 2 * (D + D * D) * 8
+    d2h = 2 * (D + D * D) * 8 + 5 * 8
+    e2e = {"value": 1.0 / float(tmax[0].item()), "unit": "sweeps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+           "test_rmse_posterior_mean": float(np.sqrt(tt[1].item() / tt[2].item())), "posterior_samples_averaged": int(sums[4]),
+           "path": "per rank: bdf_sample_mode (host mu/Lambda) + bdf_step_nw_stats" + (" + NCCL all-reduce" if world > 1 else "") +
+                   " + bdf_nw_sample_async/_fetch (host hyper-priors in, host mu/Lambda out) per entity; bdf_predict_accumulate per sweep on the held-out 1% "
+                   "registered once with bdf_set_test; wall clock, max over ranks; bytes summed over ranks"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = cpu_sweeps(D, args.cpu_scale, 1, 0)
+        cpu, _ = cpu_sweeps(D, args.cpu_scale, 2, 1)
+
+    # ---- the other half of the metric ("D=32/100"): the same workload at D=32, device-resident, both rooflines ----------------------
+    d32 = None
+    if world == 1 and D == 100 and args.scale == 1.0 and not args.no_d32:
+        eng.close()
+        eng = None
+        d32 = measure_d32(torch, local, tr_ids, tr_vals, n1, n2, nnz_tr, mean, args)
 
     if rank == 0:
         line = {
             "metric": f"Gibbs sweeps/sec (Netflix-100M, D={D})", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BPMF synthetic Netflix-scale {n1}x{n2}, {nnz_tr} training ratings (+{ntest} held out), D={D}",
-                       "alpha": ALPHA, "skew": 2.5, "seed": SEED, "noise": "device Philox",
-                       "l2": "inputs (ratings 1.2 GB/mode + factors) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"rows sharded over {world} GPU(s) ({args.partition} shard map); drawn rows stored into every peer replica by the row kernel (NVLink P2P, fused all-gather) + NCCL all-reduce of NW stats per half-sweep" if world > 1 else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "config": make_config(n1, n2, nnz_tr, ntest, D, world, args.partition),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "d32": d32, "gpu_launches": int(launches), "clocks": clk,
             "fp64_frac_of_peak_whole_sweep": (2 * alg_flops(nnz_tr, 0, D) + alg_flops(0, n1 + n2, D)) / (ms / args.steps / 1e3) / 1e12 / peak / world,
         }
         print(json.dumps(line))
-    eng.close()
+    if eng is not None:
+        eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measure_d32(torch, local, tr_ids, tr_vals, n1, n2, nnz_tr, mean, args):
+    """Device-resident sweeps/s of the same table at D=32 (warp-per-row kernel) with the row kernel against both of its bounds."""
+    import bdf_b200
+
+    D = 32
+    eng = bdf_b200.Engine(D, device=local)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_seed(SEED)
+    e1, e2 = eng.add_entity(n1), eng.add_entity(n2)
+    rel = eng.add_relation([e1, e2], tr_ids, tr_vals)
+    eng.set_relation_params(rel, ALPHA, mean)
+    eng.sweep(max(3, args.warmup))
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    eng.sweep(args.steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    kt = {e1: [], e2: []}
+    for _ in range(4):
+        for e in (e1, e2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.step_sample(e)
+            b.record()
+            b.synchronize()
+            kt[e].append(a.elapsed_time(b))
+    tk = (float(np.mean(kt[e1][1:])) + float(np.mean(kt[e2][1:]))) / 1e3
+    fl = alg_flops(nnz_tr, n1, D) + alg_flops(nnz_tr, n2, D)
+    by = 2 * nnz_tr * (8 * D + 12) + (n1 + n2) * (8 * D + 8)   # SURVEY §8d: partner rows + CSR stream + row_ptr + factor write
+    peak, _ = fp64_peak()
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm = 6555.5
+    eng.close()
+    return {"value": 1e3 / ms, "unit": "sweeps/s", "ms_per_step": ms, "steps": args.steps,
+            "roofline": {"kernel": "row_kernel<32,1> (warp per row)", "ms_per_launch": {"users": float(np.mean(kt[e1][1:])), "items": float(np.mean(kt[e2][1:]))},
+                         "tensor": {"achieved": fl / tk / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / tk / 1e12 / peak},
+                         "hbm": {"achieved": by / tk / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / tk / 1e9 / hbm,
+                                 "note": "algorithmic bytes (no cache reuse assumed); the 4.6 MB item matrix is L2-resident, so the users launch moves far fewer DRAM bytes"}}}
+
+
+def run_c1(args):
+    """BASELINE.json configs[0] (C1): BPMF on the reference's MovieLens-1M file (tests/golden/movielens_1m.npz), the recipe of docs/index.md:34-60
+    without side information, num_latent=10 — through the public `bdf_b200.macau()` call on the GPU and, for the CPU arm, through the SAME
+    host loop driven by the restated reference (tests/oracle_engine.py over oracle/), in FULL (no sampling, no extrapolation)."""
+    import bdf_b200
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import movielens
+
+    burnin, psamples = max(1, args.warmup), max(1, args.steps)
+    kw = dict(num_latent=10, burnin=burnin, psamples=psamples, verbose=False, clamp=[1.0, 5.0])
+    line = {"metric": "Gibbs sweeps/sec (MovieLens-1M BPMF, D=10)", "unit": "sweeps/s", "n_gpus": 1, "steps": psamples, "warmup": burnin, "higher_is_better": True,
+            "dtype": "f64", "data": "reference file data/movielens_1m.mat (committed fixture)", "vs_baseline": None,
+            "config": {"workload": "BPMF on MovieLens-1M 6040x3952, 500209 training ratings (+500000 held out by a seeded permutation), D=10, alpha=1.5, clamp [1,5]"}}
+    if args.impl == "ours":
+        res = bdf_b200.macau(movielens.relation_data(False), seed=SEED, **kw)
+        line.update({"value": 1.0 / res["seconds_per_iteration"], "ms_per_step": 1e3 * res["seconds_per_iteration"], "gpu_launches": res["gpu_launches"],
+                     "RMSE": res["RMSE"], "ROC": res["ROC"], "note": "wall clock per iteration of macau(): both half-sweeps, both Normal-Wishart draws, test-set metrics"})
+    if args.impl == "reference" or not args.no_cpu:
+        from oracle import oracle as orc
+        from oracle_engine import OracleEngine
+
+        ref = bdf_b200.macau(movielens.relation_data(False), engine=OracleEngine(10), host_noise=np.random.default_rng(11), **kw)
+        cb = {"value": 1.0 / ref["seconds_per_iteration"], "unit": "sweeps/s", "cores": min(orc.max_threads(), 16), "kind": "port", "sample": "the whole C1 run (no sampling)",
+              "RMSE": ref["RMSE"], "ROC": ref["ROC"]}
+        if args.impl == "reference":
+            line.update({"impl": "reference", "value": cb["value"], "ms_per_step": 1e3 * ref["seconds_per_iteration"],
+                         "e2e": {"value": cb["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
 
 
 def main():
@@ -370,10 +443,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--latent", type=int, default=100)
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 480k-user / 100M-rating workload (1.0 = the judged config)")
-    ap.add_argument("--cpu-scale", type=float, default=0.01, help="bounded sample for the CPU arm")
+    ap.add_argument("--cpu-scale", type=float, default=0.1, help="bounded sample for the CPU arm (SURVEY §8d: 1/10 scale)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-d32", action="store_true", help="skip the extra D=32 measurement of the default N=1 run")
     ap.add_argument("--partition", default="balanced", choices=["balanced", "cyclic"], help="row → GPU shard map for N > 1")
+    ap.add_argument("--config", default="c2", choices=["c2", "c1"], help="c2 = the judged Netflix-scale workload; c1 = MovieLens-1M through macau()")
     args = ap.parse_args()
+    if args.config == "c1":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_c1(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

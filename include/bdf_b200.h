@@ -243,8 +243,18 @@ int bdf_beta_gram(bdf_t* h, int entity, double* BtB);
  * beta stays on the device; beta_out / rhs_out (n×D, column-major) and iters_out (D) may be NULL. */
 int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda, double lambda_beta, double tol, const double* E1,
                     const double* E2, double* beta_out, double* rhs_out, int* iters_out);
+/* Column-split beta solve over the ranks — solve_cg2 hands the num_latent right-hand sides to its workers one column at a time
+ * (src/parallel_matrix.jl:488-507). Exchange the CUDA IPC handle of every rank's beta buffer once (after bdf_set_features_*); with all
+ * world-1 peers mapped, bdf_sample_beta (CG path, sparse F) solves only columns [D·rank/world, D·(rank+1)/world) on this rank — the gathers
+ * of the two products are as narrow as the window — and stores the solved columns into its own and every peer's replica over NVLink. The
+ * caller must synchronise the ranks (any collective on the handles' streams, e.g. the all-reduce of iters_out) before beta is used, and
+ * pass beta_out = rhs_out = NULL. Without the mappings every rank solves all columns (replicated). */
+int bdf_ipc_export_beta(bdf_t* h, int entity, unsigned char* handle64);
+int bdf_ipc_import_beta(bdf_t* h, int entity, int peer_rank, const unsigned char* handle64);
 /* Profiling hook: mean milliseconds of one device-resident AtA_mul_B! (src/parallel_cg.jl:7-14) on all num_latent columns. */
 int bdf_debug_ata_time(bdf_t* h, int entity, int reps, double* ms_per_apply);
+/* The same on a packed window of `ncols` < num_latent columns (the operand shape of one rank of a column-split CG). */
+int bdf_debug_ata_time_window(bdf_t* h, int entity, int reps, int ncols, double* ms_per_apply);
 /* sample_lambda_beta(beta, Lambda_u, nu, mu) — src/sampling.jl:136-142. gamma_variate = the injected Gamma(shape, 1) draw behind
  * rand(Gamma(b, c)), NaN → Philox. shape_out may be NULL. */
 int bdf_sample_lambda_beta(bdf_t* h, int entity, const double* Lambda, double nu, double mu, double gamma_variate, double* lambda_beta_out,

@@ -143,7 +143,7 @@ class OracleEngine:
     def beta_gram(self, e):
         return self.beta[e].T @ self.beta[e]
 
-    def sample_beta(self, e, mu, Lambda, lambda_beta, tol=float("nan"), E1=None, E2=None, want_rhs=False):
+    def sample_beta(self, e, mu, Lambda, lambda_beta, tol=float("nan"), E1=None, E2=None, want_rhs=False, want_beta=True):
         self.calls.append(("beta", e, e in self.FF))
         F = self.F[e]
         N, numF = F.shape
