@@ -30,6 +30,9 @@
 #ifndef BDF_K4_UNROLL
 #define BDF_K4_UNROLL 1
 #endif
+#ifndef BDF_K4_UNROLL4
+#define BDF_K4_UNROLL4 2  // 4-warp CTAs (D > 32): two k-steps per loop trip — the fragment loads of the second overlap the DMMAs of the first (+1 % on C2)
+#endif
 #ifndef BDF_FD_UNROLL
 #define BDF_FD_UNROLL 8
 #endif
@@ -290,7 +293,7 @@ struct RowKernel {
     constexpr int NTW = C::ntiles(W);
     if constexpr (NTW > 0) {
       const double* base = buf + (lane & 3) * S + (lane >> 2);
-      constexpr int kUnrollK4 = BDF_K4_UNROLL;
+      constexpr int kUnrollK4 = NW == 4 ? BDF_K4_UNROLL4 : BDF_K4_UNROLL;
 #pragma unroll kUnrollK4
       for (int k4 = 0; k4 < nk4; k4++) {
         double f[NF];
