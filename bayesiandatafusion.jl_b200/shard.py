@@ -106,11 +106,14 @@ def device_view(ptr: int, shape, device):
     return torch.as_tensor(_DevArray(ptr, shape), device=device)
 
 
-def balanced_partition(degrees, world: int, row_cost: float = 0.0):
+def balanced_partition(degrees, world: int, row_cost: float = 0.0, exact_top: int = 200_000):
     """Work-balanced shard map: rank_of_row for `world` ranks by greedy longest-processing-time assignment of the rows, heaviest
     first, each to the currently lightest rank. The weight of a row is its number of observations plus `row_cost` (the fixed
     factorisation + draw cost of a row in observation-equivalents). With a heavy-tailed degree distribution the cyclic deal
-    `i:Nprocs:N` (src/sampling.jl:154) always hands the heaviest row of every group of `world` to the same rank."""
+    `i:Nprocs:N` (src/sampling.jl:154) always hands the heaviest row of every group of `world` to the same rank.
+    Entities with more than `exact_top` rows (C5: 10M users) get the exact greedy assignment for their `exact_top` heaviest rows and a
+    vectorised snake deal (0 … W-1, W-1 … 0) of the remaining, light rows in descending weight order — each snake round trip adds
+    the same load to every rank up to the weight difference inside it."""
     import heapq
 
     deg = np.asarray(degrees, dtype=np.float64) + float(row_cost)
@@ -119,11 +122,18 @@ def balanced_partition(degrees, world: int, row_cost: float = 0.0):
     if world == 1:
         return rank
     order = np.argsort(-deg, kind="stable")
+    head = order[:exact_top] if n > exact_top else order
     heap = [(0.0, r) for r in range(world)]
-    for i in order.tolist():
+    for i in head.tolist():
         load, r = heap[0]
         rank[i] = r
         heapq.heapreplace(heap, (load + deg[i], r))
+    if n > exact_top:
+        tail = order[exact_top:]
+        by_load = np.asarray([r for _, r in sorted(heap)], dtype=np.int32)   # lightest rank first
+        pos = np.arange(tail.shape[0]) % (2 * world)
+        snake = np.where(pos < world, pos, 2 * world - 1 - pos)
+        rank[tail] = by_load[snake]
     return rank
 
 
