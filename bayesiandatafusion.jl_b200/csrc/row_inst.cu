@@ -53,12 +53,17 @@ static int launch_rows_ws(bdf_t* h, const RowParams& p0, int n_items) {
   return BDF_OK;
 }
 
+// warp-per-row kernel on 3-mode tensors: both partners are staged, so a 16-observation stage ring costs 28 KB per one-warp CTA and only 7
+// of them fit an SM (ncu: 11 % of the warp slots active); 8-observation stages double the rows in flight
+#ifndef BDF_TKS1
+#define BDF_TKS1 8
+#endif
 template <bool TENSOR>
 static int launch_rows_t(bdf_t* h, const RowParams& p, int n_items) {
   if constexpr (kWS && !TENSOR) {
     if (h->use_ws) return launch_rows_ws(h, p, n_items);
   }
-  using K = RowKernel<kDP, kNW, TENSOR>;
+  using K = RowKernel<kDP, kNW, TENSOR, (kNW == 1 && TENSOR) ? BDF_TKS1 : 0, 0>;
   const uint32_t bit = TENSOR ? BDF_OPTIN_ROWS_TENSOR : BDF_OPTIN_ROWS;
   if (!(h->smem_optin & bit)) {
     CU(cudaFuncSetAttribute(row_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
