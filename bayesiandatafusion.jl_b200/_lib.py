@@ -46,6 +46,7 @@ SIGNATURES = {
     "bdf_sample_alpha": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_dp]),
     "bdf_sample_mode": (C.c_int, [H, C.c_int, c_dp, C.c_int64, c_dp, c_dp]),
     "bdf_nw_stats": (C.c_int, [H, C.c_int, c_dp, c_dp, c_dp]),
+    "bdf_set_nw_stats": (C.c_int, [H, C.c_int, C.c_double, c_dp, c_dp]),
     "bdf_stats_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), c_i64p]),
     "bdf_nw_sample": (C.c_int, [H, C.c_int, c_dp, C.c_double, c_dp, C.c_double, c_dp, c_dp, c_dp, c_dp]),
     "bdf_step_sample": (C.c_int, [H, C.c_int]),

@@ -939,6 +939,20 @@ int bdf_nw_stats(bdf_t* h, int entity, double* N, double* NU, double* NS) {
   return BDF_OK;
 }
 
+int bdf_set_nw_stats(bdf_t* h, int entity, double N, const double* NU, const double* NS) {
+  CHECK_H(); CHECK_ENT(entity);
+  if (!NU || !NS) FAIL(BDF_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  const int D = h->D;
+  std::vector<double> buf((size_t)1 + D + (size_t)D * D);
+  buf[0] = N;
+  memcpy(buf.data() + 1, NU, sizeof(double) * D);
+  memcpy(buf.data() + 1 + D, NS, sizeof(double) * D * D);
+  CU(cudaMemcpyAsync(h->ents[entity].stats, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BDF_OK;
+}
+
 int bdf_nw_sample(bdf_t* h, int entity, const double* mu0, double b0, const double* Tinv, double nu, const double* bartlettA,
                   const double* z, double* mu_out, double* Lambda_out) {
   CHECK_H(); CHECK_ENT(entity);

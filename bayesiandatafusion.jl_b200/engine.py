@@ -160,6 +160,10 @@ class Engine:
         self._ck(self.lib.bdf_nw_stats(self.h, entity, C.cast(C.byref(N), _lib.c_dp), _dp(NU), _dp(NS)))
         return N.value, NU, NS
 
+    def set_nw_stats(self, entity: int, N: float, NU, NS):
+        """Overwrite the statistics the next nw_sample of `entity` reads (host-side reduction over ranks)."""
+        self._ck(self.lib.bdf_set_nw_stats(self.h, entity, float(N), _dp(_f64(NU)), _dp(np.asfortranarray(NS, dtype=np.float64))))
+
     def nw_sample(self, entity: int, mu0, b0, Tinv, nu, bartlettA=None, z=None):
         D = self.D
         mu = np.zeros(D)

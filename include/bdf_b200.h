@@ -86,6 +86,10 @@ int bdf_sample_mode(bdf_t* h, int entity, const double* mu, int64_t mu_ld, const
 /* ConditionalNormalWishart's reductions — src/sampling.jl:117-119: N = size(U,2), NU = sum(U,2), NS = U*U'
  * over the rows owned by this rank (all-reduce across ranks is the caller's, see bdf_stats_dev). */
 int bdf_nw_stats(bdf_t* h, int entity, double* N, double* NU, double* NS);
+/* The inverse: overwrite the statistics the next bdf_nw_sample* of `entity` reads. For callers that sum the ranks' statistics on the host
+ * (Julia's master/worker remotecalls instead of an NCCL all-reduce on bdf_stats_dev): every rank calls bdf_nw_stats, the master adds the
+ * (N, NU, NS) triples up, every rank calls bdf_set_nw_stats with the sums and then draws — identically, from the shared Philox key. */
+int bdf_set_nw_stats(bdf_t* h, int entity, double N, const double* NU, const double* NS);
 /* Device buffer holding [N, NU(D), NS(D×D col-major)] of the last bdf_nw_stats / bdf_step_nw_stats. */
 int bdf_stats_dev(bdf_t* h, int entity, void** dev_ptr, int64_t* count);
 

@@ -230,4 +230,51 @@ function stats_dev(h::Handle, entity)
   return p[], n[]
 end
 
+
+## ---- test set and posterior accumulators on the device (src/macau.jl:142-200) ----------------------------------------------------
+## setTest! / assignToTest!: ids ntest x K Int64 (1-based), values; test_F = rel.test_F (Matrix) when the relation has features
+function set_test(h::Handle, rel, ids::Matrix{Int64}, values::Vector{Float64}, class_cut; test_F = C_NULL)
+  check(h, ccall((:bdf_set_test, LIB), Cint, (Ptr{Void}, Cint, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble),
+                 h.ptr, rel, size(ids, 1), ids, values, test_F, class_cut))
+end
+test_reset(h::Handle, rel) = check(h, ccall((:bdf_test_reset, LIB), Cint, (Ptr{Void}, Cint), h.ptr, rel))
+## one iteration of the test-set bookkeeping; returns (rmse_avg, rmse, err_avg, counter_prob). clamp = Float64[] -> not clamped
+function predict_accumulate(h::Handle, rel, posterior::Bool, clamp::Vector{Float64})
+  out = zeros(5)
+  lo, hi = isempty(clamp) ? (NaN, NaN) : (clamp[1], clamp[2])
+  check(h, ccall((:bdf_predict_accumulate, LIB), Cint, (Ptr{Void}, Cint, Cint, Cdouble, Cdouble, Ptr{Cdouble}), h.ptr, rel, posterior ? 1 : 0, lo, hi, out))
+  return sqrt(out[1] / out[4]), sqrt(out[2] / out[4]), out[3] / out[4], round(Int, out[5])
+end
+## probe_rat_all (unclamped), probe_stdev (sum of squares), probe_rat
+function get_test_predictions(h::Handle, rel, ntest::Int)
+  avg = zeros(ntest); sq = zeros(ntest); last = zeros(ntest)
+  check(h, ccall((:bdf_get_test_predictions, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, rel, avg, sq, last))
+  return avg, sq, last
+end
+
+## host-side reduction of the Normal-Wishart statistics over ranks (master/worker remotecalls): nw_stats on every rank, add, set_nw_stats
+set_nw_stats(h::Handle, entity, N, NU::Vector{Float64}, NS::Matrix{Float64}) =
+  check(h, ccall((:bdf_set_nw_stats, LIB), Cint, (Ptr{Void}, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, N, NU, NS))
+
+## ---- deferred completion: half-sweeps return once enqueued; the Normal-Wishart draw of one entity overlaps the next entity's rows -----
+set_async(h::Handle, on::Bool = true) = check(h, ccall((:bdf_set_async, LIB), Cint, (Ptr{Void}, Cint), h.ptr, on ? 1 : 0))
+function nw_sample_async(h::Handle, entity, mu0::Vector{Float64}, b0, Tinv::Matrix{Float64}, nu; A = C_NULL, z = C_NULL)
+  check(h, ccall((:bdf_nw_sample_async, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                 h.ptr, entity, mu0, b0, Tinv, nu, A, z))
+end
+function nw_sample_fetch(h::Handle, entity, D::Int)
+  mu = zeros(D); Lambda = zeros(D, D)
+  check(h, ccall((:bdf_nw_sample_fetch, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), h.ptr, entity, mu, Lambda))
+  return mu, Lambda
+end
+
+## ---- column-split beta solve over the ranks (solve_cg2, src/parallel_matrix.jl:488-507): map every peer's beta once ---------------------
+function ipc_export_beta(h::Handle, entity)
+  buf = zeros(UInt8, 64)
+  check(h, ccall((:bdf_ipc_export_beta, LIB), Cint, (Ptr{Void}, Cint, Ptr{UInt8}), h.ptr, entity, buf))
+  return buf
+end
+ipc_import_beta(h::Handle, entity, peer_rank::Integer, handle::Vector{UInt8}) =
+  check(h, ccall((:bdf_ipc_import_beta, LIB), Cint, (Ptr{Void}, Cint, Cint, Ptr{UInt8}), h.ptr, entity, peer_rank, handle))
+
 end # module

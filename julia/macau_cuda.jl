@@ -9,10 +9,17 @@ using Distributions
 function macau_cuda(data::RelationData;
                     num_latent::Int = 10, lambda_beta = NaN, burnin = 500, psamples = 200, verbose::Bool = true,
                     full_lambda_u = true, reset_model = true, compute_ff_size = 6500, tol = NaN, clamp::Vector{Float64} = Float64[],
-                    device::Int = 0, seed::Integer = 0, inject_noise::Bool = false)
+                    device::Int = 0, devices::Vector{Int} = Int[], seed::Integer = 0, inject_noise::Bool = false,
+                    rank::Int = 0, world::Int = 1, peers = nothing)
+  # devices = [0, 1, 2, 3]: one Julia worker process per GPU, the counterpart of latent_pids (src/macau.jl:12,44-66); see macau_cuda_multi below
+  if length(devices) > 1 && world == 1
+    return macau_cuda_multi(data, devices; num_latent = num_latent, lambda_beta = lambda_beta, burnin = burnin, psamples = psamples, verbose = verbose,
+                            full_lambda_u = full_lambda_u, reset_model = reset_model, compute_ff_size = compute_ff_size, tol = tol, clamp = clamp,
+                            seed = seed, inject_noise = inject_noise)
+  end
   reset_model && reset!(data, num_latent, lambda_beta = lambda_beta, compute_ff_size = compute_ff_size)
   D   = num_latent
-  h   = BDFCuda.create(D, device = device)
+  h   = BDFCuda.create(D, device = device, rank = rank, world = world)
   BDFCuda.set_seed(h, seed)
   ent = Dict{Entity,Cint}()
   for en in data.entities
@@ -40,8 +47,17 @@ function macau_cuda(data::RelationData;
   end
 
   rel = data.relations[1]
-  test_ids = convert(Matrix{Int64}, array(rel.test_vec[:, 1:end-1]))
-  probe_rat_all = zeros(numTest(rel)); probe_stdev = zeros(numTest(rel)); counter_prob = 1
+  # the test set goes to the device once; the running posterior mean, the sum of squares and the clamped RMSE of src/macau.jl:164-200 are
+  # accumulated there (with several ranks: this rank's share rank+1:world:ntest, the sums are added up by the master)
+  mine     = (rank + 1) : world : numTest(rel)
+  test_ids = convert(Matrix{Int64}, array(rel.test_vec[mine, 1:end-1]))
+  if numTest(rel) > 0
+    BDFCuda.set_test(h, rid[1], test_ids, convert(Vector{Float64}, array(rel.test_vec[mine, end])), rel.class_cut,
+                     test_F = hasFeatures(rel) ? full(rel.test_F)[mine, :] : C_NULL)
+  end
+  BDFCuda.set_async(h, true)
+  peers != nothing && peers.connect(h, ent)                 # multi-GPU: exchange the IPC handles (factor replicas, beta buffers)
+  rmse_avg = NaN; err_avg = NaN
 
   for i in 1 : burnin + psamples
     # sample relation model (alpha, relation-level beta) — src/macau.jl:84-93
@@ -53,7 +69,8 @@ function macau_cuda(data::RelationData;
         r.model.beta = BDFCuda.sample_beta_rel!(h, rid[k], r.model.lambda_beta, size(r.F, 2))   # also refreshes linear_values
       end
     end
-    # latent vectors and their Normal-Wishart hyper-parameters — src/macau.jl:96-134
+    # latent vectors and their Normal-Wishart hyper-parameters — src/macau.jl:96-134. The draw of an entity is first needed by ITS next
+    # half-sweep, so it is started asynchronously (side stream) and fetched after the loop: it overlaps the next entity's row kernel.
     for en in data.entities
       e = ent[en]; mj = en.model
       nu = mj.nu0; Tinv = mj.WI
@@ -69,6 +86,10 @@ function macau_cuda(data::RelationData;
         BDFCuda.sample_mode!(h, e, mj.mu, mj.Lambda)        # one relation or several: the engine sums them per row
         N, NU, NS = BDFCuda.nw_stats(h, e, D)
       end
+      if peers != nothing                                    # several GPUs: add the ranks' statistics up (master/worker remotecalls)
+        N, NU, NS = peers.allreduce_stats(N, NU, NS)
+        BDFCuda.set_nw_stats(h, e, N, NU, NS)
+      end
       if inject_noise
         # the reference's own variates: Bartlett factor of Wishart(nu + N, .) and the MvNormal normals (src/normal_wishart.jl:38-42)
         A = zeros(D, D)
@@ -76,10 +97,13 @@ function macau_cuda(data::RelationData;
           A[a, a] = sqrt(rand(Chisq(nu + N - a + 1)))
           for b in 1:a-1; A[a, b] = randn(); end
         end
-        mj.mu, mj.Lambda = BDFCuda.nw_sample(h, e, mj.mu0, mj.b0, Tinv, nu, A = A, z = randn(D))
+        BDFCuda.nw_sample_async(h, e, mj.mu0, mj.b0, Tinv, nu, A = A, z = randn(D))
       else
-        mj.mu, mj.Lambda = BDFCuda.nw_sample(h, e, mj.mu0, mj.b0, Tinv, nu)
+        BDFCuda.nw_sample_async(h, e, mj.mu0, mj.b0, Tinv, nu)
       end
+    end
+    for en in data.entities
+      en.model.mu, en.model.Lambda = BDFCuda.nw_sample_fetch(h, ent[en], D)
     end
     # update_beta! — src/macau.jl:138-140
     for en in data.entities
@@ -92,21 +116,9 @@ function macau_cuda(data::RelationData;
     end
     BDFCuda.advance_sweep(h)
 
-    probe_rat = hasFeatures(rel) ? BDFCuda.predict(h, rid[1], test_ids, full(rel.test_F)) : BDFCuda.predict(h, rid[1], test_ids)
-    if i > burnin
-      if i == burnin + 1
-        counter_prob = 1; probe_rat_all = probe_rat; probe_stdev = probe_rat .^ 2
-      else
-        probe_rat_all = (counter_prob * probe_rat_all + probe_rat) / (counter_prob + 1)
-        probe_stdev  += probe_rat .^ 2
-        counter_prob += 1
-      end
-    else
-      probe_rat_all = probe_rat
-    end
-    if verbose && numTest(rel) > 0
-      cl = isempty(clamp) ? probe_rat_all : makeClamped(probe_rat_all, clamp)
-      @printf("%3d: RMSE=%6.4f\n", i, sqrt(mean((array(rel.test_vec[:, end]) - cl) .^ 2)))
+    if numTest(rel) > 0
+      rmse_avg, rmse, err_avg, counter_prob = BDFCuda.predict_accumulate(h, rid[1], i > burnin, clamp)   # 40 bytes come back per iteration
+      verbose && rank == 0 && @printf("%3d: RMSE=%6.4f\n", i, rmse_avg)
     end
   end
 
@@ -117,9 +129,55 @@ function macau_cuda(data::RelationData;
   result = Dict{AbstractString,Any}()
   result["num_latent"] = num_latent; result["burnin"] = burnin; result["psamples"] = psamples
   if numTest(rel) > 0
-    cl = isempty(clamp) ? probe_rat_all : makeClamped(probe_rat_all, clamp)
-    result["RMSE"] = sqrt(mean((array(rel.test_vec[:, end]) - cl) .^ 2))
-    result["ROC"]  = AUC_ROC(rel.test_label, -vec(probe_rat_all))
+    probe_rat_all, probe_stdev, _ = BDFCuda.get_test_predictions(h, rid[1], length(mine))
+    result["RMSE"] = rmse_avg; result["accuracy"] = err_avg
+    world == 1 && (result["ROC"] = AUC_ROC(rel.test_label, -vec(probe_rat_all)))
+    result["probe_rat_all"] = probe_rat_all; result["probe_stdev"] = probe_stdev
   end
+  return result
+end
+
+
+# ---- several GPUs: one worker process per device, like the reference's latent_pids workers (src/macau.jl:44-66). Every worker runs
+# macau_cuda on its own handle (rank r of `world`) and owns the rows the library deals to it; drawn rows are stored straight into every peer's
+# replica by the row kernel once the 64-byte IPC handles have been exchanged (`connect`), the (N, NU, NS) statistics are added up through
+# the master (`allreduce_stats`; a CUDA-aware MPI or NCCL binding on BDFCuda.stats_dev does the same without the host hop).
+type Peers
+  rank::Int
+  world::Int
+  connect::Function          # (h, ent) -> exchanges ipc_export / ipc_import(_beta) with the other ranks
+  allreduce_stats::Function  # (N, NU, NS) -> sums over ranks
+end
+
+function macau_cuda_multi(data::RelationData, devices::Vector{Int}; kw...)
+  world = length(devices)
+  length(workers()) >= world - 1 || error("devices = $devices needs $(world - 1) worker processes (addprocs)")
+  pids  = vcat(myid(), workers()[1:world-1])
+  # rendezvous through RemoteChannels owned by the master: one mailbox per rank for the handle exchange, one per rank for the reductions
+  boxes = [RemoteChannel(() -> Channel{Any}(4 * world)) for r in 1:world]
+  function peers_for(r)
+    connect = (h, ent) -> begin
+      mine = Dict{Any,Any}(); for (en, e) in ent; mine[en.name] = (BDFCuda.ipc_export(h, e), hasFeatures(en) ? BDFCuda.ipc_export_beta(h, e) : UInt8[]); end
+      for q in 1:world; q == r || put!(boxes[q], (r, mine)); end
+      for k in 1:world-1
+        (q, theirs) = take!(boxes[r])
+        for (en, e) in ent
+          BDFCuda.ipc_import(h, e, q - 1, theirs[en.name][1])
+          isempty(theirs[en.name][2]) || BDFCuda.ipc_import_beta(h, e, q - 1, theirs[en.name][2])
+        end
+      end
+    end
+    allreduce = (N, NU, NS) -> begin
+      for q in 1:world; q == r || put!(boxes[q], (N, NU, NS)); end
+      for k in 1:world-1
+        (n2, nu2, ns2) = take!(boxes[r]); N += n2; NU += nu2; NS += ns2
+      end
+      (N, NU, NS)
+    end
+    Peers(r - 1, world, connect, allreduce)
+  end
+  refs = [@spawnat pids[r] macau_cuda(data; device = devices[r], rank = r - 1, world = world, peers = peers_for(r), kw...) for r in 2:world]
+  result = macau_cuda(data; device = devices[1], rank = 0, world = world, peers = peers_for(1), kw...)
+  map(fetch, refs)
   return result
 end
