@@ -254,8 +254,15 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 pending.append((e, mj))
             else:
                 mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu, A, z)
-        for e, mj in pending:
-            mj.mu, mj.Lambda = eng.nw_sample_fetch(e)
+        def fetch_draws():
+            for e, mj in pending:
+                mj.mu, mj.Lambda = eng.nw_sample_fetch(e)
+            pending.clear()
+
+        # the draws are needed on the host by update_beta! (this iteration) or else by the next iteration: fetch them as late as possible so
+        # that the last entity's draw overlaps the test-set kernel
+        if any(en.hasFeatures() for en in data.entities):
+            fetch_draws()
         # update_beta! — src/macau.jl:138-140, src/sampling.jl:361-370
         for e, en in zip(ents, data.entities):
             if en.hasFeatures():
@@ -281,6 +288,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 sums = host_acc.step(probe_rat, posterior)
             rmse_avg = math.sqrt(sums[0] / sums[3])   # src/macau.jl:196
             err_avg = sums[2] / sums[3]                # :193-194
+        fetch_draws()
         if posterior:
             if output and lead:
                 # saving latent vectors to disk — src/macau.jl:149-162 (Float32, num_latent × count as Julia holds model.sample)

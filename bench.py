@@ -304,10 +304,11 @@ def run_ours(args):
             if dist is not None:
                 dist.all_reduce(ds.views[e][2])               # (1+D+D²) doubles; also orders the peer stores
             eng.nw_sample_async(e, mu0, 2.0, WI, float(D))    # H2D hyper-priors; the draw runs beside the next entity's row kernel
-        for e in (e1, e2):
-            hyper[e] = eng.nw_sample_fetch(e)                 # D2H (mu, Lambda); the same draw on every rank
         eng.advance_sweep()
-        return eng.predict_accumulate(rel, True, clamp)       # running posterior mean + clamped SSE on the device; 40 bytes D2H
+        out = eng.predict_accumulate(rel, True, clamp)        # running posterior mean + clamped SSE on the device; 40 bytes D2H
+        for e in (e1, e2):
+            hyper[e] = eng.nw_sample_fetch(e)                 # D2H (mu, Lambda), first needed by the NEXT sweep; the same draw on every rank
+        return out
 
     eng.test_reset(rel)
     for _ in range(max(1, min(args.warmup, 2))):
