@@ -30,6 +30,15 @@
 #ifndef BDF_K4_UNROLL
 #define BDF_K4_UNROLL 1
 #endif
+#ifndef BDF_KS4
+#define BDF_KS4 16   // observations per gather stage of the 4-warp CTAs
+#endif
+#ifndef BDF_NBUF4
+#define BDF_NBUF4 3  // stages in their ring
+#endif
+#ifndef BDF_GATHER_LDGSTS
+#define BDF_GATHER_LDGSTS 0  // 1: the 4-warp CTAs gather with 16-byte cp.async (LDGSTS) instead of one TMA bulk copy per row (A/B knob)
+#endif
 #ifndef BDF_K4_UNROLL4
 #define BDF_K4_UNROLL4 2  // 4-warp CTAs (D > 32): two k-steps per loop trip — the fragment loads of the second overlap the DMMAs of the first (+1 % on C2)
 #endif
@@ -138,6 +147,10 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// makes the mbarrier track the completion of all prior cp.async of this thread; counts as one of the barrier's expected arrivals
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -246,9 +259,10 @@ struct RowKernel {
   static constexpr int PST = NW * TPW * 64 + DP;  // doubles per parked partial
   // gather ring of the row kernel
   static constexpr int GP = NW == 8 ? 1 : (NW == 4 ? 2 : 8);  // passes per stage
-  static constexpr int KS = KS_ > 0 ? KS_ : OPP * GP;         // observations per stage (16)
-  static constexpr int NBUF = NBUF_ > 0 ? NBUF_ : (NW == 1 ? BDF_NBUF1 : 3);
+  static constexpr int KS = KS_ > 0 ? KS_ : (NW == 4 ? BDF_KS4 : OPP * GP);  // observations per stage (16)
+  static constexpr int NBUF = NBUF_ > 0 ? NBUF_ : (NW == 1 ? BDF_NBUF1 : (NW == 4 ? BDF_NBUF4 : 3));
   static constexpr int PF = NBUF - 1;                          // stages in flight ahead of the one being consumed
+  static constexpr bool LDGSTS = BDF_GATHER_LDGSTS && NW == 4 && KS == 16;  // gather by cp.async: 8 threads per row, 16 rows per stage
   static constexpr int STG = KS * S * (TENSOR ? 2 : 1) + KS;   // doubles per stage: tile(s) + residuals
   static constexpr int PSZ = 64 * C::NT;  // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
   static constexpr int REGSZ = PSZ > NBUF * STG ? PSZ : NBUF * STG;  // the tiles alias the (dead) stage ring
@@ -365,7 +379,7 @@ struct RowKernel {
       }
     if (tid == 0) {
 #pragma unroll
-      for (int b = 0; b < NBUF; b++) mbar_init(fullb + b, 1);
+      for (int b = 0; b < NBUF; b++) mbar_init(fullb + b, LDGSTS ? NTHR : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -419,6 +433,35 @@ struct RowKernel {
       cp_async_commit();
     };
     auto issue = [&](int s) {
+      if constexpr (LDGSTS) {
+        // 8 threads per partner row, 16-byte pieces (t%8) + 8j; rows past the end of the item are zero-filled (src-size 0)
+        const int b = (int)((gs + (uint32_t)s) % NBUF);
+        double* st = ring + b * STG;
+        int nvalid = len - s * KS;
+        if (nvalid > KS) nvalid = KS;
+        const int row = tid >> 3, q = tid & 7;
+        const bool ok = row < nvalid;
+        const int mb = (int)((gs + (uint32_t)s) & 1u);
+        const int c0 = mcol[(mb * 2) * KS + row];
+        const double* src0 = rt.P0 + (size_t)c0 * p.ld;
+#pragma unroll 1
+        for (int pc = q; pc < npc; pc += 8) cp_async16(st + row * S + 2 * pc, src0 + 2 * pc, ok ? 16 : 0);
+        if (TENSOR) {
+          const int c1 = rt.col1 ? mcol[(mb * 2 + 1) * KS + row] : 0;
+          const double* src1 = rt.P1 + (size_t)c1 * p.ld;
+#pragma unroll 1
+          for (int pc = q; pc < npc; pc += 8) cp_async16(st + (KS + row) * S + 2 * pc, src1 + 2 * pc, ok ? 16 : 0);
+        }
+        cp_async_mbar_arrive_noinc(fullb + b);
+        cp_async_commit();  // the gather of a stage is one cp.async group of its own (see the wait in the stage loop)
+        if (q == 0) {
+          const double r = ok ? mval[mb * KS + row] - rt.mean : 0.0;
+          st[(TENSOR ? 2 : 1) * KS * S + row] = r;
+          // the aug column (index D) lies outside the copied pieces only if D is even; a cp.async piece never covers it then
+          if (aug) st[row * S + D] = r;
+        }
+        return;
+      }
       if (gl) {
         const int b = (int)((gs + (uint32_t)s) % NBUF);
         double* st = ring + b * STG;
@@ -455,11 +498,15 @@ struct RowKernel {
       load_meta(0);
       if (PF > 1 && nst > 1) load_meta(1);
       cp_async_wait<0>();
+      if (LDGSTS) sync();  // every thread reads the metadata the issuing lanes fetched
       if (!dbg_nogather) {
         issue(0);
         if (PF > 1 && nst > 1) issue(1);
       }
-      if (PF < nst) load_meta(PF);
+      if (PF < nst) {
+        if (LDGSTS) sync();  // … and is done reading table buffer 0 before it is refilled
+        load_meta(PF);
+      }
     }
     // ---- everything below runs under the shadow of the first gathers ---------------------------------------------------
     // Λ rides in the accumulators from the start (as Λ/α, on the row's first chunk), so that parking the tiles after the
@@ -509,13 +556,15 @@ struct RowKernel {
       const uint32_t g = gs + (uint32_t)s;
       if (!dbg_nogather) mbar_wait(fullb + (g % NBUF), (g / NBUF) & 1);  // the rows of stage s have landed
       BDF_TP(1)
-      sync();                                          // everyone is done with stage s-1: its buffer may be refilled
-      BDF_TP(2)
       if (s + PF < nst) {
-        cp_async_wait<0>();  // this thread's metadata of stage s+PF (requested a stage ago)
-        if (!dbg_nogather) issue(s + PF);
+        // the metadata of stage s+PF, requested a stage ago. With the cp.async gather the groups alternate (metadata, gather, metadata, …):
+        // all but the newest group — the gather issued in the previous trip — must have landed
+        if (LDGSTS && s > 0) cp_async_wait<1>(); else cp_async_wait<0>();
       }
+      sync();                                          // everyone is done with stage s-1 (its buffer may be refilled) and sees the metadata
+      BDF_TP(2)
       if (s + PF + 1 < nst) load_meta(s + PF + 1);
+      if (s + PF < nst && !dbg_nogather) issue(s + PF);
       BDF_TP(3)
       const double* buf = ring + (g % NBUF) * STG;
       const double* rs = buf + (TENSOR ? 2 : 1) * KS * S;

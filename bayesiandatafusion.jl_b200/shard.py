@@ -151,6 +151,13 @@ class DistributedSweep:
         self.group = group
         self.dist = dist if engine.world > 1 else None
         dev = torch.device("cuda", torch.cuda.current_device())
+        # ONE stream for the engine's kernels, the collectives and the side-stream events: bind the engine to torch's current stream.
+        # The default stream's handle is NULL, which bdf_set_stream reads as "the engine's own stream", so in that case a fresh torch
+        # stream is made current first. half_sweep() refuses to run if the caller has switched streams since.
+        if torch.cuda.current_stream().cuda_stream == 0:
+            torch.cuda.set_stream(torch.cuda.Stream())
+        self.stream = torch.cuda.current_stream()
+        engine.set_stream(self.stream.cuda_stream)
         self.views = {}
         for e in self.entities:
             ptr, nper, ld = engine.factors_dev(e)
@@ -188,6 +195,8 @@ class DistributedSweep:
 
         eng = self.eng
         main = torch.cuda.current_stream()
+        if main.cuda_stream != self.stream.cuda_stream:
+            raise RuntimeError("DistributedSweep: the current CUDA stream changed since construction; the engine's kernels and the collectives must share one stream")
         if e in self.draw_done:
             main.wait_event(self.draw_done.pop(e))  # this entity's (mu, Lambda) from its previous draw
         eng.step_sample(e)
