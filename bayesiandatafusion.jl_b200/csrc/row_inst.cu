@@ -63,7 +63,7 @@ static int launch_rows_t(bdf_t* h, const RowParams& p, int n_items) {
   if constexpr (kWS && !TENSOR) {
     if (h->use_ws) return launch_rows_ws(h, p, n_items);
   }
-  using K = RowKernel<kDP, kNW, TENSOR, (kNW == 1 && TENSOR) ? BDF_TKS1 : 0, 0>;
+  using K = RowKernel<kDP, kNW, TENSOR, (kNW == 1 && TENSOR) ? BDF_TKS1 : 0, (kNW == 1 && TENSOR) ? 3 : 0>;
   const uint32_t bit = TENSOR ? BDF_OPTIN_ROWS_TENSOR : BDF_OPTIN_ROWS;
   if (!(h->smem_optin & bit)) {
     CU(cudaFuncSetAttribute(row_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));

@@ -30,6 +30,9 @@
 #ifndef BDF_K4_UNROLL
 #define BDF_K4_UNROLL 1
 #endif
+#ifndef BDF_KS1
+#define BDF_KS1 24   // observations per gather stage of the one-warp CTAs (D <= 32): two 24-row stages, same shared memory as three of 16 (+3 % at D=32)
+#endif
 #ifndef BDF_KS4
 #define BDF_KS4 28   // observations per gather stage of the 4-warp CTAs: two 28-row stages beat three 16-row ones (fewer barrier / issue phases per observation; +2.5 % at D=100, +5 % at D=64, +10 % at D=48); 28 is the most that keeps four D=100 CTAs per SM
 #endif
@@ -46,7 +49,7 @@
 #define BDF_FD_UNROLL 8
 #endif
 #ifndef BDF_NBUF1
-#define BDF_NBUF1 3
+#define BDF_NBUF1 2
 #endif
 #ifndef BDF_MINB1
 #define BDF_MINB1 16
@@ -259,7 +262,7 @@ struct RowKernel {
   static constexpr int PST = NW * TPW * 64 + DP;  // doubles per parked partial
   // gather ring of the row kernel
   static constexpr int GP = NW == 8 ? 1 : (NW == 4 ? 2 : 8);  // passes per stage
-  static constexpr int KS = KS_ > 0 ? KS_ : (NW == 4 ? BDF_KS4 : OPP * GP);  // observations per stage (16)
+  static constexpr int KS = KS_ > 0 ? KS_ : (NW == 4 ? BDF_KS4 : (NW == 1 ? BDF_KS1 : OPP * GP));  // observations per stage (16)
   static constexpr int NBUF = NBUF_ > 0 ? NBUF_ : (NW == 1 ? BDF_NBUF1 : (NW == 4 ? BDF_NBUF4 : 3));
   static constexpr int PF = NBUF - 1;                          // stages in flight ahead of the one being consumed
   static constexpr bool LDGSTS = BDF_GATHER_LDGSTS && NW == 4 && KS == 16;  // gather by cp.async: 8 threads per row, 16 rows per stage
