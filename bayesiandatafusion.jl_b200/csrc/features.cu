@@ -107,51 +107,71 @@ __global__ void __launch_bounds__(256) spbin_gather_kernel(const SpItem* __restr
   }
 }
 
-// The same product for a NARROW column window (pitch ≤ 16 doubles: the rank's share of the right-hand sides in a column-split CG). With one
-// index per warp step only `ld` of the 32 lanes would load — the kernel is bound by L2 requests per second, so half the bytes would cost the
-// same time. Here the warp handles 32/LPR indices per step, LPR lanes (= one 8·LPR-byte segment) per gathered row, so a load instruction
-// still moves 256 bytes; the 32/LPR interleaved partial sums are combined by a shuffle tree at the end (deterministic; not the strictly
-// sequential order of the full-width kernel, which stays the one behind bdf_spmm and every single-GPU product).
-template <int LPR, bool VAL>
-__global__ void __launch_bounds__(256) spbin_gather_narrow_kernel(const SpItem* __restrict__ items, int n_items, const int32_t* __restrict__ idx,
-                                                                  const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                                                                  double* __restrict__ part, int ld, double lam, const double* __restrict__ P) {
+// The same product with as few instructions per index as the hardware allows — the kernel above is issue-bound (ncu: 69 % of the issue slots
+// busy, ≈20 warp instructions per index, L2 at 21–38 % of its throughput). Here LPR lanes cover one gathered row with 128-bit loads (two columns per
+// lane) and the warp handles 32/LPR indices per step: a load instruction always moves 512 bytes, one shuffle serves 32/LPR indices. The 32/LPR
+// interleaved partial sums are combined by a shuffle tree at the end, so the summation order is deterministic but NOT the strictly sequential
+// order of the reference — this kernel is used where that order is unobservable (inside the CG iteration, whose iterates are chaotic anyway,
+// and on the packed column windows of a column-split solve); bdf_spmm, F·beta and the rhs of sample_beta keep the in-order kernel.
+template <int LPR, int NC2, bool VAL>
+__global__ void __launch_bounds__(256) spbin_gather_fast_kernel(const SpItem* __restrict__ items, int n_items, const int32_t* __restrict__ idx,
+                                                                const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                                                                double* __restrict__ part, int ld, double lam, const double* __restrict__ P) {
   constexpr int G = 32 / LPR;
   const int lane = threadIdx.x & 31, g = lane / LPR, c = lane % LPR;
-  const bool col_ok = c < ld;
+  bool ok[NC2];
+#pragma unroll
+  for (int k = 0; k < NC2; k++) ok[k] = 2 * (c + LPR * k) < ld;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int it = warp0; it < n_items; it += nwarps) {
     const SpItem w = items[it];
-    double acc = 0.0;
+    double2 acc[NC2];
+#pragma unroll
+    for (int k = 0; k < NC2; k++) acc[k] = make_double2(0.0, 0.0);
     for (int64_t o = w.beg; o < w.end; o += 32) {
       const int n = (int)min((int64_t)32, w.end - o);
       const int mine = lane < n ? __ldg(idx + o + lane) : 0;
       const double myval = (VAL && lane < n) ? __ldg(vals + o + lane) : 0.0;
-      for (int j0 = 0; j0 < n; j0 += 4 * G) {
-        double v[4];
+      constexpr int U = G >= 8 ? 2 : 4;  // index groups in flight
+      for (int j0 = 0; j0 < n; j0 += U * G) {
+        double2 v[U][NC2];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < U; u++) {
           const int j = j0 + u * G + g;
           const int ci = __shfl_sync(0xffffffffu, mine, j & 31);
           const double a = VAL ? __shfl_sync(0xffffffffu, myval, j & 31) : 1.0;
-          const double x = (j < n && col_ok) ? __ldg(X + (size_t)ci * ld + c) : 0.0;
-          v[u] = VAL ? __dmul_rn(a, x) : x;
+          const double2* src = reinterpret_cast<const double2*>(X + (size_t)ci * ld) + c;
+#pragma unroll
+          for (int k = 0; k < NC2; k++) {
+            double2 x = (j < n && ok[k]) ? __ldg(src + LPR * k) : make_double2(0.0, 0.0);
+            if (VAL) { x.x = __dmul_rn(a, x.x); x.y = __dmul_rn(a, x.y); }
+            v[u][k] = x;
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) acc = __dadd_rn(acc, v[u]);
+        for (int u = 0; u < U; u++)
+#pragma unroll
+          for (int k = 0; k < NC2; k++) { acc[k].x = __dadd_rn(acc[k].x, v[u][k].x); acc[k].y = __dadd_rn(acc[k].y, v[u][k].y); }
       }
     }
 #pragma unroll
-    for (int off = LPR; off < 32; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (g == 0 && col_ok) {
-      if (w.slot < 0) {
-        double sres = acc;
-        if (P) sres += lam * P[(size_t)w.row * ld + c];
-        Y[(size_t)w.row * ld + c] = sres;
-      } else {
-        part[(size_t)w.slot * ld + c] = acc;
-      }
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+      for (int k = 0; k < NC2; k++) { acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, off); acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, off); }
+    if (g == 0) {
+#pragma unroll
+      for (int k = 0; k < NC2; k++)
+        if (ok[k]) {
+          const int col = 2 * (c + LPR * k);
+          if (w.slot < 0) {
+            double2 r = acc[k];
+            if (P) { const double2 pv = *reinterpret_cast<const double2*>(P + (size_t)w.row * ld + col); r.x += lam * pv.x; r.y += lam * pv.y; }
+            *reinterpret_cast<double2*>(Y + (size_t)w.row * ld + col) = r;
+          } else {
+            *reinterpret_cast<double2*>(part + (size_t)w.slot * ld + col) = acc[k];
+          }
+        }
     }
   }
 }
@@ -562,7 +582,7 @@ int need_features(bdf_t* h, int entity) {
 
 // `ldx` = pitch of X / Y / P in doubles (0 = the handle's): a column window of the right-hand sides (the rank's share of a sharded CG,
 // src/parallel_matrix.jl:488-507) is a packed buffer with a smaller pitch, so a gathered row is only as wide as the window
-int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr, int ldx = 0) {
+int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y, double lam = 0.0, const double* P = nullptr, int ldx = 0, bool exact = true) {
   const int ld = ldx > 0 ? ldx : h->ld;
   if (e.f_dense) {
     if (ld != h->ld) FAIL(BDF_ERR_STATE, "column windows are not used with dense feature matrices");
@@ -577,12 +597,12 @@ int spmm(bdf_t* h, const EntityS& e, bool transpose, const double* X, double* Y,
   const int nc = (ld + 31) / 32;
   double* part = reinterpret_cast<double*>(e.sp_part);
   const double* vals = transpose ? e.f_val_csc : e.f_val_csr;
-  if (ld <= 16 && ld < h->ld) {  // a column window of a sharded solve (never the full-width products)
-#define SPN(LPR_)                                                                                                                             \
-  if (vals) spbin_gather_narrow_kernel<LPR_, true><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, vals, X, Y, part, ld, lam, P);            \
-  else spbin_gather_narrow_kernel<LPR_, false><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, nullptr, X, Y, part, ld, lam, P);
-    if (ld <= 4) { SPN(4) } else if (ld <= 8) { SPN(8) } else { SPN(16) }
-#undef SPN
+  if (!exact) {  // order-free variant (CG iterations, column windows): fewest instructions per index
+#define SPF(LPR_, NC2_)                                                                                                                          \
+  if (vals) spbin_gather_fast_kernel<LPR_, NC2_, true><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, vals, X, Y, part, ld, lam, P);           \
+  else spbin_gather_fast_kernel<LPR_, NC2_, false><<<(int)g, 256, 0, h->stream>>>(items, ni, idx, nullptr, X, Y, part, ld, lam, P);
+    if (ld <= 4) { SPF(2, 1) } else if (ld <= 8) { SPF(4, 1) } else if (ld <= 16) { SPF(8, 1) } else if (ld <= 32) { SPF(16, 1) } else if (ld <= 64) { SPF(32, 1) } else { SPF(32, 2) }
+#undef SPF
     h->launches++;
     if (e.sp_nlong[o] > 0) {
       spbin_reduce_kernel<<<std::min(e.sp_nlong[o], 148 * 4), 128, 0, h->stream>>>(reinterpret_cast<const SpLong*>(e.sp_long[o]), e.sp_nlong[o], part, Y, ld, lam, P);
@@ -676,8 +696,8 @@ int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda
     coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(R, R, n, ld, D, part);
     cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 0, (int)std::min<int64_t>(iter, 2), st);
     cg_update_p_kernel<<<grid_for(vn), 256, 0, h->stream>>>(P, R, n, ld, D, st.coef, st.active, (int)std::min<int64_t>(iter, 2));
-    int rc = spmm(h, e, false, P, T, 0.0, nullptr, ld);    // T = F·P
-    if (!rc) rc = spmm(h, e, true, T, Z, lambda, P, ld);   // Z = Fᵀ·T + λ·P
+    int rc = spmm(h, e, false, P, T, 0.0, nullptr, ld, false);    // T = F·P       (order-free gather: see spbin_gather_fast_kernel)
+    if (!rc) rc = spmm(h, e, true, T, Z, lambda, P, ld, false);   // Z = Fᵀ·T + λ·P
     coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(Z, P, n, ld, D, part);
     cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 1, (int)std::min<int64_t>(iter, 2), st);
     cg_update_xr_kernel<<<grid_for(vn), 256, 0, h->stream>>>(X, R, P, Z, n, ld, D, st.coef, st.active);
@@ -1476,9 +1496,10 @@ int bdf_debug_ata_time_window(bdf_t* h, int entity, int reps, int ncols, double*
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   const int ldw = ncols > 0 && ncols < h->D ? (ncols + 3) / 4 * 4 : 0;  // a packed column window like a rank's share of a column-split CG
-  spmm(h, e, false, e.beta, T, 0.0, nullptr, ldw); spmm(h, e, true, T, Z, 1.0, e.beta, ldw);
+  const bool exact = ncols < 0;  // ncols < 0: the in-order kernel pair of bdf_ata_mul; else the order-free pair the CG iteration runs
+  spmm(h, e, false, e.beta, T, 0.0, nullptr, ldw, exact); spmm(h, e, true, T, Z, 1.0, e.beta, ldw, exact);
   cudaEventRecord(a, h->stream);
-  for (int i = 0; i < reps; i++) { spmm(h, e, false, e.beta, T, 0.0, nullptr, ldw); spmm(h, e, true, T, Z, 1.0, e.beta, ldw); }
+  for (int i = 0; i < reps; i++) { spmm(h, e, false, e.beta, T, 0.0, nullptr, ldw, exact); spmm(h, e, true, T, Z, 1.0, e.beta, ldw, exact); }
   cudaEventRecord(b, h->stream);
   cudaEventSynchronize(b);
   float ms = 0.f;

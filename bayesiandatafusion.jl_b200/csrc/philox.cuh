@@ -57,4 +57,15 @@ __host__ __device__ inline double philox_normal(uint64_t seed, uint64_t sweep, u
   return (j & 1) ? r * s : r * c;
 }
 
+// both normals of pair j/2 at once (z0 = number 2·(j/2), z1 = number 2·(j/2)+1): the same values philox_normal returns one at a time
+__host__ __device__ inline void philox_normal_pair(uint64_t seed, uint64_t sweep, uint32_t stream, uint64_t row, int pair, double& z0, double& z1) {
+  double u1, u2;
+  philox_uniform2(seed, sweep, stream, row, (uint32_t)pair, u1, u2);
+  const double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
 }  // namespace bdf

@@ -541,16 +541,22 @@ struct RowKernel {
       }
       lmu[tid] = s;
     }
-    // The row's standard normals (injected, or Philox + Box–Muller in double: a few hundred instructions each) are
-    // produced here by DP threads in parallel, under the shadow of the first gather, and parked until the
-    // substitution needs them — not serially by one warp at the end of the row.
-    if (tid < DP) {
-      double z = 0.0;
-      if (tid < D) {
-        const int64_t grow0 = p.row_of_slot ? (int64_t)p.row_of_slot[c.slot] : (int64_t)c.lrow * p.world + p.rank;
-        z = p.Z ? __ldg(p.Z + (size_t)c.slot * p.ld + tid) : philox_normal(p.seed, p.sweep, philox_stream(PHILOX_ROW, (uint32_t)p.entity), grow0, tid);
+    // The row's standard normals (injected, or Philox + Box–Muller in double: a few hundred instructions per PAIR) are
+    // produced here in parallel, under the shadow of the first gather, and parked until the substitution needs them — not serially by
+    // one warp at the end of the row. Even threads compute a Box–Muller pair and hand its second member to their odd neighbour.
+    {
+      double z = 0.0, zn = 0.0;
+      const int64_t grow0 = p.row_of_slot ? (int64_t)p.row_of_slot[c.slot] : (int64_t)c.lrow * p.world + p.rank;
+      if (p.Z) {
+        if (tid < D) z = __ldg(p.Z + (size_t)c.slot * p.ld + tid);
+      } else if (tid < D && !(tid & 1)) {
+        philox_normal_pair(p.seed, p.sweep, philox_stream(PHILOX_ROW, (uint32_t)p.entity), grow0, tid >> 1, z, zn);
       }
-      zs[tid] = z;
+      if (!p.Z) {  // uniform branch: every lane of the warp takes part in the shuffle
+        const double up = __shfl_up_sync(0xffffffffu, zn, 1);
+        if ((tid & 1) && tid < D) z = up;
+      }
+      if (tid < DP) zs[tid] = z;
     }
 
     BDF_STAMP(1);
