@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) spbin_gather_fast_kernel(const SpItem* __
       const int n = (int)min((int64_t)32, w.end - o);
       const int mine = lane < n ? __ldg(idx + o + lane) : 0;
       const double myval = (VAL && lane < n) ? __ldg(vals + o + lane) : 0.0;
-      constexpr int U = G >= 8 ? 2 : 4;  // index groups in flight
+      constexpr int U = G >= 8 ? 2 : (G >= 4 ? 4 : 8);  // index groups in flight (16 gathered rows per warp)
       for (int j0 = 0; j0 < n; j0 += U * G) {
         double2 v[U][NC2];
 #pragma unroll
