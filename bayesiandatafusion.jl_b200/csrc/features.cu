@@ -265,6 +265,73 @@ __global__ void cg_scalars_kernel(const double* __restrict__ part, int nblk, int
   }
 }
 
+// coldot_partial_kernel + cg_scalars_kernel in one launch: the block that finishes last (arrival counter) adds the partials up in block order —
+// the same fixed order as the two-kernel form — and updates the CG scalars. Two launches less per CG iteration.
+__global__ void __launch_bounds__(256) coldot_scalars_kernel(const double* __restrict__ A, const double* __restrict__ B, int64_t rows, int ld, int D,
+                                                             double* __restrict__ part, int* __restrict__ counter, int mode, int iter, CGState st) {
+  const int d0 = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t r = (int64_t)blockIdx.x * 8 + ty; r < rows; r += (int64_t)gridDim.x * 8) {
+    const double* a = A + (size_t)r * ld;
+    const double* b = B + (size_t)r * ld;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int d = d0 + 32 * k;
+      if (d < D) s[k] = fma(a[d], b[d], s[k]);
+    }
+  }
+  __shared__ double sh[8][128];
+  __shared__ int s_last;
+#pragma unroll
+  for (int k = 0; k < 4; k++) sh[ty][d0 + 32 * k] = s[k];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) t += sh[y][threadIdx.x];
+    part[(size_t)blockIdx.x * 128 + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(counter, 1);
+    s_last = old == (int)gridDim.x - 1;
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int d = threadIdx.x;
+  if (d < D) {
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; b++) t += __ldcg(part + (size_t)b * 128 + d);
+    if (mode == 2) {
+      st.tolv[d] = st.tolv[d] * sqrt(t);
+    } else if (mode == 0) {
+      double bk = 0.0;
+      if (st.active[d]) {
+        if (sqrt(t) < st.tolv[d]) {
+          st.active[d] = 0;
+        } else {
+          if (iter > 1) bk = t / st.bkden[d];
+          st.bkden[d] = t;
+          st.bknum[d] = t;
+          st.iters[d] += 1;
+        }
+      }
+      st.coef[d] = bk;
+    } else {
+      st.coef[d] = st.active[d] ? st.bknum[d] / t : 0.0;
+    }
+  }
+  __syncthreads();
+  if (mode == 0 && threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < D; k++) n += st.active[k];
+    *st.nactive = n;
+  }
+}
+
 // p = bk·p + r on the active columns (prod_add!, src/parallel_cg.jl:28-32); iter 1 keeps p = r
 __global__ void cg_update_p_kernel(double* __restrict__ P, const double* __restrict__ R, int64_t rows, int ld, int D, const double* __restrict__ bk,
                                    const int* __restrict__ active, int iter) {
@@ -671,13 +738,15 @@ int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda
   const size_t vn = (size_t)n * ld, vm = (size_t)m * ld;
   const int NBLK = 296;
   if (!e.cgbuf) {  // sized for the full width; a column window uses a prefix of each vector
-    int rc = dalloc(h, &e.cgbuf, 3 * (size_t)n * h->ld + (size_t)m * h->ld + (size_t)NBLK * 128 + 4 * 128 + 4 * 128);
+    int rc = dalloc(h, &e.cgbuf, 3 * (size_t)n * h->ld + (size_t)m * h->ld + (size_t)NBLK * 128 + 4 * 128 + 4 * 128 + 8);
     if (rc) return rc;
+    CU(cudaMemsetAsync(e.cgbuf + 3 * (size_t)n * h->ld + (size_t)m * h->ld + (size_t)NBLK * 128 + 8 * 128, 0, 64, h->stream));  // arrival counter
   }
   double* R = e.cgbuf; double* P = R + (size_t)n * h->ld; double* Z = P + (size_t)n * h->ld; double* T = Z + (size_t)n * h->ld; double* part = T + (size_t)m * h->ld;
   CGState st;
   st.bknum = part + (size_t)NBLK * 128; st.bkden = st.bknum + 128; st.coef = st.bkden + 128; st.tolv = st.coef + 128;
   st.active = reinterpret_cast<int*>(st.tolv + 128); st.iters = st.active + 128; st.nactive = st.iters + 128;
+  int* counter = reinterpret_cast<int*>(part + (size_t)NBLK * 128 + 8 * 128);  // self-resetting arrival counter of coldot_scalars_kernel
   std::vector<double> tolh(128, tol);
   std::vector<int> acth(128, 0), zero(128, 0);
   for (int d = 0; d < D; d++) acth[d] = 1;
@@ -687,21 +756,18 @@ int cg_solve_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda
   CU(cudaMemsetAsync(X, 0, vn * 8, h->stream));                                        // x = 0
   CU(cudaMemcpyAsync(R, B, vn * 8, cudaMemcpyDeviceToDevice, h->stream));              // r = b
   CU(cudaMemcpyAsync(P, B, vn * 8, cudaMemcpyDeviceToDevice, h->stream));              // p = r
-  coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(B, B, n, ld, D, part);
-  cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 2, 0, st);                // tol ← tol·‖b‖
-  h->launches += 2;
+  coldot_scalars_kernel<<<NBLK, 256, 0, h->stream>>>(B, B, n, ld, D, part, counter, 2, 0, st);   // tol ← tol·‖b‖
+  h->launches += 1;
   int nact = D;
   // one CG iteration (src/parallel_cg.jl:73-92); `iter` only matters as iter == 1 (p = r) versus iter > 1
   auto body = [&](int64_t iter) -> int {
-    coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(R, R, n, ld, D, part);
-    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 0, (int)std::min<int64_t>(iter, 2), st);
+    coldot_scalars_kernel<<<NBLK, 256, 0, h->stream>>>(R, R, n, ld, D, part, counter, 0, (int)std::min<int64_t>(iter, 2), st);
     cg_update_p_kernel<<<grid_for(vn), 256, 0, h->stream>>>(P, R, n, ld, D, st.coef, st.active, (int)std::min<int64_t>(iter, 2));
     int rc = spmm(h, e, false, P, T, 0.0, nullptr, ld, false);    // T = F·P       (order-free gather: see spbin_gather_fast_kernel)
     if (!rc) rc = spmm(h, e, true, T, Z, lambda, P, ld, false);   // Z = Fᵀ·T + λ·P
-    coldot_partial_kernel<<<NBLK, 256, 0, h->stream>>>(Z, P, n, ld, D, part);
-    cg_scalars_kernel<<<1, 128, 0, h->stream>>>(part, NBLK, D, 1, (int)std::min<int64_t>(iter, 2), st);
+    coldot_scalars_kernel<<<NBLK, 256, 0, h->stream>>>(Z, P, n, ld, D, part, counter, 1, (int)std::min<int64_t>(iter, 2), st);
     cg_update_xr_kernel<<<grid_for(vn), 256, 0, h->stream>>>(X, R, P, Z, n, ld, D, st.coef, st.active);
-    h->launches += 6;
+    h->launches += 4;
     return rc;
   };
   auto check = [&]() -> int {  // the all-converged test costs a drain of the stream

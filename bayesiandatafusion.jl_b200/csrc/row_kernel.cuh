@@ -36,6 +36,12 @@
 #ifndef BDF_KS4
 #define BDF_KS4 28   // observations per gather stage of the 4-warp CTAs: two 28-row stages beat three 16-row ones (fewer barrier / issue phases per observation; +2.5 % at D=100, +5 % at D=64, +10 % at D=48); 28 is the most that keeps four D=100 CTAs per SM
 #endif
+#ifndef BDF_KS4S
+#define BDF_KS4S 28  // the same for 32 < D <= 64 (six or more CTAs per SM)
+#endif
+#ifndef BDF_MINB4S
+#define BDF_MINB4S 6 // CTAs per SM the 4-warp kernel is compiled for at 32 < D <= 64
+#endif
 #ifndef BDF_NBUF4
 #define BDF_NBUF4 2  // stages in their ring
 #endif
@@ -262,7 +268,7 @@ struct RowKernel {
   static constexpr int PST = NW * TPW * 64 + DP;  // doubles per parked partial
   // gather ring of the row kernel
   static constexpr int GP = NW == 8 ? 1 : (NW == 4 ? 2 : 8);  // passes per stage
-  static constexpr int KS = KS_ > 0 ? KS_ : (NW == 4 ? BDF_KS4 : (NW == 1 ? BDF_KS1 : OPP * GP));  // observations per stage (16)
+  static constexpr int KS = KS_ > 0 ? KS_ : (NW == 4 ? (DP <= 64 ? BDF_KS4S : BDF_KS4) : (NW == 1 ? BDF_KS1 : OPP * GP));  // observations per stage (16)
   static constexpr int NBUF = NBUF_ > 0 ? NBUF_ : (NW == 1 ? BDF_NBUF1 : (NW == 4 ? BDF_NBUF4 : 3));
   static constexpr int PF = NBUF - 1;                          // stages in flight ahead of the one being consumed
   static constexpr bool LDGSTS = BDF_GATHER_LDGSTS && NW == 4 && KS == 16;  // gather by cp.async: 8 threads per row, 16 rows per stage
@@ -1002,7 +1008,7 @@ constexpr int big4_min_blocks() {
   return fit < 1 ? 1 : (fit > BDF_MINB4BIG ? BDF_MINB4BIG : fit);
 }
 template <class K>
-__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? BDF_MINB1 : (K::NW == 4 ? (K::DP > 64 ? big4_min_blocks<K>() : (K::TENSOR ? 4 : 6)) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
+__global__ void __launch_bounds__(K::NTHR, (K::NW == 1 ? BDF_MINB1 : (K::NW == 4 ? (K::DP > 64 ? big4_min_blocks<K>() : (K::TENSOR ? 4 : BDF_MINB4S)) : (K::TENSOR ? 2 : BDF_MINB)))) row_kernel(const RowParams p) {
   extern __shared__ __align__(16) double smem_dyn[];
   K::run(p, smem_dyn);
 }

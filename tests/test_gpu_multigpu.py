@@ -47,3 +47,10 @@ def test_macau_through_the_reference_api_on_several_devices():
         pytest.skip("needs at least two GPUs")
     out = _torchrun(2, "tools/mgpu_macau_check.py")
     assert "MGPU MACAU OK" in out, out[-2000:]
+
+
+def test_macau_devices_from_a_plain_process_spawns_its_workers():
+    if _ngpu() < 2:
+        pytest.skip("needs at least two GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mgpu_macau_spawn.py")], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU MACAU SPAWN OK" in r.stdout, r.stdout[-2000:] + "\n" + r.stderr[-3000:]
