@@ -187,6 +187,15 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
     tol_arg = math.nan if math.isnan(tol) else float(tol)
     stale = True  # the host model lags behind the device
     iter_seconds = []
+    pending = {}  # entity -> its model: Normal-Wishart draws started with nw_sample_async and not yet fetched
+
+    def fetch_draws(only=None):
+        """(mu, Lambda) of the asynchronous draws, as late as the host needs them: a draw is first used by the SAME entity's next half-sweep,
+        so it overlaps the other entities' row kernels and the test-set kernel (across iterations too)."""
+        for e in ([only] if only is not None else list(pending)):
+            if e in pending:
+                mj = pending.pop(e)
+                mj.mu, mj.Lambda = eng.nw_sample_fetch(e)
 
     def refresh_host_model():
         for e, en in zip(ents, data.entities):
@@ -219,9 +228,9 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 z2 = host_noise.standard_normal(r.F.shape[1]) if host_noise is not None else None
                 r.model.beta = eng.sample_beta_rel(rid, r.model.lambda_beta, z1, z2)
         # Sampling latent vectors — src/macau.jl:96-134 (entities in several relations: sample_user2_all!, :109-118)
-        pending = []
         for e, en in zip(ents, data.entities):
             mj = en.model
+            fetch_draws(e)
             if en.hasFeatures():
                 eng.update_uhat(e, mj.mu)               # uhat = (F·beta)', mu_matrix = mu .+ uhat, on the device (:102-104)
                 eng.sample_mode_uhat(e, mj.Lambda, None)
@@ -251,18 +260,13 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
             if hasattr(eng, "nw_sample_async"):
                 # the draw is first needed by THIS entity's next half-sweep: it runs beside the next entity's row kernel
                 eng.nw_sample_async(e, mj.mu0, mj.b0, Tinv, nu, A, z)
-                pending.append((e, mj))
+                pending[e] = mj
             else:
                 mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu, A, z)
-        def fetch_draws():
-            for e, mj in pending:
-                mj.mu, mj.Lambda = eng.nw_sample_fetch(e)
-            pending.clear()
-
-        # the draws are needed on the host by update_beta! (this iteration) or else by the next iteration: fetch them as late as possible so
-        # that the last entity's draw overlaps the test-set kernel
-        if any(en.hasFeatures() for en in data.entities):
-            fetch_draws()
+        # update_beta! needs this iteration's (mu, Lambda) of the entities with features on the host
+        for e, en in zip(ents, data.entities):
+            if en.hasFeatures():
+                fetch_draws(e)
         # update_beta! — src/macau.jl:138-140, src/sampling.jl:361-370
         for e, en in zip(ents, data.entities):
             if en.hasFeatures():
@@ -288,7 +292,8 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 sums = host_acc.step(probe_rat, posterior)
             rmse_avg = math.sqrt(sums[0] / sums[3])   # src/macau.jl:196
             err_avg = sums[2] / sums[3]                # :193-194
-        fetch_draws()
+        if say or (callable(f) and posterior) or i == burnin + psamples:
+            fetch_draws()  # the progress line / the callback / the caller read model.mu, model.Lambda
         if posterior:
             if output and lead:
                 # saving latent vectors to disk — src/macau.jl:149-162 (Float32, num_latent × count as Julia holds model.sample)
