@@ -250,3 +250,23 @@ def test_c5_shard_generator_partitions_the_table():
         assert np.array_equal(ids[mine2], np.stack([i1[need2], i2[need2]], 1)) and np.array_equal(vals[mine2], v[need2])
         total += len(vals)
     assert nnz <= total <= 2 * nnz
+
+
+def test_balanced_partition_of_a_large_entity_is_balanced_and_deterministic():
+    """Entities beyond `exact_top` rows (C5: 10M users): exact LPT for the heaviest rows, snake deal of the light tail."""
+    from bdf_b200.shard import balanced_partition
+
+    rng = np.random.default_rng(0)
+    n = 400_000
+    deg = np.bincount(np.minimum((n * rng.random(3_000_000) ** 2.5).astype(np.int64), n - 1), minlength=n)
+    for world in (2, 8):
+        r = balanced_partition(deg, world, 64.0, exact_top=50_000)
+        assert r.shape == (n,) and r.min() == 0 and r.max() == world - 1
+        loads = np.bincount(r, weights=deg + 64.0, minlength=world)
+        assert loads.max() / loads.mean() < 1.001
+        counts = np.bincount(r, minlength=world)
+        assert counts.max() - counts.min() <= 0.02 * n / world
+        assert np.array_equal(r, balanced_partition(deg, world, 64.0, exact_top=50_000))
+    # below the threshold the exact greedy assignment is unchanged
+    small = deg[:5000]
+    assert np.array_equal(balanced_partition(small, 4, 1.0), balanced_partition(small, 4, 1.0, exact_top=10**9))

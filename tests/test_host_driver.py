@@ -91,3 +91,51 @@ def test_macau_feature_branch_on_the_driver():
     eng2 = OracleEngine(3)
     bdf_b200.macau(rd2, num_latent=3, burnin=1, psamples=1, verbose=False, engine=eng2, compute_ff_size=0)
     assert not rd2.entities[0].use_FF and ("ff", 0) not in eng2.calls and ("beta", 0, False) in eng2.calls
+
+
+def test_macau_keyword_contract_follows_the_reference():
+    """src/macau.jl:24-30: output_beta without an output prefix and an unknown output_type are errors raised before any work is done;
+    output_type defaults to "csv"."""
+    import inspect
+
+    import pytest
+
+    rng = np.random.default_rng(2)
+    Y = sp.csc_matrix(np.where(rng.random((12, 9)) < 0.5, rng.standard_normal((12, 9)), 0.0))
+    rd = bdf_b200.RelationData(Y, class_cut=0.0)
+    eng = OracleEngine(2)
+    with pytest.raises(ValueError, match="output_beta"):
+        bdf_b200.macau(rd, num_latent=2, burnin=1, psamples=1, verbose=False, engine=eng, output_beta=True)
+    with pytest.raises(ValueError, match="output_type"):
+        bdf_b200.macau(rd, num_latent=2, burnin=1, psamples=1, verbose=False, engine=eng, output="x", output_type="hdf5")
+    assert eng.calls == []   # both failed before the first sampler call
+    assert inspect.signature(bdf_b200.macau).parameters["output_type"].default == "csv"
+    with pytest.raises(ValueError, match="backend"):
+        bdf_b200.macau(rd, num_latent=2, backend="julia")
+
+
+def test_f_callback_sees_the_live_model_and_rmse_train_is_averaged(tmp_path):
+    """src/macau.jl:186-189: f(data) is called with the current sample after every posterior iteration; :164-178, 222-226: RMSE_train is the
+    RMSE of the posterior MEAN of the training predictions, not of the last sample."""
+    rng = np.random.default_rng(4)
+    N, M, k = 25, 18, 2
+    A, B = rng.standard_normal((N, k)), rng.standard_normal((M, k))
+    Y = sp.csc_matrix(np.where(rng.random((N, M)) < 0.6, A @ B.T + 0.05 * rng.standard_normal((N, M)), 0.0))
+    rd = bdf_b200.RelationData(Y, class_cut=0.0, alpha=5.0)
+    assignToTest(rd.relations[0], 30, rng)
+    eng = OracleEngine(3)
+    seen = []
+
+    def f(data):
+        seen.append(data.entities[0].model.sample.copy())
+        return float(np.linalg.norm(seen[-1]))
+
+    res = bdf_b200.macau(rd, num_latent=3, burnin=4, psamples=6, verbose=False, engine=eng, host_noise=np.random.default_rng(1), f=f, rmse_train=True)
+    assert len(seen) == 6 and len(res["f_output"]) == 6
+    assert all(np.any(seen[i] != seen[i + 1]) for i in range(5))          # a fresh sample every time, not the stale initial zeros
+    assert np.array_equal(seen[-1], rd.entities[0].model.sample)
+    # RMSE_train of the averaged predictions is smaller than that of the last sample alone (averaging removes sampling noise)
+    rel = rd.relations[0]
+    last = eng.predict(0, rel.data.ids)
+    rmse_last = float(np.sqrt(np.mean((rel.data.values - last) ** 2)))
+    assert 0.0 < res["RMSE_train"] < rmse_last
