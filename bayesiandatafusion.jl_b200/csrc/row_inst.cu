@@ -22,7 +22,10 @@ static constexpr int kDP = BDF_DP;
 #ifndef BDF_NW_BIG
 #define BDF_NW_BIG 4
 #endif
-static constexpr int kNW = kDP <= 32 ? 1 : (kDP <= 64 ? 4 : BDF_NW_BIG);
+#ifndef BDF_NW1_MAXDP
+#define BDF_NW1_MAXDP 32  // largest padded D that runs one warp per row
+#endif
+static constexpr int kNW = kDP <= BDF_NW1_MAXDP ? 1 : (kDP <= 64 ? 4 : BDF_NW_BIG);
 
 // 64 < D <= 104, 2-mode relations: the persistent warp-specialised kernel (5 rows in flight per SM instead of 4, row_kernel_ws.cuh) is
 // compiled in and parity-tested, but opt-in (BDF_ROWS_WS=1 at bdf_create): on C2 it measured slower than one CTA per row
