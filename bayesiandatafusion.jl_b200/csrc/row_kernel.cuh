@@ -48,6 +48,9 @@
 #ifndef BDF_GATHER_LDGSTS
 #define BDF_GATHER_LDGSTS 0  // 1: the 4-warp CTAs gather with 16-byte cp.async (LDGSTS) instead of one TMA bulk copy per row (A/B knob)
 #endif
+#ifndef BDF_GATHER_LDGSTS1
+#define BDF_GATHER_LDGSTS1 0  // 1: the one-warp CTAs (D <= 32) gather with cp.async, 16 lanes per row, two rows per instruction
+#endif
 #ifndef BDF_K4_UNROLL4
 #define BDF_K4_UNROLL4 2  // 4-warp CTAs (D > 32): two k-steps per loop trip — the fragment loads of the second overlap the DMMAs of the first (+1 % on C2)
 #endif
@@ -271,7 +274,11 @@ struct RowKernel {
   static constexpr int KS = KS_ > 0 ? KS_ : (NW == 4 ? (DP <= 64 ? BDF_KS4S : BDF_KS4) : (NW == 1 ? BDF_KS1 : OPP * GP));  // observations per stage (16)
   static constexpr int NBUF = NBUF_ > 0 ? NBUF_ : (NW == 1 ? BDF_NBUF1 : (NW == 4 ? BDF_NBUF4 : 3));
   static constexpr int PF = NBUF - 1;                          // stages in flight ahead of the one being consumed
-  static constexpr bool LDGSTS = BDF_GATHER_LDGSTS && NW == 4 && KS == 16;  // gather by cp.async: 8 threads per row, 16 rows per stage
+  // gather by cp.async instead of TMA: TPR threads per partner row, NTHR/TPR rows per pass
+  static constexpr bool LDGSTS = (BDF_GATHER_LDGSTS && NW == 4 && KS == 16) || (BDF_GATHER_LDGSTS1 && NW == 1);
+  static constexpr int TPR = NW == 1 ? 16 : 8;
+  static constexpr int RPP = NTHR / TPR;
+  static_assert(!LDGSTS || KS % RPP == 0, "cp.async gather: a stage is a whole number of passes");
   static constexpr int STG = KS * S * (TENSOR ? 2 : 1) + KS;   // doubles per stage: tile(s) + residuals
   static constexpr int PSZ = 64 * C::NT;  // lower-triangle tiles, 64 doubles each, tile (I,J) at 64·(tri(I)+J)
   static constexpr int REGSZ = PSZ > NBUF * STG ? PSZ : NBUF * STG;  // the tiles alias the (dead) stage ring
@@ -443,32 +450,35 @@ struct RowKernel {
     };
     auto issue = [&](int s) {
       if constexpr (LDGSTS) {
-        // 8 threads per partner row, 16-byte pieces (t%8) + 8j; rows past the end of the item are zero-filled (src-size 0)
+        // TPR threads per partner row, 16-byte pieces (t % TPR) + TPR·j; rows past the end of the item are zero-filled (src-size 0)
         const int b = (int)((gs + (uint32_t)s) % NBUF);
         double* st = ring + b * STG;
         int nvalid = len - s * KS;
         if (nvalid > KS) nvalid = KS;
-        const int row = tid >> 3, q = tid & 7;
-        const bool ok = row < nvalid;
+        const int q = tid % TPR;
         const int mb = (int)((gs + (uint32_t)s) & 1u);
-        const int c0 = mcol[(mb * 2) * KS + row];
-        const double* src0 = rt.P0 + (size_t)c0 * p.ld;
 #pragma unroll 1
-        for (int pc = q; pc < npc; pc += 8) cp_async16(st + row * S + 2 * pc, src0 + 2 * pc, ok ? 16 : 0);
-        if (TENSOR) {
-          const int c1 = rt.col1 ? mcol[(mb * 2 + 1) * KS + row] : 0;
-          const double* src1 = rt.P1 + (size_t)c1 * p.ld;
+        for (int ps = 0; ps < KS / RPP; ps++) {
+          const int row = ps * RPP + tid / TPR;
+          const bool ok = row < nvalid;
+          const int c0 = mcol[(mb * 2) * KS + row];
+          const double* src0 = rt.P0 + (size_t)c0 * p.ld;
 #pragma unroll 1
-          for (int pc = q; pc < npc; pc += 8) cp_async16(st + (KS + row) * S + 2 * pc, src1 + 2 * pc, ok ? 16 : 0);
+          for (int pc = q; pc < npc; pc += TPR) cp_async16(st + row * S + 2 * pc, src0 + 2 * pc, ok ? 16 : 0);
+          if (TENSOR) {
+            const int c1 = rt.col1 ? mcol[(mb * 2 + 1) * KS + row] : 0;
+            const double* src1 = rt.P1 + (size_t)c1 * p.ld;
+#pragma unroll 1
+            for (int pc = q; pc < npc; pc += TPR) cp_async16(st + (KS + row) * S + 2 * pc, src1 + 2 * pc, ok ? 16 : 0);
+          }
+          if (q == 0) {
+            const double r = ok ? mval[mb * KS + row] - rt.mean : 0.0;
+            st[(TENSOR ? 2 : 1) * KS * S + row] = r;
+            if (aug) st[row * S + D] = r;  // the aug column (index D, D even) lies outside the copied pieces
+          }
         }
         cp_async_mbar_arrive_noinc(fullb + b);
         cp_async_commit();  // the gather of a stage is one cp.async group of its own (see the wait in the stage loop)
-        if (q == 0) {
-          const double r = ok ? mval[mb * KS + row] - rt.mean : 0.0;
-          st[(TENSOR ? 2 : 1) * KS * S + row] = r;
-          // the aug column (index D) lies outside the copied pieces only if D is even; a cp.async piece never covers it then
-          if (aug) st[row * S + D] = r;
-        }
         return;
       }
       if (gl) {
