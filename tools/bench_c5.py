@@ -102,6 +102,20 @@ def shard_table_dev(rank, owner1, owner2, n1, n2, nnz, dev):
     return ids, torch.cat(vals).numpy()
 
 
+def nvlink_bytes(index):
+    """Cumulative NVLink data counters of one GPU (nvidia-smi nvlink -gt d): (tx_bytes, rx_bytes) summed over its links, or None."""
+    import re
+    import subprocess
+
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=30).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        return (tx * 1024, rx * 1024) if (tx or rx) else None
+    except Exception:
+        return None
+
+
 def main():
     import time
 
@@ -150,9 +164,12 @@ def main():
 
     ds.sweep(args.warmup)
     barrier()
+    nv0 = nvlink_bytes(local) if rank == 0 else None  # N/A on pools that do not expose the NVLink counters; then the computed figure stands alone
+    barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); ds.sweep(args.steps); b.record()
     barrier()
+    nv1 = nvlink_bytes(local) if rank == 0 else None
     t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
     if args.check:  # N GPUs == 1 GPU: the same number of device-resident sweeps on one handle that holds the whole table
         multi = [eng.get_factors(e1), eng.get_factors(e2)]
@@ -233,6 +250,9 @@ def main():
                 "whole_sweep_frac_of_fp64_dmma_peak": flops / world / (ms / 1e3) / 1e12 / peak,
                 "hbm_in_use_gb_max_over_ranks": float(mem.item()) / 1e9, "observations_registered_per_rank": nloc,
                 "nvlink_bytes_stored_per_rank_per_sweep": int((n1 + n2) / world * ld * 8 * (world - 1)),
+                "nvlink_counters_gpu0_per_sweep": ({"tx_bytes": (nv1[0] - nv0[0]) / args.steps, "rx_bytes": (nv1[1] - nv0[1]) / args.steps,
+                                                    "source": "nvidia-smi nvlink -gt d around the timed sweeps (row-kernel peer stores + the NCCL all-reduces of the statistics)"}
+                                                   if nv0 and nv1 else None),
                 "setup_seconds": t_setup, "partition": "work-balanced (LPT on the 200k heaviest rows, snake deal of the rest)"}
         print(json.dumps(line))
     if world > 1:
