@@ -976,24 +976,57 @@ __global__ void pred_all3_kernel(const double* __restrict__ U1, const double* __
   }
 }
 
+// factor rows in the caller's row order (pitch ld) out of the slot-ordered replica of a sharded / partitioned entity
+__global__ void natural_rows_kernel(const double* __restrict__ U, const int32_t* __restrict__ slot_tab, int world, int64_t nper, int64_t N, int ld,
+                                    double* __restrict__ out) {
+  const int64_t n = N * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / ld;
+    const int64_t sl = slot_tab ? slot_tab[i] : (i % world) * nper + i / world;
+    out[e] = U[(size_t)sl * ld + e % ld];
+  }
+}
+
 extern "C" int bdf_predict_all(bdf_t* h, int rel, double* out) {
   CHECK_H();
   if (rel < 0 || rel >= (int)h->rels.size()) FAIL(BDF_ERR_INVALID, "relation id out of range");
   if (!out) FAIL(BDF_ERR_INVALID, "null argument");
   RelationS& r = h->rels[rel];
-  if (h->world != 1) FAIL(BDF_ERR_INVALID, "pred_all runs on one GPU");
   EntityS& a = h->ents[r.entity_of_mode[0]];
   EntityS& b = h->ents[r.entity_of_mode[1]];
-  if (a.slot_of_row || b.slot_of_row) FAIL(BDF_ERR_INVALID, "pred_all needs the default row order");
   CU(cudaSetDevice(h->device));
+  // every rank holds all factor rows (slot order): with several ranks or an explicit shard map the rows are first put back into the
+  // caller's order in the second arena
+  const double* Un[3] = {a.U, b.U, r.K == 3 ? h->ents[r.entity_of_mode[2]].U : nullptr};
+  {
+    size_t need = 0;
+    for (int m = 0; m < r.K; m++) {
+      const EntityS& e = h->ents[r.entity_of_mode[m]];
+      if (h->world > 1 || e.slot_of_row) need += (size_t)e.N * h->ld;
+    }
+    if (need) {
+      int rcn = bdf_ensure_arena2(h, sizeof(double) * need);
+      if (rcn) return rcn;
+      double* dst = reinterpret_cast<double*>(h->arena2);
+      for (int m = 0; m < r.K; m++) {
+        const EntityS& e = h->ents[r.entity_of_mode[m]];
+        if (h->world > 1 || e.slot_of_row) {
+          natural_rows_kernel<<<grid_for(e.N * h->ld), 256, 0, h->stream>>>(e.U, e.slot_of_row, h->world, e.Nper, e.N, h->ld, dst);
+          h->launches++;
+          Un[m] = dst;
+          dst += (size_t)e.N * h->ld;
+        }
+      }
+      CU(cudaGetLastError());
+    }
+  }
   if (r.K == 3) {  // the reference enumerates every cell (src/sampling.jl:78-89); so does this kernel, one thread per cell
     EntityS& c = h->ents[r.entity_of_mode[2]];
-    if (c.slot_of_row) FAIL(BDF_ERR_INVALID, "pred_all needs the default row order");
     const size_t n3 = (size_t)a.N * b.N * c.N;
     int rc3 = bdf_ensure_arena(h, sizeof(double) * n3);
     if (rc3) return rc3;
     double* Y3 = reinterpret_cast<double*>(h->arena);
-    pred_all3_kernel<<<grid_for((int64_t)n3), 256, 0, h->stream>>>(a.U, b.U, c.U, a.N, b.N, c.N, h->ld, h->D, r.mean, Y3);
+    pred_all3_kernel<<<grid_for((int64_t)n3), 256, 0, h->stream>>>(Un[0], Un[1], Un[2], a.N, b.N, c.N, h->ld, h->D, r.mean, Y3);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, Y3, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
@@ -1007,7 +1040,7 @@ extern "C" int bdf_predict_all(bdf_t* h, int rel, double* out) {
   double* Y = reinterpret_cast<double*>(h->arena);
   const double one = 1.0, zero = 0.0;
   // factor buffers are row-major N × ld = column-major ld × N: Y (N1 × N2, column-major) = U1·U2ᵀ
-  if (cublasDgemm((cublasHandle_t)h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)a.N, (int)b.N, h->D, &one, a.U, h->ld, b.U, h->ld, &zero, Y, (int)a.N) != CUBLAS_STATUS_SUCCESS)
+  if (cublasDgemm((cublasHandle_t)h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)a.N, (int)b.N, h->D, &one, Un[0], h->ld, Un[1], h->ld, &zero, Y, (int)a.N) != CUBLAS_STATUS_SUCCESS)
     FAIL(BDF_ERR_CUDA, "cublasDgemm failed");
   add_scalar_kernel<<<grid_for((int64_t)n), 256, 0, h->stream>>>(Y, (int64_t)n, r.mean);
   h->launches += 2;

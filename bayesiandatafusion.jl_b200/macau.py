@@ -317,7 +317,7 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                 else:
                     train_rat_all = (train_counter * train_rat_all + train_rat) / (train_counter + 1)
                     train_counter += 1
-            if full_prediction:
+            if full_prediction and lead:
                 if rel.hasFeatures():
                     raise ValueError("Prediction of all elements is not possible when Relation has features.")  # src/sampling.jl:93-95
                 yhat_full += eng.predict_all(r_id, tuple(rel.data.dims))  # pred_all — src/macau.jl:145-146

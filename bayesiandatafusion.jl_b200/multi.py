@@ -164,8 +164,8 @@ def macau_multi(data, devices, kw):
     import torch.distributed as dist
 
     world = len(devices)
-    if kw.get("full_prediction") or any(r.hasFeatures() for r in data.relations):
-        raise ValueError("full_prediction and relation-level features run on one GPU (devices=[d]): bdf_predict_all / bdf_set_relation_features")
+    if any(r.hasFeatures() for r in data.relations):
+        raise ValueError("relation-level features run on one GPU (devices=[d]): bdf_set_relation_features")
     if dist.is_available() and dist.is_initialized():
         if dist.get_world_size() != world:
             raise ValueError(f"devices has {world} entries but the process group has {dist.get_world_size()} ranks")

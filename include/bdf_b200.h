@@ -141,7 +141,8 @@ int bdf_sample_alpha(bdf_t* h, int rel, double alpha_lambda0, double alpha_nu0, 
 
 /* pred_all(r) = udot_all(r) + mean_value — src/sampling.jl:72-97, used by macau(full_prediction = true), src/macau.jl:145-146: every cell of a
  * relation, column-major: N1 × N2 for a matrix relation (one cuBLAS dgemm of the two factor matrices), N1 × N2 × N3 for a 3-mode tensor
- * (one thread per cell, like the reference's enumeration :78-89; test/parallel_latent_tensor.jl:33-39). One GPU. */
+ * (one thread per cell, like the reference's enumeration :78-89; test/parallel_latent_tensor.jl:33-39). With several ranks every rank holds
+ * all factor rows, so any rank can call it (no collective); sharded / partitioned entities are put back into row order first. */
 int bdf_predict_all(bdf_t* h, int rel, double* out);
 
 /* ---- relation-level features (Relation.F: one feature row per training observation) — src/macau.jl:89-92, src/sampling.jl:322-337 ---- */

@@ -198,3 +198,26 @@ def test_pred_all_full_prediction_and_output_dumps(tmp_path):
     assert S.shape == (4, N) and np.allclose(S.T, rd.entities[0].model.sample, rtol=1e-6, atol=1e-6)
     B = dr.read_binary_float32(f"{out}-E1-4.beta.binary")
     assert B.shape == (9, 4) and np.allclose(B, rd.entities[0].model.beta, rtol=1e-6, atol=1e-6)
+
+
+def test_pred_all_with_an_explicit_shard_map_and_emulated_ranks():
+    """pred_all (src/sampling.jl:72-97) reads the factor rows back in the caller's order when the entity was created with an explicit shard map
+    or the handle is one rank of several (every rank holds all rows, in slot order)."""
+    import bdf_b200
+
+    rng = np.random.default_rng(6)
+    N, M, D = 37, 23, 12
+    U, V = rng.standard_normal((N, D)), rng.standard_normal((M, D))
+    ids = np.stack([rng.integers(1, N + 1, 300), rng.integers(1, M + 1, 300)], 1)
+    vals = rng.standard_normal(300)
+    want = U @ V.T + 0.4
+    for rank, world in ((0, 1), (1, 3)):
+        eng = bdf_b200.Engine(D, rank=rank, world=world)
+        e1 = eng.add_entity_partitioned(N, rng.integers(0, world, N).astype(np.int32))
+        e2 = eng.add_entity(M)
+        rel = eng.add_relation([e1, e2], ids, vals)
+        eng.set_relation_params(rel, 1.0, 0.4)
+        eng.set_factors(e1, U)
+        eng.set_factors(e2, V)
+        assert rel_err(eng.predict_all(rel, (N, M)), want) <= 1e-13
+        eng.close()

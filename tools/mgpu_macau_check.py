@@ -34,7 +34,7 @@ def problem(with_features):
 
 for feat in (False, True):
     for D in (16, 100):
-        kw = dict(num_latent=D, burnin=6, psamples=6, verbose=False, seed=11, clamp=[-6.0, 6.0], compute_ff_size=0)
+        kw = dict(num_latent=D, burnin=6, psamples=6, verbose=False, seed=11, clamp=[-6.0, 6.0], compute_ff_size=0, full_prediction=(D == 16))
         multi = bdf_b200.macau(problem(feat), devices=list(range(world)), **kw)
         dist.barrier()
         if rank == 0:
@@ -46,6 +46,8 @@ for feat in (False, True):
             # (mu, Lambda) that 12 Gibbs sweeps carry along but do not blow up
             assert d_rmse < 1e-6 and d_pred < 1e-4, (d_rmse, d_pred)
             assert abs(multi["ROC"] - single["ROC"]) < 1e-6 and abs(multi["accuracy"] - single["accuracy"]) < 1e-3
+            if "predictions_full" in single:   # pred_all from the slot-ordered replicas of a sharded run
+                assert float(np.max(np.abs(multi["predictions_full"] - single["predictions_full"]))) < 1e-4
         dist.barrier()
 if rank == 0:
     print("MGPU MACAU OK")
