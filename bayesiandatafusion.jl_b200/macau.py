@@ -328,6 +328,8 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
                     refresh_host_model()  # f(data) sees the live sample / beta, as in src/macau.jl:186-189
                     stale = False
                 f_output.append(f(data))
+        if comm is not None:
+            comm.fence()  # the other ranks must not start storing the next iteration's rows into replicas rank 0 is still reading
         time1 = time.time()
         iter_seconds.append(time1 - time0)
         if ntest and (verbose or i == burnin + psamples):

@@ -119,6 +119,14 @@ class Comm:
             full[r::self.world] = out[r, :cnt]
         return full
 
+    def fence(self):
+        """Stream-ordered rendezvous without a host sync: no rank's next kernel starts before every rank has finished what it enqueued so
+        far. Needed at the end of an iteration: rank 0 may still be READING the factor replicas (pred_all, sample dumps, RMSE_train, the
+        refresh before f(data)) while the other ranks would already store the next iteration's rows into them."""
+        if not hasattr(self, "_fence"):
+            self._fence = self.torch.zeros(1, device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(self._fence)
+
     def barrier(self):
         self.dist.barrier()
         self.torch.cuda.synchronize()
