@@ -2,21 +2,26 @@
 // sample_latent_all2!/sample_latent_range, :149-198) as one fused sm_100a kernel.
 //
 // One CTA (NW warps) owns one work item = (row, chunk of that row's observations):
-//   1. gather the partner factor rows of the chunk into a 3-deep ring of shared-memory stages with cp.async
-//      (LDGSTS, 16 B per thread, zero-fill past the row end), KS observations per stage, two stages in flight, one
-//      barrier per stage; for 3-mode tensors both partners are staged and multiplied while forming the fragments;
+//   1. gather the partner factor rows of the chunk into a ring of shared-memory stages (2 × 28 observations for the 4-warp CTAs, 2 × 24 for
+//      the one-warp CTAs) with TMA 1-D bulk copies — one cp.async.bulk (UBLKCP) per partner row, completion counted in bytes on the
+//      stage's mbarrier; the partner slots / values of a stage are fetched one stage ahead with cp.async into a small shared-memory
+//      table; one barrier per stage; for 3-mode tensors both partners are staged and multiplied while forming the fragments;
 //   2. accumulate the lower triangle of G = Σ v vᵀ with FP64 tensor-core MMAs (DMMA.8x8x4, mma.sync m8n8k4 f64),
 //      8×8 tiles dealt to the warps at compile time (tiles.cuh); the rhs Σ v·r rides along as one more column
 //      of the tile when D is even and not a multiple of 8 ("aug"), else it is a DFMA side-sum;
 //   3. rows split over several CTAs park their partial in a workspace; the last CTA to arrive adds the partials
-//      in chunk order (deterministic);
-//   4. the Gram tiles are parked in shared memory (row-major 8×8 blocks), Λ* = Λ + αG is formed there and factored
+//      in chunk order, in two levels for rows with many chunks (deterministic);
+//   4. the Gram tiles are parked in shared memory (8×8 blocks in a swizzled layout that makes both the accumulator-layout writes and
+//      the transposed fragment reads conflict-free), Λ* = Λ + αG is formed there and factored
 //      as Λ* = W·Wᵀ with W UPPER triangular ("UL" Cholesky, block rows eliminated from the last to the first): per
-//      8-row panel warp 0 factors the 8×8 diagonal block with shuffles (carrying its inverse), the panel tiles are
-//      scaled by one DMMA pair each, the trailing update is a DMMA syrk with the sign flipped, and warp 0 factors
+//      8-row panel one warp factors the 8×8 diagonal block with shuffles (its inverse then replaces the diagonal tile), the panel
+//      tiles are scaled by one DMMA pair each, the trailing update is a DMMA syrk with the sign flipped, and the diagonal warp factors
 //      the next diagonal block while the other warps finish the update (look-ahead); y = W⁻¹·rhs rides along;
-//   5. warp 0 runs the forward substitution and stores the draw x = W⁻ᵀ(z + W⁻¹·rhs) — algebraically identical,
-//      for the same z, to the reference's chol(inv(Λ*))ᵀ·z + inv(Λ*)·rhs (DESIGN.md §"draw formula").
+//   5. one warp runs the forward substitution and stores the draw x = W⁻ᵀ(z + W⁻¹·rhs) — algebraically identical,
+//      for the same z, to the reference's chol(inv(Λ*))ᵀ·z + inv(Λ*)·rhs (DESIGN.md §"draw formula") — into its own replica and,
+//      with several GPUs, into every peer's (fused all-gather).
+// The body is four pieces (syrk_item, split_reduce, park_tiles, factor_and_draw) parameterised on the group-wide barrier; the opt-in
+// persistent warp-specialised kernel of row_kernel_ws.cuh is built from the same pieces.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
