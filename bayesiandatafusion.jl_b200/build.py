@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
                     print(log)
     objs = [os.path.join(OBJ, "engine.o"), os.path.join(OBJ, "features.o"), os.path.join(OBJ, "predict.o")] + [os.path.join(OBJ, f"row_inst_{dp}.o") for dp in DPS]
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
-           "-lcublas", "-lcusolver", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]  # dense features / FF direct solve (A9) are library calls
+           "-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]  # dense feature products (FᵀF, F·β, UᵀV) are plain library dgemm calls
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed: {r.stdout}\n{r.stderr}")

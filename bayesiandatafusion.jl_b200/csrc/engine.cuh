@@ -152,8 +152,7 @@ struct bdf_handle {
   double* ones = nullptr;  // a row of ones (ld doubles, zero padding): the second partner of a 2-mode relation inside a 3-mode launch
   int num_sms = 148;
   double* lt = nullptr;  // Λ in tile order + Λ·μ, rebuilt per half-sweep
-  void* cublas = nullptr;    // cublasHandle_t / cusolverDnHandle_t of the dense-feature and FF direct-solve paths (created on first use)
-  void* cusolver = nullptr;
+  void* cublas = nullptr;    // cublasHandle_t of the dense-feature products (plain dgemm / dgemv; created on first use)
   char* arena = nullptr;  // grow-only staging for host-facing calls (predict ids/slots/output, beta sampler temporaries)
   size_t arena_bytes = 0;
   char* arena2 = nullptr;  // second grow-only region: solver work space that must coexist with arena-resident operands

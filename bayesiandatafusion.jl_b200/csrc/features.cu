@@ -10,7 +10,6 @@
 // order), one warp per output row, indices read 128 bits at a time, the D columns spread over the lanes.
 #include <cub/cub.cuh>
 #include <cublas_v2.h>
-#include <cusolverDn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -19,6 +18,7 @@
 
 #include "../../include/bdf_b200.h"
 #include "engine.cuh"
+#include "dense_spd.cuh"
 #include "nw_device.cuh"
 #include "row_kernel.cuh"
 
@@ -590,13 +590,7 @@ int dense_handles(bdf_t* h) {
     if (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cublasCreate failed");
     h->cublas = cb;
   }
-  if (!h->cusolver) {
-    cusolverDnHandle_t cs = nullptr;
-    if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnCreate failed");
-    h->cusolver = cs;
-  }
   cublasSetStream((cublasHandle_t)h->cublas, h->stream);
-  cusolverDnSetStream((cusolverDnHandle_t)h->cusolver, h->stream);
   return BDF_OK;
 }
 
@@ -885,8 +879,7 @@ static int set_features_dev(bdf_t* h, int entity, int64_t m, int64_t n, int64_t 
 
 void bdf_dense_teardown(bdf_t* h) {
   if (h->cublas) cublasDestroy((cublasHandle_t)h->cublas);
-  if (h->cusolver) cusolverDnDestroy((cusolverDnHandle_t)h->cusolver);
-  h->cublas = h->cusolver = nullptr;
+  h->cublas = nullptr;
 }
 
 // FF = full(At_mul_B(F, F)) (src/RelationData.jl:337-339). Sparse F: num_latent columns of the identity at a time through the two
@@ -922,38 +915,34 @@ static int compute_ff_dev(bdf_t* h, EntityS& e) {
 }
 
 // solve_full(FF, rhs, lambda) — src/sampling.jl:314-320: (FF + λI) \ rhs for num_latent right-hand sides; B and X row-major numF × ld.
-// The regularised matrix is symmetric positive definite, so the factorisation is a Cholesky (cuSOLVER potrf/potrs).
+// The regularised matrix is symmetric positive definite: blocked Cholesky + substitutions of dense_spd.cuh, in place on X.
+__global__ void copy_rows_zero_pad_kernel(const double* __restrict__ B, int64_t rows, int ncol, int ld, double* __restrict__ X) {
+  const int64_t n = rows * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) X[e] = (int)(e % ld) < ncol ? B[e] : 0.0;
+}
+
 static int solve_full_dev(bdf_t* h, EntityS& e, const double* B, double* X, double lambda) {
-  int rc = dense_handles(h);
-  if (rc) return rc;
+  int rc;
   if (!e.FF) FAIL(BDF_ERR_STATE, "FF has not been computed (bdf_compute_ff)");
-  cusolverDnHandle_t cs = (cusolverDnHandle_t)h->cusolver;
-  const int n = (int)e.numF, D = h->D;
-  int lwork = 0;
-  if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, n, e.FF, n, &lwork) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
-  // work space from the handle's second grow-only arena (the first one holds the caller's B / X): no cudaMalloc per draw
-  const size_t nA = ((size_t)n * n + 31) / 32 * 32, nB = ((size_t)n * D + 31) / 32 * 32, nW = ((size_t)std::max(lwork, 1) + 31) / 32 * 32;
-  if ((rc = bdf_ensure_arena2(h, sizeof(double) * (nA + nB + nW + 32)))) return rc;
+  if (B == X) FAIL(BDF_ERR_INVALID, "solve_full: the right-hand sides and the solution must not alias");
+  const int64_t n = e.numF;
+  const int D = h->D;
+  // the factor lives in the handle's second grow-only arena (the first one holds the caller's B / X): no cudaMalloc per draw
+  const size_t nA = ((size_t)n * n + 31) / 32 * 32;
+  if ((rc = bdf_ensure_arena2(h, sizeof(double) * (nA + 32)))) return rc;
   double* A = reinterpret_cast<double*>(h->arena2);
-  double* Bc = A + nA;
-  double* work = Bc + nB;
-  int* info = reinterpret_cast<int*>(work + nW);
-  auto cleanup = [&]() {};
+  int* info = reinterpret_cast<int*>(A + nA);
   cudaMemcpyAsync(A, e.FF, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, h->stream);
+  cudaMemsetAsync(info, 0, sizeof(int), h->stream);
   add_diag_kernel<<<grid_for(n), 256, 0, h->stream>>>(A, n, lambda);
-  to_colmajor_kernel<<<grid_for((int64_t)n * D), 256, 0, h->stream>>>(B, n, D, h->ld, Bc);
-  int hinfo[2] = {0, 0};
-  cusolverStatus_t s1 = cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, n, A, n, work, lwork, info);
-  cudaMemcpyAsync(&hinfo[0], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-  cusolverStatus_t s2 = cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, n, D, A, n, Bc, n, info);
-  cudaMemcpyAsync(&hinfo[1], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-  to_rowmajor_kernel<<<grid_for((int64_t)n * h->ld), 256, 0, h->stream>>>(Bc, n, D, h->ld, X);
-  h->launches += 5;
+  copy_rows_zero_pad_kernel<<<grid_for(n * h->ld), 256, 0, h->stream>>>(B, n, D, h->ld, X);
+  h->launches += 2 + spd::solve(h->stream, A, n, X, h->ld, D, info);
+  int hinfo = 0;
+  cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaError_t ce = cudaStreamSynchronize(h->stream);
-  cleanup();
+  if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
-  if (s1 != CUSOLVER_STATUS_SUCCESS || s2 != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cuSOLVER potrf/potrs failed");
-  if (hinfo[0] != 0 || hinfo[1] != 0) FAIL(BDF_ERR_NUMERIC, "solve_full: FF + lambda*I is not positive definite");
+  if (hinfo != 0) FAIL(BDF_ERR_NUMERIC, "solve_full: FF + lambda*I is not positive definite");
   return BDF_OK;
 }
 
@@ -1135,21 +1124,17 @@ extern "C" int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const 
   int rc = dense_handles(h);
   if (rc) return rc;
   cublasHandle_t cb = (cublasHandle_t)h->cublas;
-  cusolverDnHandle_t cs = (cusolverDnHandle_t)h->cusolver;
   const int nF = (int)r.nF;
   const int64_t nnz = r.nnz;
-  int lwork = 0;
   // temporaries from the handle's second grow-only arena: no cudaMalloc per draw
-  if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, nF, r.FF, nF, &lwork) != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
   auto up32 = [](size_t x) { return (x + 31) / 32 * 32; };
-  const size_t nK = up32((size_t)nF * nF), nR = up32((size_t)nF), nW = up32((size_t)std::max(lwork, 1)), nZ1 = z1 ? up32((size_t)std::max<int64_t>(nnz, 1)) : 0, nZ2 = z2 ? nR : 0;
-  if ((rc = bdf_ensure_arena2(h, sizeof(double) * (nK + nR + nW + nZ1 + nZ2 + 32)))) return rc;
+  const size_t nK = up32((size_t)nF * nF), nR = up32((size_t)nF), nZ1 = z1 ? up32((size_t)std::max<int64_t>(nnz, 1)) : 0, nZ2 = z2 ? nR : 0;
+  if ((rc = bdf_ensure_arena2(h, sizeof(double) * (nK + nR + nZ1 + nZ2 + 32)))) return rc;
   double* K = reinterpret_cast<double*>(h->arena2);
   double* rhs = K + nK;
-  double* work = rhs + nR;
-  double* dz1 = z1 ? work + nW : nullptr;
-  double* dz2 = z2 ? work + nW + nZ1 : nullptr;
-  int* info = reinterpret_cast<int*>(work + nW + nZ1 + nZ2);
+  double* dz1 = z1 ? rhs + nR : nullptr;
+  double* dz2 = z2 ? rhs + nR + nZ1 : nullptr;
+  int* info = reinterpret_cast<int*>(rhs + nR + nZ1 + nZ2);
   auto cleanup = [&]() {};
   if (z1) cudaMemcpyAsync(dz1, z1, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->stream);
   if (z2) cudaMemcpyAsync(dz2, z2, sizeof(double) * nF, cudaMemcpyHostToDevice, h->stream);
@@ -1161,21 +1146,21 @@ extern "C" int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const 
   if (nnz == 0) cudaMemsetAsync(rhs, 0, sizeof(double) * nF, h->stream);
   relfeat_rhs_kernel<<<grid_for(nF), 256, 0, h->stream>>>(rhs, dz2, nF, r.alpha, sqrt(lambda_beta), h->seed, h->sweep, st + 1);
   relfeat_k_kernel<<<grid_for((int64_t)nF * nF), 256, 0, h->stream>>>(r.FF, nF, r.alpha, lambda_beta, K);
-  int hinfo[2] = {0, 0};
-  cusolverStatus_t s1 = cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, nF, K, nF, work, lwork, info);
-  cudaMemcpyAsync(&hinfo[0], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-  cusolverStatus_t s2 = cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, nF, 1, K, nF, rhs, nF, info);
-  cudaMemcpyAsync(&hinfo[1], info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  // (alpha·FF + lambda_beta·I) \ rhs: one right-hand side, pitch 1 (dense_spd.cuh)
+  int hinfo = 0;
+  cudaMemsetAsync(info, 0, sizeof(int), h->stream);
+  h->launches += spd::solve(h->stream, K, (int64_t)nF, rhs, 1, 1, info);
+  cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaMemcpyAsync(r.beta, rhs, sizeof(double) * nF, cudaMemcpyDeviceToDevice, h->stream);
-  h->launches += 7;
+  h->launches += 5;
   rc = bdf_refresh_relation_offsets(h, rel);
   if (!rc && beta_out) cudaMemcpyAsync(beta_out, r.beta, sizeof(double) * nF, cudaMemcpyDeviceToHost, h->stream);
   cudaError_t ce = cudaStreamSynchronize(h->stream);
   cleanup();
   if (rc) return rc;
   if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
-  if (s0 != CUBLAS_STATUS_SUCCESS || s1 != CUSOLVER_STATUS_SUCCESS || s2 != CUSOLVER_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cuBLAS/cuSOLVER call failed");
-  if (hinfo[0] != 0 || hinfo[1] != 0) FAIL(BDF_ERR_NUMERIC, "sample_beta_rel: alpha*FF + lambda*I is not positive definite");
+  if (s0 != CUBLAS_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cublasDgemv failed");
+  if (hinfo != 0) FAIL(BDF_ERR_NUMERIC, "sample_beta_rel: alpha*FF + lambda*I is not positive definite");
   return BDF_OK;
 }
 

@@ -151,8 +151,8 @@ int bdf_predict_all(bdf_t* h, int rel, double* out);
  * the per-observation offset linear_values[i] in place of mean_value (src/sampling.jl:273, :17-19). One GPU. */
 int bdf_set_relation_features(bdf_t* h, int rel, int64_t nnz, int64_t nF, const double* F);
 /* r.model.beta = sample_beta_rel(r); r.temp.linear_values = mean_value + F*beta. z1 (nnz) and z2 (nF) are the injected standard normals
- * behind randn(N) and randn(F) (consumed in that order), NULL = Philox. K = alpha*FF + lambda*I is SPD: Cholesky (cuSOLVER) for the
- * reference's `\`. beta_out (nF) may be NULL. */
+ * behind randn(N) and randn(F) (consumed in that order), NULL = Philox. K = alpha*FF + lambda*I is SPD: blocked Cholesky
+ * (csrc/dense_spd.cuh) for the reference's `\`. beta_out (nF) may be NULL. */
 int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const double* z1, const double* z2, double* beta_out);
 int bdf_get_relation_beta(bdf_t* h, int rel, double* beta);
 int bdf_set_relation_beta(bdf_t* h, int rel, const double* beta);
@@ -215,7 +215,7 @@ int bdf_compute_ff(bdf_t* h, int entity, double* FF_out);
 /* en.use_FF — switch between the direct solve and CG (the FF matrix stays resident). */
 int bdf_set_use_ff(bdf_t* h, int entity, int use_ff);
 /* solve_full(FF, rhs, lambda) — src/sampling.jl:314-320: (FF + lambda·I) \ rhs, rhs and x n × ncol column-major, ncol == num_latent.
- * The regularised matrix is symmetric positive definite; the device factorisation is a Cholesky (cuSOLVER potrf/potrs). */
+ * The regularised matrix is symmetric positive definite; the device factorisation is a blocked Cholesky (csrc/dense_spd.cuh). */
 int bdf_solve_full(bdf_t* h, int entity, const double* rhs, int ncol, double lambda, double* x);
 /* Parity hook: the device CSR in the reference's representation — row_ptr (m+1, or n+1 for the transpose) and col_ind
  * (nnz), Int32, 1-based (fields of SparseBinMatrixCSR, src/sparsebin_csr.jl:6-11). */
