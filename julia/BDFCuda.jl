@@ -104,6 +104,15 @@ function sample_beta!(h::Handle, entity, mu::Vector{Float64}, Lambda::Matrix{Flo
   return beta, rhs
 end
 
+## the same draw with beta left on the device (get_beta! fetches it when the host wants it): nothing comes back per iteration
+function sample_beta_device!(h::Handle, entity, mu::Vector{Float64}, Lambda::Matrix{Float64}, lambda_beta, tol; E1 = C_NULL, E2 = C_NULL)
+  iters = zeros(Cint, length(mu))
+  check(h, ccall((:bdf_sample_beta, LIB), Cint,
+                 (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                 h.ptr, entity, mu, Lambda, lambda_beta, tol, E1, E2, C_NULL, C_NULL, iters))
+  return iters
+end
+
 function sample_lambda_beta(h::Handle, entity, Lambda::Matrix{Float64}, nu, mu; gamma_variate = NaN)
   out = Ref{Cdouble}(0.0)
   check(h, ccall((:bdf_sample_lambda_beta, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
@@ -133,13 +142,22 @@ function solve_full(h::Handle, entity, rhs::Matrix{Float64}, lambda)
   return x
 end
 
-## sample_alpha — src/macau.jl:84-88: err'err on the device, then the 1x1 Wishart draw (chi2 = injected variate or NaN for Philox)
-function sample_alpha!(h::Handle, rel, alpha_lambda0, alpha_nu0; chi2 = NaN)
-  sse = Ref{Cdouble}(0.0); n = Ref{Int64}(0); alpha = Ref{Cdouble}(0.0)
+## sample_alpha — src/macau.jl:84-88: err'err over this handle's training observations on the device (with several ranks: add the ranks'
+## (sse, n) up first), then the 1x1 Wishart draw (chi2 = injected variate or NaN for Philox); the relation's alpha is updated on the device
+function train_sse(h::Handle, rel)
+  sse = Ref{Cdouble}(0.0); n = Ref{Int64}(0)
   check(h, ccall((:bdf_train_sse, LIB), Cint, (Ptr{Void}, Cint, Ptr{Cdouble}, Ptr{Int64}), h.ptr, rel, sse, n))
+  return sse[], Float64(n[])
+end
+function sample_alpha(h::Handle, rel, alpha_lambda0, alpha_nu0, sse, n; chi2 = NaN)
+  alpha = Ref{Cdouble}(0.0)
   check(h, ccall((:bdf_sample_alpha, LIB), Cint, (Ptr{Void}, Cint, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}),
-                 h.ptr, rel, alpha_lambda0, alpha_nu0, sse[], Float64(n[]), chi2, alpha))
+                 h.ptr, rel, alpha_lambda0, alpha_nu0, sse, n, chi2, alpha))
   return alpha[]
+end
+function sample_alpha!(h::Handle, rel, alpha_lambda0, alpha_nu0; chi2 = NaN)
+  sse, n = train_sse(h, rel)
+  return sample_alpha(h, rel, alpha_lambda0, alpha_nu0, sse, n, chi2 = chi2)
 end
 
 ## an entity with an explicit (e.g. work-balanced) shard map instead of the cyclic i:Nprocs:N deal; rank_of_row is 0-based
@@ -238,13 +256,17 @@ function set_test(h::Handle, rel, ids::Matrix{Int64}, values::Vector{Float64}, c
                  h.ptr, rel, size(ids, 1), ids, values, test_F, class_cut))
 end
 test_reset(h::Handle, rel) = check(h, ccall((:bdf_test_reset, LIB), Cint, (Ptr{Void}, Cint), h.ptr, rel))
-## one iteration of the test-set bookkeeping; returns (rmse_avg, rmse, err_avg, counter_prob). clamp = Float64[] -> not clamped
-function predict_accumulate(h::Handle, rel, posterior::Bool, clamp::Vector{Float64})
+## one iteration of the test-set bookkeeping. clamp = Float64[] -> not clamped. The raw sums of THIS handle's test entries:
+## [sum sq. error of the running average, sum sq. error of this sample, number of correctly classified, ntest, posterior samples so far]
+function predict_accumulate_sums(h::Handle, rel, posterior::Bool, clamp::Vector{Float64})
   out = zeros(5)
   lo, hi = isempty(clamp) ? (NaN, NaN) : (clamp[1], clamp[2])
   check(h, ccall((:bdf_predict_accumulate, LIB), Cint, (Ptr{Void}, Cint, Cint, Cdouble, Cdouble, Ptr{Cdouble}), h.ptr, rel, posterior ? 1 : 0, lo, hi, out))
-  return sqrt(out[1] / out[4]), sqrt(out[2] / out[4]), out[3] / out[4], round(Int, out[5])
+  return out
 end
+## (rmse_avg, rmse, err_avg, counter_prob) of src/macau.jl:164-200 from those sums (with several ranks: from the sums added over the ranks)
+test_metrics(out::Vector{Float64}) = (sqrt(out[1] / out[4]), sqrt(out[2] / out[4]), out[3] / out[4], round(Int, out[5]))
+predict_accumulate(h::Handle, rel, posterior::Bool, clamp::Vector{Float64}) = test_metrics(predict_accumulate_sums(h, rel, posterior, clamp))
 ## probe_rat_all (unclamped), probe_stdev (sum of squares), probe_rat
 function get_test_predictions(h::Handle, rel, ntest::Int)
   avg = zeros(ntest); sq = zeros(ntest); last = zeros(ntest)

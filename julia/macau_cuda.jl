@@ -18,6 +18,7 @@ function macau_cuda(data::RelationData;
                             seed = seed, inject_noise = inject_noise)
   end
   reset_model && reset!(data, num_latent, lambda_beta = lambda_beta, compute_ff_size = compute_ff_size)
+  inject_noise && world > 1 && srand(seed)               # host-drawn variates must be the same on every rank (the Philox ones are by construction)
   D   = num_latent
   h   = BDFCuda.create(D, device = device, rank = rank, world = world)
   BDFCuda.set_seed(h, seed)
@@ -63,7 +64,11 @@ function macau_cuda(data::RelationData;
     # sample relation model (alpha, relation-level beta) — src/macau.jl:84-93
     for (k, r) in enumerate(data.relations)
       if r.model.alpha_sample
-        r.model.alpha = BDFCuda.sample_alpha!(h, rid[k], r.model.alpha_lambda0, r.model.alpha_nu0)
+        sse, n = BDFCuda.train_sse(h, rid[k])
+        if peers != nothing
+          sse, n = peers.allreduce((sse, n))                 # every rank holds the observations of the rows it owns
+        end
+        r.model.alpha = BDFCuda.sample_alpha(h, rid[k], r.model.alpha_lambda0, r.model.alpha_nu0, sse, n)
       end
       if hasFeatures(r)
         r.model.beta = BDFCuda.sample_beta_rel!(h, rid[k], r.model.lambda_beta, size(r.F, 2))   # also refreshes linear_values
@@ -86,8 +91,8 @@ function macau_cuda(data::RelationData;
         BDFCuda.sample_mode!(h, e, mj.mu, mj.Lambda)        # one relation or several: the engine sums them per row
         N, NU, NS = BDFCuda.nw_stats(h, e, D)
       end
-      if peers != nothing                                    # several GPUs: add the ranks' statistics up (master/worker remotecalls)
-        N, NU, NS = peers.allreduce_stats(N, NU, NS)
+      if peers != nothing                                    # several GPUs: add the ranks' statistics up (master/worker mailboxes)
+        N, NU, NS = peers.allreduce((N, NU, NS))
         BDFCuda.set_nw_stats(h, e, N, NU, NS)
       end
       if inject_noise
@@ -109,7 +114,13 @@ function macau_cuda(data::RelationData;
     for en in data.entities
       hasFeatures(en) || continue
       e = ent[en]; mj = en.model
-      mj.beta, rhs = BDFCuda.sample_beta!(h, e, mj.mu, mj.Lambda, en.lambda_beta, tol, size(en.F, 2))
+      BDFCuda.sample_beta_device!(h, e, mj.mu, mj.Lambda, en.lambda_beta, tol)   # beta stays on the device until the end of the run
+      if peers != nothing
+        # column-split solve: every rank has stored its columns of beta into all replicas once its stream has drained; nobody reads beta
+        # (lambda_beta below, uhat in the next iteration) before every rank has got there
+        BDFCuda.synchronize(h)
+        peers.allreduce(Float64[0.0])
+      end
       if en.lambda_beta_sample
         en.lambda_beta = BDFCuda.sample_lambda_beta(h, e, mj.Lambda, en.nu, en.mu)
       end
@@ -117,8 +128,17 @@ function macau_cuda(data::RelationData;
     BDFCuda.advance_sweep(h)
 
     if numTest(rel) > 0
-      rmse_avg, rmse, err_avg, counter_prob = BDFCuda.predict_accumulate(h, rid[1], i > burnin, clamp)   # 40 bytes come back per iteration
+      sums = BDFCuda.predict_accumulate_sums(h, rid[1], i > burnin, clamp)      # 40 bytes come back per iteration
+      if peers != nothing                                   # every rank holds the sums of its share of the test set
+        sums[1:4] = peers.allreduce(sums[1:4])
+      end
+      rmse_avg, rmse, err_avg, counter_prob = BDFCuda.test_metrics(sums)
       verbose && rank == 0 && @printf("%3d: RMSE=%6.4f\n", i, rmse_avg)
+    elseif peers != nothing
+      # end-of-iteration rendezvous: no rank may start storing the next iteration's rows into a peer's replica while that peer still reads
+      # it (the exchange above is that rendezvous when there is a test set)
+      BDFCuda.synchronize(h)
+      peers.allreduce(Float64[0.0])
     end
   end
 
@@ -130,8 +150,16 @@ function macau_cuda(data::RelationData;
   result["num_latent"] = num_latent; result["burnin"] = burnin; result["psamples"] = psamples
   if numTest(rel) > 0
     probe_rat_all, probe_stdev, _ = BDFCuda.get_test_predictions(h, rid[1], length(mine))
+    if peers != nothing                                     # put the ranks' shares (rank+1 : world : ntest) back into test-set order
+      shares = peers.allgather((probe_rat_all, probe_stdev))
+      probe_rat_all = zeros(numTest(rel)); probe_stdev = zeros(numTest(rel))
+      for q in 1:world
+        probe_rat_all[q:world:end] = shares[q][1]
+        probe_stdev[q:world:end]   = shares[q][2]
+      end
+    end
     result["RMSE"] = rmse_avg; result["accuracy"] = err_avg
-    world == 1 && (result["ROC"] = AUC_ROC(rel.test_label, -vec(probe_rat_all)))
+    result["ROC"] = AUC_ROC(rel.test_label, -vec(probe_rat_all))
     result["probe_rat_all"] = probe_rat_all; result["probe_stdev"] = probe_stdev
   end
   return result
@@ -141,40 +169,61 @@ end
 # ---- several GPUs: one worker process per device, like the reference's latent_pids workers (src/macau.jl:44-66). Every worker runs
 # macau_cuda on its own handle (rank r of `world`) and owns the rows the library deals to it; drawn rows are stored straight into every peer's
 # replica by the row kernel once the 64-byte IPC handles have been exchanged (`connect`), the (N, NU, NS) statistics are added up through
-# the master (`allreduce_stats`; a CUDA-aware MPI or NCCL binding on BDFCuda.stats_dev does the same without the host hop).
+# mailboxes on the master (`allreduce`; a CUDA-aware MPI or NCCL binding on BDFCuda.stats_dev does the same without the host hop).
 type Peers
   rank::Int
   world::Int
-  connect::Function          # (h, ent) -> exchanges ipc_export / ipc_import(_beta) with the other ranks
-  allreduce_stats::Function  # (N, NU, NS) -> sums over ranks
+  connect::Function    # (h, ent) -> exchanges ipc_export / ipc_import(_beta) with the other ranks
+  allgather::Function  # payload -> the payloads of all ranks, indexed by rank + 1
+  allreduce::Function  # a number, an array or a tuple of those -> the sum over the ranks, added in rank order (identical on every rank)
 end
+
+addup(a::Tuple, b::Tuple) = map(addup, a, b)
+addup(a, b) = a + b
 
 function macau_cuda_multi(data::RelationData, devices::Vector{Int}; kw...)
   world = length(devices)
   length(workers()) >= world - 1 || error("devices = $devices needs $(world - 1) worker processes (addprocs)")
   pids  = vcat(myid(), workers()[1:world-1])
-  # rendezvous through RemoteChannels owned by the master: one mailbox per rank for the handle exchange, one per rank for the reductions
-  boxes = [RemoteChannel(() -> Channel{Any}(4 * world)) for r in 1:world]
+  # rendezvous through RemoteChannels owned by the master: one mailbox per rank
+  boxes = [RemoteChannel(() -> Channel{Any}(8 * world)) for r in 1:world]
   function peers_for(r)
+    seq = [0]; stash = Any[]
+    # all-to-all exchange of one payload per rank. Messages carry a sequence number: a fast rank may already post exchange k+1 while this
+    # rank still collects exchange k. Nobody leaves exchange k before every rank has entered it, so it is also a barrier.
+    allgather = payload -> begin
+      seq[1] += 1
+      for q in 1:world; q == r || put!(boxes[q], (seq[1], r, payload)); end
+      parts = Array(Any, world); parts[r] = payload
+      missing = world - 1
+      early = Any[]
+      for m in stash
+        if m[1] == seq[1]; parts[m[2]] = m[3]; missing -= 1; else push!(early, m); end
+      end
+      empty!(stash); append!(stash, early)
+      while missing > 0
+        m = take!(boxes[r])
+        if m[1] == seq[1]; parts[m[2]] = m[3]; missing -= 1; else push!(stash, m); end
+      end
+      parts
+    end
+    # summed in rank order on every rank: all ranks must end up with bit-identical statistics, or their hyper-parameter draws diverge
+    allreduce = x -> reduce(addup, allgather(x))
     connect = (h, ent) -> begin
-      mine = Dict{Any,Any}(); for (en, e) in ent; mine[en.name] = (BDFCuda.ipc_export(h, e), hasFeatures(en) ? BDFCuda.ipc_export_beta(h, e) : UInt8[]); end
-      for q in 1:world; q == r || put!(boxes[q], (r, mine)); end
-      for k in 1:world-1
-        (q, theirs) = take!(boxes[r])
+      mine = Dict{Any,Any}()
+      for (en, e) in ent
+        mine[en.name] = (BDFCuda.ipc_export(h, e), hasFeatures(en) ? BDFCuda.ipc_export_beta(h, e) : UInt8[])
+      end
+      everyone = allgather(mine)
+      for q in 1:world
+        q == r && continue
         for (en, e) in ent
-          BDFCuda.ipc_import(h, e, q - 1, theirs[en.name][1])
-          isempty(theirs[en.name][2]) || BDFCuda.ipc_import_beta(h, e, q - 1, theirs[en.name][2])
+          BDFCuda.ipc_import(h, e, q - 1, everyone[q][en.name][1])
+          isempty(everyone[q][en.name][2]) || BDFCuda.ipc_import_beta(h, e, q - 1, everyone[q][en.name][2])
         end
       end
     end
-    allreduce = (N, NU, NS) -> begin
-      for q in 1:world; q == r || put!(boxes[q], (N, NU, NS)); end
-      for k in 1:world-1
-        (n2, nu2, ns2) = take!(boxes[r]); N += n2; NU += nu2; NS += ns2
-      end
-      (N, NU, NS)
-    end
-    Peers(r - 1, world, connect, allreduce)
+    Peers(r - 1, world, connect, allgather, allreduce)
   end
   refs = [@spawnat pids[r] macau_cuda(data; device = devices[r], rank = r - 1, world = world, peers = peers_for(r), kw...) for r in 2:world]
   result = macau_cuda(data; device = devices[1], rank = 0, world = world, peers = peers_for(1), kw...)
