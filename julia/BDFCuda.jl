@@ -35,7 +35,11 @@ function create(num_latent::Int; device::Int = 0, rank::Int = 0, world::Int = 1)
   return h
 end
 
-add_entity(h::Handle, count::Integer) = ccall((:bdf_add_entity, LIB), Cint, (Ptr{Void}, Int64), h.ptr, count)
+function add_entity(h::Handle, count::Integer)
+  e = ccall((:bdf_add_entity, LIB), Cint, (Ptr{Void}, Int64), h.ptr, count)
+  e >= 0 || check(h, e)
+  return e
+end
 
 ## FastIDF(rel.data) — ids is nnz x K Int64 (1-based), values Float64
 function add_relation(h::Handle, entities::Vector{Cint}, ids::Matrix{Int64}, values::Vector{Float64})
@@ -161,8 +165,11 @@ function sample_alpha!(h::Handle, rel, alpha_lambda0, alpha_nu0; chi2 = NaN)
 end
 
 ## an entity with an explicit (e.g. work-balanced) shard map instead of the cyclic i:Nprocs:N deal; rank_of_row is 0-based
-add_entity_partitioned(h::Handle, count::Integer, rank_of_row::Vector{Int32}) =
-  check(h, ccall((:bdf_add_entity_partitioned, LIB), Cint, (Ptr{Void}, Int64, Ptr{Int32}), h.ptr, count, rank_of_row))
+function add_entity_partitioned(h::Handle, count::Integer, rank_of_row::Vector{Int32})
+  e = ccall((:bdf_add_entity_partitioned, LIB), Cint, (Ptr{Void}, Int64, Ptr{Int32}), h.ptr, count, rank_of_row)
+  e >= 0 || check(h, e)
+  return e                                                  # the entity id, like add_entity
+end
 
 ## pred_all(r) — src/sampling.jl:92-97 (macau(full_prediction = true), src/macau.jl:145-146)
 function predict_all(h::Handle, rel, n1::Integer, n2::Integer)

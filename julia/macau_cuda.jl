@@ -29,7 +29,7 @@ function macau_cuda(data::RelationData;
   rid = Cint[]
   for r in data.relations
     f = FastIDF(r.data)                                   # ids::Matrix{Int64} (nnz x K, 1-based), values::Vector{Float64}
-    push!(rid, BDFCuda.add_relation(h, Cint[ent[en] for en in r.entities], f.ids, f.values))
+    push!(rid, BDFCuda.add_relation(h, Cint[ent[en] for en in r.entities], convert(Matrix{Int64}, f.ids), convert(Vector{Float64}, f.values)))
     BDFCuda.set_relation_params(h, rid[end], r.model.alpha, r.model.mean_value)
     hasFeatures(r) && BDFCuda.set_relation_features(h, rid[end], full(r.F))
   end
@@ -51,9 +51,9 @@ function macau_cuda(data::RelationData;
   # the test set goes to the device once; the running posterior mean, the sum of squares and the clamped RMSE of src/macau.jl:164-200 are
   # accumulated there (with several ranks: this rank's share rank+1:world:ntest, the sums are added up by the master)
   mine     = (rank + 1) : world : numTest(rel)
-  test_ids = convert(Matrix{Int64}, array(rel.test_vec[mine, 1:end-1]))
+  test_ids = convert(Matrix{Int64}, convert(Array, rel.test_vec[mine, 1:end-1]))   # the conversion FastIDF uses (src/IndexedDF.jl:53)
   if numTest(rel) > 0
-    BDFCuda.set_test(h, rid[1], test_ids, convert(Vector{Float64}, array(rel.test_vec[mine, end])), rel.class_cut,
+    BDFCuda.set_test(h, rid[1], test_ids, convert(Vector{Float64}, convert(Array, rel.test_vec[mine, end])), rel.class_cut,
                      test_F = hasFeatures(rel) ? full(rel.test_F)[mine, :] : C_NULL)
   end
   BDFCuda.set_async(h, true)
