@@ -1135,10 +1135,9 @@ extern "C" int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const 
   double* dz1 = z1 ? rhs + nR : nullptr;
   double* dz2 = z2 ? rhs + nR + nZ1 : nullptr;
   int* info = reinterpret_cast<int*>(rhs + nR + nZ1 + nZ2);
-  auto cleanup = [&]() {};
   if (z1) cudaMemcpyAsync(dz1, z1, sizeof(double) * nnz, cudaMemcpyHostToDevice, h->stream);
   if (z2) cudaMemcpyAsync(dz2, z2, sizeof(double) * nF, cudaMemcpyHostToDevice, h->stream);
-  if ((rc = bdf_relation_residuals(h, rel))) { cleanup(); return rc; }
+  if ((rc = bdf_relation_residuals(h, rel))) return rc;
   const uint32_t st = philox_stream(PHILOX_RELFEAT, 2u * (uint32_t)rel);
   relfeat_noise_kernel<<<grid_for(nnz), 256, 0, h->stream>>>(r.res, dz1, nnz, 1.0 / sqrt(r.alpha), h->seed, h->sweep, st);
   const double one = 1.0, zero = 0.0;
@@ -1156,7 +1155,6 @@ extern "C" int bdf_sample_beta_rel(bdf_t* h, int rel, double lambda_beta, const 
   rc = bdf_refresh_relation_offsets(h, rel);
   if (!rc && beta_out) cudaMemcpyAsync(beta_out, r.beta, sizeof(double) * nF, cudaMemcpyDeviceToHost, h->stream);
   cudaError_t ce = cudaStreamSynchronize(h->stream);
-  cleanup();
   if (rc) return rc;
   if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
   if (s0 != CUBLAS_STATUS_SUCCESS) FAIL(BDF_ERR_CUDA, "cublasDgemv failed");
@@ -1489,7 +1487,6 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   double* rhs = T + nT;
   double* E1d = E1 ? rhs + nR : nullptr;
   double* E2d = E2 ? rhs + nR + nT : nullptr;
-  auto cleanup = [&]() {};
   color_matrix_kernel<<<1, 256, 0, h->stream>>>(e.Lambda, D, h->scratch, Cm, h->err_flag);
   if (E1) cudaMemcpy2DAsync(E1d, sizeof(double) * ld, E1, sizeof(double) * D, sizeof(double) * D, (size_t)e.N, cudaMemcpyHostToDevice, h->stream);
   if (E2) cudaMemcpy2DAsync(E2d, sizeof(double) * ld, E2, sizeof(double) * D, sizeof(double) * D, (size_t)e.numF, cudaMemcpyHostToDevice, h->stream);
@@ -1505,7 +1502,7 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   colored_rows_kernel<<<grid_for(e.numF, 4), 128, smem, h->stream>>>(nullptr, nullptr, Cm, E2d, e.numF, ld, D, sqrt(lambda_beta), h->seed, h->sweep, s0 + 1, rhs, 1);
   h->launches += 3;
   cudaError_t ce = cudaGetLastError();
-  if (ce != cudaSuccess) { cleanup(); FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce)); }
+  if (ce != cudaSuccess) FAIL(BDF_ERR_CUDA, cudaGetErrorString(ce));
   if (e.use_ff) {  // use_ff: solve_full(entity.FF, Ft_y, lambda_beta), src/sampling.jl:303-304
     rc = solve_full_dev(h, e, rhs, e.beta, lambda_beta);
     if (iters_out) for (int d = 0; d < D; d++) iters_out[d] = 0;
@@ -1534,7 +1531,6 @@ int bdf_sample_beta(bdf_t* h, int entity, const double* mu, const double* Lambda
   if (!rc && beta_out) rc = download_colmajor(h, e.beta, e.numF, D, beta_out);
   if (!rc && rhs_out) rc = download_colmajor(h, rhs, e.numF, D, rhs_out);
   if (!rc) rc = bdf_check_err_flag(h); else cudaStreamSynchronize(h->stream);
-  cleanup();
   return rc;
 }
 
