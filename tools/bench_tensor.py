@@ -4,7 +4,6 @@ mode has 250k observations per row, so every one of its rows is split over ~31 C
 sweeps/s, per-mode kernel times and the row kernel's algorithmic FP64 rate and gather bandwidth (SURVEY §8d formulas, K=3)."""
 import json
 import sys
-import time
 
 import numpy as np
 import torch

@@ -1,8 +1,6 @@
 """Set up a synthetic BPMF problem and run a few device-resident half-sweeps (target for ncu)."""
 import sys
 
-import numpy as np
-
 sys.path.insert(0, ".")
 import bdf_b200
 from tools.quick_bench import synth

@@ -5,7 +5,6 @@ import sys
 import time
 
 import numpy as np
-import torch
 
 sys.path.insert(0, ".")
 import bdf_b200

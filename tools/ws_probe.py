@@ -2,8 +2,6 @@
 BDF_EXTRA_NVCC=-DBDF_DEBUG python bayesiandatafusion.jl_b200/build.py; run with BDF_B200_LIB=.../libbdf_dbg.so BDF_DEBUG_WS=1)."""
 import sys
 
-import numpy as np
-
 sys.path.insert(0, ".")
 import bdf_b200
 from tools.quick_bench import synth
