@@ -7,7 +7,7 @@
 // tiles) but few registers. So one persistent CTA per SM holds
 //   * NSG = 2 "syrk" groups of 4 warps at 128 registers: each streams work items off a global queue (heaviest first) — TMA gather ring →
 //     DMMA accumulate → (split rows: park/add up partials in global memory) → park Λ* into a free tile slot → signal → next item;
-//   * NFG = 3 "finalise" groups of 4 warps at 80 registers (setmaxnreg), each owning one 48 KB tile slot: wait for a parked row →
+//   * NFG = 3 "finalise" groups of 4 warps at 72 registers (setmaxnreg), each owning one 48 KB tile slot: wait for a parked row →
 //     blocked UL Cholesky → substitutions → store the draw (and into the peers) → free the slot.
 // i.e. 5 rows in flight per SM, two of them feeding the pipe. Hand-off is by shared-memory mbarriers (full[slot] / empty[slot]); each
 // group synchronises internally on its own named barrier. Slots are handed out round-robin by ticket; the ticket is taken and its slot
