@@ -305,3 +305,40 @@ def test_pred_identity():
     approx(out[0], (U[0][3] * U[1][1] * U[2][0]).sum() + 0.25)
     out2 = orc.pred(ids[:, :2], U[:2], -1.0)
     approx(out2[1], U[0][0] @ U[1][0] - 1.0)
+
+
+def test_restated_wishart_and_mvnormal_conventions_have_the_right_distribution():
+    """No reference test pins the Distributions.jl / PDMats.jl streams, so the restated conventions — Bartlett factor with
+    A[i,i] = sqrt(chi2(nu - i)), Z = chol_lower(T)·A, Lam = Z·Zᵀ; mu = mu_N + chol_lower(inv(Lam)/beta_N)·z — are at least pinned
+    DISTRIBUTIONALLY against an independent implementation (scipy.stats): a small nu makes the marginals sensitive to the order of the
+    chi-square degrees of freedom and to a lower/upper mix-up, which the moments at nu >> D are not."""
+    from scipy import stats
+
+    rng = np.random.default_rng(2024)
+    D, nu, kappa, n = 4, 5.0, 3.0, 12000
+    G = rng.standard_normal((D, D))
+    T = G @ G.T / D + 0.3 * np.eye(D)
+    T[0, 0] *= 6.0                                  # unequal scales: a permuted dof order would show in the diagonal marginals
+    T = (T + T.T) / 2
+    mu_N = rng.standard_normal(D)
+    Lam = np.empty((n, D, D))
+    q = np.empty(n)
+    for s in range(n):
+        A = orc.bartlett_factor(rng, D, nu)
+        mu, L = orc.nw_rand(mu_N, kappa, T, A, rng.standard_normal(D))
+        Lam[s] = L
+        q[s] = kappa * (mu - mu_N) @ L @ (mu - mu_N)   # ~ chi2(D) whatever Lam was
+    ref = stats.wishart(df=nu, scale=T).rvs(n, random_state=np.random.default_rng(7))
+    # first moment: E[Lam] = nu·T, element-wise within 5 standard errors (Var = nu (T_ij² + T_ii T_jj))
+    se = np.sqrt(nu * (T ** 2 + np.outer(np.diag(T), np.diag(T))) / n)
+    assert np.all(np.abs(Lam.mean(0) - nu * T) <= 5 * se)
+    # marginals against scipy's sampler: diagonal elements, one off-diagonal, log-determinant
+    for pick in (lambda M: M[:, 0, 0], lambda M: M[:, D - 1, D - 1], lambda M: M[:, 1, 1], lambda M: M[:, 2, 0],
+                 lambda M: np.linalg.slogdet(M)[1]):
+        assert stats.ks_2samp(pick(Lam), pick(ref)).pvalue > 1e-4
+    # Lam_ii / T_ii ~ chi2(nu) exactly, for every i (this is what fails if the dof run the wrong way along the diagonal)
+    for i in range(D):
+        assert stats.kstest(Lam[:, i, i] / T[i, i], stats.chi2(nu).cdf).pvalue > 1e-4
+    assert stats.kstest(q, stats.chi2(D).cdf).pvalue > 1e-4
+    # sample_alpha's 1×1 Wishart and sample_lambda_beta's Gamma are plain scalings of the injected chi-square / gamma variate
+    assert abs(orc.sample_alpha(2.0, 1.0, np.array([1.0, 2.0]), 3.0) - 3.0 / (0.5 + 5.0)) <= 1e-15
