@@ -275,7 +275,7 @@ def run_ours(args):
     traffic = None
     try:
         if D == 100 and args.scale == 1.0 and world == 1:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "row_kernel_r01_traffic.json")))["traffic_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "row_kernel_r02_traffic.json")))["traffic_bytes_per_launch"]
     except Exception:
         pass
     roofline = {
