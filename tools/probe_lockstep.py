@@ -1,3 +1,6 @@
+"""Lockstep check for the row kernel (needs a -DBDF_DEBUG library for the phase clocks): rows of equal length, 1, 2, 4 and 16 waves of
+592 rows (4 per SM) — does a wave whose four co-resident rows are all in the same phase cost more per row than a steady stream? Results in
+profiles/README.md ("Lockstep check")."""
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
