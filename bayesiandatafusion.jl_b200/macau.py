@@ -100,31 +100,6 @@ def macau(data: RelationData, num_latent: int = 10, lambda_beta: float = math.na
             eng.close()
 
 
-class _HostAccumulators:
-    """src/macau.jl:164-200 on the host, for engine objects without the device-side test set (test doubles passed as `engine=`)."""
-
-    def __init__(self, rel, clamp):
-        self.rel, self.clamp = rel, clamp
-        self.all = np.zeros(rel.numTest())
-        self.sq = np.zeros(rel.numTest())
-        self.counter = 0
-
-    def step(self, probe_rat, posterior):
-        if not posterior:
-            self.all = probe_rat
-        elif self.counter == 0:
-            self.all, self.sq, self.counter = probe_rat.copy(), probe_rat ** 2, 1
-        else:
-            self.all = (self.counter * self.all + probe_rat) / (self.counter + 1)
-            self.sq = self.sq + probe_rat ** 2
-            self.counter += 1
-        rel = self.rel
-        sse = float(np.sum((rel.test_values - makeClamped(self.all, self.clamp)) ** 2))
-        sse_s = float(np.sum((rel.test_values - makeClamped(probe_rat, self.clamp)) ** 2))
-        ok = float(np.sum(rel.test_label == (self.all < rel.class_cut)))
-        return sse, sse_s, ok, float(rel.numTest()), float(self.counter)
-
-
 def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, verbose, full_lambda_u, reset_model, compute_ff_size, tol,
                 output, output_beta, output_type, full_prediction, clamp, f, rmse_train, seed, host_noise):
     """The Gibbs loop of src/macau.jl:80-254 over one engine. `comm` is None on one GPU; with several GPUs every rank runs this loop on
@@ -170,16 +145,11 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
     if say:
         print("Sampling")
     ntest = rel.numTest()
-    dev_test = ntest > 0 and hasattr(eng, "predict_accumulate")
-    if dev_test:
-        # every rank registers its share of the test set (all ranks hold every factor row); the sums are all-reduced below
+    if ntest:
+        # the test set goes to the device once; every rank registers its share (all ranks hold every factor row), the sums are all-reduced below
         sl = slice(None) if comm is None else slice(comm.rank, None, comm.world)
         eng.set_test(r_id, rel.test_ids[sl], rel.test_values[sl], rel.test_F[sl] if rel.hasFeatures() else None, rel.class_cut)
-        host_acc = None
-    else:
-        host_acc = _HostAccumulators(rel, clamp) if ntest else None
-    if hasattr(eng, "set_async"):
-        eng.set_async(True)  # half-sweeps return once enqueued; a numeric failure surfaces at the next call that reads results back
+    eng.set_async(True)  # half-sweeps return once enqueued; a numeric failure surfaces at the next call that reads results back
     train_rat_all, train_counter = None, 0
     yhat_full = np.zeros(tuple(rel.data.dims), order="F") if full_prediction else None
     rmse_avg = roc_avg = err_avg = math.nan
@@ -205,8 +175,6 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
 
     def test_predictions():
         """(probe_rat_all, probe_stdev) in test-set order on the lead rank."""
-        if host_acc is not None:
-            return host_acc.all, host_acc.sq
         avg, sq = eng.get_test_predictions(r_id)
         if comm is None:
             return avg, sq
@@ -250,19 +218,16 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
             elif comm is not None:
                 comm.nw_stats(eng, e, uhat=False)       # device statistics, all-reduced over the ranks
                 N = float(en.count)
-            elif need_N or not hasattr(eng, "step_nw_stats"):
+            elif need_N:
                 N, NU, NS = eng.nw_stats(e)
             else:
                 eng.step_nw_stats(e)                    # the statistics stay on the device: the draw reads them there
                 N = float(en.count)
             A = bartlett_factor(host_noise, D, nu + N) if host_noise is not None else None
             z = host_noise.standard_normal(D) if host_noise is not None else None
-            if hasattr(eng, "nw_sample_async"):
-                # the draw is first needed by THIS entity's next half-sweep: it runs beside the next entity's row kernel
-                eng.nw_sample_async(e, mj.mu0, mj.b0, Tinv, nu, A, z)
-                pending[e] = mj
-            else:
-                mj.mu, mj.Lambda = eng.nw_sample(e, mj.mu0, mj.b0, Tinv, nu, A, z)
+            # the draw is first needed by THIS entity's next half-sweep: it runs beside the next entity's row kernel
+            eng.nw_sample_async(e, mj.mu0, mj.b0, Tinv, nu, A, z)
+            pending[e] = mj
         # update_beta! needs this iteration's (mu, Lambda) of the entities with features on the host
         for e, en in zip(ents, data.entities):
             if en.hasFeatures():
@@ -283,13 +248,9 @@ def _macau_loop(data, eng, comm, *, num_latent, lambda_beta, burnin, psamples, v
 
         posterior = i > burnin
         if ntest:
-            if dev_test:
-                sums = eng.predict_accumulate(r_id, posterior, clamp)
-                if comm is not None:
-                    sums = comm.allreduce_scalars(list(sums[:4])) + [sums[4]]
-            else:
-                probe_rat = eng.predict(r_id, rel.test_ids, rel.test_F if rel.hasFeatures() else None)
-                sums = host_acc.step(probe_rat, posterior)
+            sums = eng.predict_accumulate(r_id, posterior, clamp)   # running mean, sum of squares, clamped errors: on the device
+            if comm is not None:
+                sums = comm.allreduce_scalars(list(sums[:4])) + [sums[4]]
             rmse_avg = math.sqrt(sums[0] / sums[3])   # src/macau.jl:196
             err_avg = sums[2] / sums[3]                # :193-194
         if say or (callable(f) and posterior) or i == burnin + psamples:

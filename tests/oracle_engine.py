@@ -84,6 +84,51 @@ class OracleEngine:
         zz = self.rng.standard_normal(self.D) if z is None else z
         return orc.nw_rand(mu_N, beta_N, T_N, A, zz)
 
+    # ---- the deferred / device-resident forms the product loop uses (here they simply run at once on the host) ---------------------
+    def set_async(self, on=True):
+        pass
+
+    def step_nw_stats(self, e):
+        self.nw_stats(e)
+
+    def nw_sample_async(self, e, mu0, b0, Tinv, nu, bartlettA=None, z=None):
+        self._draws = getattr(self, "_draws", {})
+        self._draws[e] = self.nw_sample(e, mu0, b0, Tinv, nu, bartlettA, z)
+
+    def nw_sample_fetch(self, e):
+        return self._draws.pop(e)
+
+    # ---- test set and posterior accumulators (bdf_set_test / bdf_predict_accumulate / bdf_get_test_predictions): src/macau.jl:143-200 ----
+    def set_test(self, rel, ids, vals, test_F=None, class_cut=0.0):
+        self._test = getattr(self, "_test", {})
+        n = len(vals)
+        self._test[rel] = {"ids": np.asarray(ids), "vals": np.asarray(vals, dtype=np.float64), "F": test_F, "cut": class_cut,
+                           "all": np.zeros(n), "sq": np.zeros(n), "counter": 0}
+
+    def predict_accumulate(self, rel, posterior, clamp=()):
+        t = self._test[rel]
+        probe_rat = self.predict(rel, t["ids"], t["F"])
+        if not posterior:
+            t["all"] = probe_rat
+        elif t["counter"] == 0:
+            t["all"], t["sq"], t["counter"] = probe_rat.copy(), probe_rat ** 2, 1
+        else:
+            t["all"] = (t["counter"] * t["all"] + probe_rat) / (t["counter"] + 1)
+            t["sq"] = t["sq"] + probe_rat ** 2
+            t["counter"] += 1
+
+        def clamped(x):  # makeClamped, src/sampling.jl:99-106
+            return np.clip(x, clamp[0], clamp[1]) if clamp is not None and len(clamp) else x
+
+        sse = float(np.sum((t["vals"] - clamped(t["all"])) ** 2))
+        sse_s = float(np.sum((t["vals"] - clamped(probe_rat)) ** 2))
+        ok = float(np.sum((t["vals"] < t["cut"]) == (t["all"] < t["cut"])))
+        return sse, sse_s, ok, float(len(t["vals"])), float(t["counter"])
+
+    def get_test_predictions(self, rel, want_last=False):
+        t = self._test[rel]
+        return t["all"], t["sq"]
+
     def train_sse(self, rel):
         ents, ids, vals = self.rels[rel]
         err = orc.pred(ids, [self.U[k] for k in ents], self.mean[rel]) - vals
