@@ -33,6 +33,7 @@ class Engine:
         self.rank, self.world = rank, world
         self.counts = []
         self.rel_modes = []
+        self.numF, self.rel_nF, self.ntest = {}, {}, {}   # feature columns per entity / per relation, registered test entries per relation
         h = C.c_void_p()
         rc = self.lib.bdf_create(C.byref(h), device, num_latent, rank, world)
         if rc:
@@ -196,7 +197,6 @@ class Engine:
         vals = _f64(vals)
         Fd = np.asfortranarray(test_F, dtype=np.float64) if test_F is not None else None
         self._ck(self.lib.bdf_set_test(self.h, rel, C.c_int64(ids.shape[0]), ids.ctypes.data_as(_lib.c_i64p), _dp(vals), _dp(Fd), float(class_cut)))
-        self.ntest = getattr(self, "ntest", {})
         self.ntest[rel] = int(ids.shape[0])
 
     def test_reset(self, rel: int):
@@ -257,7 +257,6 @@ class Engine:
             Fd = np.asfortranarray(F, dtype=np.float64)
             m, n = Fd.shape
             self._ck(self.lib.bdf_set_features_dense(self.h, entity, m, n, _dp(Fd)))
-            self.numF = getattr(self, "numF", {})
             self.numF[entity] = int(n)
             return
         if hasattr(F, "rows") and hasattr(F, "cols"):
@@ -272,7 +271,6 @@ class Engine:
                 nzval = np.ascontiguousarray(csc.data, dtype=np.float64)
                 m, n = F.shape
                 self._ck(self.lib.bdf_set_features_csc(self.h, entity, m, n, colptr.ctypes.data_as(_lib.c_i64p), rowval.ctypes.data_as(_lib.c_i64p), _dp(nzval)))
-                self.numF = getattr(self, "numF", {})
                 self.numF[entity] = int(n)
                 return
             coo = csc.tocoo()
@@ -282,7 +280,6 @@ class Engine:
         if len(rows) != len(cols):
             raise ValueError("DimensionMismatch: length(rows) must equal length(cols)")  # src/parallel_matrix.jl:20
         self._ck(self.lib.bdf_set_features_sbm(self.h, entity, m, n, len(rows), rows.ctypes.data_as(_lib.c_i32p), cols.ctypes.data_as(_lib.c_i32p)))
-        self.numF = getattr(self, "numF", {})
         self.numF[entity] = int(n)
 
     def compute_ff(self, entity: int, want: bool = False):
@@ -416,7 +413,6 @@ class Engine:
         """Relation.F (nnz × nF, rows in the order of the table given to add_relation); FF = F'F, beta = 0 on the device."""
         Fd = np.asfortranarray(F, dtype=np.float64)
         self._ck(self.lib.bdf_set_relation_features(self.h, rel, Fd.shape[0], Fd.shape[1], _dp(Fd)))
-        self.rel_nF = getattr(self, "rel_nF", {})
         self.rel_nF[rel] = int(Fd.shape[1])
 
     def sample_beta_rel(self, rel: int, lambda_beta: float, z1=None, z2=None):
