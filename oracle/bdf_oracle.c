@@ -20,7 +20,9 @@
  * test/parallel_latent_basic.jl), and (b) a numpy/scipy twin (oracle/oracle.py) that calls
  * the SAME LAPACK routines Julia Base calls (dgetrf/dgetri/dpotrf). The Wishart / MvNormal /
  * Gamma streams of Distributions.jl are NOT pinned by any reference test ("parity unpinned"
- * for those draws): all randomness is injected as standard variates.
+ * for those draws): all randomness is injected as standard variates, and the restated
+ * conventions (Bartlett factor, chol_lower colouring) are checked as DISTRIBUTIONS against
+ * scipy.stats (tests/test_oracle.py), which is as far as they can be pinned without Julia.
  *
  * All matrices are column-major double. Index arrays that cross this interface are 1-based
  * exactly as Julia holds them.
