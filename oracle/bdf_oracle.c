@@ -16,8 +16,8 @@
  *
  * Parity pinning: Julia is not installable here, so the reference itself cannot run.
  * The restatement is pinned by (a) the reference's own known-answer fixtures
- * (test/sparsebin_csr.jl, test/parallel_matrix.jl, test/solver.jl, test/basic.jl,
- * test/parallel_latent_basic.jl), and (b) a numpy/scipy twin (oracle/oracle.py) that calls
+ * (test/sparsebin_csr.jl, test/sparse_csr.jl, test/parallel_matrix.jl, test/solver.jl,
+ * test/basic.jl, test/parallel_latent_basic.jl), and (b) a numpy/scipy twin (oracle/oracle.py) that calls
  * the SAME LAPACK routines Julia Base calls (dgetrf/dgetri/dpotrf). The Wishart / MvNormal /
  * Gamma streams of Distributions.jl are NOT pinned by any reference test ("parity unpinned"
  * for those draws): all randomness is injected as standard variates, and the restated

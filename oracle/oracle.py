@@ -291,6 +291,48 @@ def csr_mul(m, row_ptr, col_ind, x):
     return y
 
 
+def csc_from_triplets(rows, cols, vals, m=None, n=None):
+    """Julia's sparse(rows, cols, vals) (1-based triplets; duplicates are added, entries sorted by row inside a column) as the fields of a
+    SparseMatrixCSC: (m, n, colptr, rowval, nzval), 1-based. [ext: Julia Base]"""
+    rows, cols, vals = np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64), _f64(vals)
+    m = int(rows.max()) if m is None else m
+    n = int(cols.max()) if n is None else n
+    order = np.lexsort((rows, cols))
+    r, c, v = rows[order], cols[order], vals[order]
+    keep = np.ones(len(r), dtype=bool)
+    keep[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
+    starts = np.flatnonzero(keep)
+    nz = np.add.reduceat(v, starts) if len(v) else v
+    r, c = r[starts], c[starts]
+    colptr = np.ones(n + 1, dtype=np.int64)
+    np.add.at(colptr, c, 1)          # colptr[j+1] counts column j (1-based c → index c)
+    colptr = np.cumsum(colptr) - np.arange(n + 1)
+    return m, n, colptr, r, nz
+
+
+def csc_mul(m, n, colptr, rowval, nzval, x):
+    """A * x for a SparseMatrixCSC (Julia Base A_mul_B!: column by column, y[rowval[k]] += nzval[k]*x[j]) [ext]. This is what
+    `At_mul_B(::SparseMatrixCSR, u)` runs on the stored transpose (src/parallel_csr.jl:41-42)."""
+    y = np.zeros(m)
+    for j in range(n):
+        xj = x[j]
+        for k in range(colptr[j] - 1, colptr[j + 1] - 1):
+            y[rowval[k] - 1] += nzval[k] * xj
+    return y
+
+
+def csc_tmul(m, n, colptr, rowval, nzval, x):
+    """At_mul_B(A, x) for a SparseMatrixCSC (Julia Base: y[j] = sum_k nzval[k]*x[rowval[k]] in stored order) [ext]. This is what
+    `*(::SparseMatrixCSR, u)` runs on the stored transpose (src/parallel_csr.jl:43) — a row-wise CSR product."""
+    y = np.zeros(n)
+    for j in range(n):
+        s = 0.0
+        for k in range(colptr[j] - 1, colptr[j + 1] - 1):
+            s += nzval[k] * x[rowval[k] - 1]
+        y[j] = s
+    return y
+
+
 def sbm_ata_mul(m, n, rows, cols, x, lam):
     rows, cols, x = _i32(rows), _i32(cols), _f64(x)
     y = np.zeros(n)

@@ -342,3 +342,36 @@ def test_restated_wishart_and_mvnormal_conventions_have_the_right_distribution()
     assert stats.kstest(q, stats.chi2(D).cdf).pvalue > 1e-4
     # sample_alpha's 1×1 Wishart and sample_lambda_beta's Gamma are plain scalings of the injected chi-square / gamma variate
     assert abs(orc.sample_alpha(2.0, 1.0, np.array([1.0, 2.0]), 3.0) - 3.0 / (0.5 + 5.0)) <= 1e-15
+
+
+def test_sparse_csr_wrapper_known_answers():
+    """test/sparse_csr.jl:4-34 — SparseMatrixCSR (src/parallel_csr.jl:36-54) stores the CSC of the transpose; `Xr*y` is the row-wise product
+    on it, `At_mul_B(Xr, y)` the column-wise one; both equal the products of the original matrix, as does the 4-entry triplet fixture."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(12)
+    X = sp.random(50, 100, 0.1, random_state=3, format="coo")             # sprand(50, 100, 0.1)
+    r, c, v = X.row + 1, X.col + 1, X.data
+    mt, nt, colptr, rowval, nzval = orc.csc_from_triplets(c, r, v, m=100, n=50)   # sparse_csr(X) = SparseMatrixCSR(X')
+    assert (nt, mt) == X.shape                                             # size(Xr) == size(X): (n, m) of the stored transpose
+    y1, y2 = rng.random(100), rng.random(50)
+    Xd = X.toarray()
+    approx(orc.csc_tmul(mt, nt, colptr, rowval, nzval, y1), Xd @ y1)       # Xr * y1
+    approx(orc.csc_mul(mt, nt, colptr, rowval, nzval, y2), Xd.T @ y2)      # At_mul_B(Xr, y2) == Ac_mul_B(Xr, y2)
+    # the products are also bit-identical to scipy's CSR / CSC kernels, which accumulate in the same (stored) order — the reason the
+    # GPU test of general sparse features can compare against scipy bit for bit
+    Xcsc = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(mt, nt))
+    assert np.array_equal(orc.csc_mul(mt, nt, colptr, rowval, nzval, y2), Xcsc @ y2)
+    assert np.array_equal(orc.csc_tmul(mt, nt, colptr, rowval, nzval, y1), sp.csr_matrix(Xcsc.T) @ y1)
+    # At_mul_B(Xr, Xr) == At_mul_B(X, X)
+    approx((Xcsc @ Xcsc.T).toarray(), Xd.T @ Xd)
+    # rows = [1, 2, 2, 4]; cols = [2, 1, 3, 3]; vals = [0.1, 0.2, 0.15, 0.3]: sparse(rows, cols, vals) * z == sparse_csr(rows, cols, vals) * z
+    rows, cols, vals = [1, 2, 2, 4], [2, 1, 3, 3], [0.1, 0.2, 0.15, 0.3]
+    z = rng.random(3)
+    m1, n1, cp1, rv1, nz1 = orc.csc_from_triplets(rows, cols, vals)        # sparse(rows, cols, vals): 4 x 3
+    m2, n2, cp2, rv2, nz2 = orc.csc_from_triplets(cols, rows, vals)        # sparse_csr: SparseMatrixCSR(sparse(cols, rows, vals)): 3 x 4 stored
+    assert (m1, n1, m2, n2) == (4, 3, 3, 4)
+    w1 = orc.csc_mul(m1, n1, cp1, rv1, nz1, z)
+    w2 = orc.csc_tmul(m2, n2, cp2, rv2, nz2, z)
+    approx(w1, w2)
+    approx(w1, np.array([0.1 * z[1], 0.2 * z[0] + 0.15 * z[2], 0.0, 0.3 * z[2]]))
